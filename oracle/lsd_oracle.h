@@ -1,0 +1,185 @@
+/*
+ * lsd_oracle.h -- CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A plain-C, Eigen-free restatement of the two LSD-SLAM hot paths
+ *   SE3Tracker::trackFrame            lsd_slam_core/src/Tracking/SE3Tracker.cpp:280-486
+ *   DepthMap::updateKeyframe          lsd_slam_core/src/DepthEstimation/DepthMap.cpp:1072-1213
+ *   DepthMap::createKeyFrame          lsd_slam_core/src/DepthEstimation/DepthMap.cpp:1222-1327
+ * and of everything below them (Frame builders, TrackingReference point cloud,
+ * Sophus SE3 exp / product / inverse, 6x6 LDLT).  Each function cites the
+ * reference file:line it follows.
+ *
+ * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
+ * this path and cannot be compiled in this image (Eigen,
+ * Boost, OpenCV C++, g2o, ROS are absent), so this restatement is checked only
+ * against (a) the property tests the vendored Sophus test-suite states
+ * (thirdparty/Sophus/sophus/test_se3.cpp:38-60, tests.hpp:70-133) and (b) its
+ * own self-consistency KATs (tests/test_oracle_*.py).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.  The product (lsd_slam_b200/) never does.
+ *
+ * Third-party arithmetic restated here because its source is not vendored:
+ *   Eigen 3.x (unpinned: find_package(Eigen3 REQUIRED), lsd_slam_core/CMakeLists.txt:19)
+ *   - 3x3 inverse by cofactors (Eigen/src/LU/Inverse.h compute_inverse_size3)
+ *   - Quaternion product / toRotationMatrix / _transformVector (Eigen/src/Geometry/Quaternion.h)
+ *   - LDLT with diagonal pivoting (Eigen/src/Cholesky/LDLT.h, unblocked)
+ *   - fixed-size 3x3*3x1 products evaluated coefficient-wise, left to right.
+ */
+#ifndef LSD_ORACLE_H
+#define LSD_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSDO_LEVELS 5           /* PYRAMID_LEVELS, util/settings.h:106 */
+
+/* DepthMapPixelHypothesis, DepthEstimation/DepthMapPixelHypothesis.h:37-61 (sizeof == 32) */
+typedef struct {
+    uint8_t isValid;
+    uint8_t _pad[3];
+    int32_t blacklisted;
+    float   nextStereoFrameMinID;
+    int32_t validity_counter;
+    float   idepth;
+    float   idepth_var;
+    float   idepth_smoothed;
+    float   idepth_var_smoothed;
+} lsdo_hyp;
+
+/* global runtime flags, util/settings.cpp:77-88 */
+typedef struct {
+    float minUseGrad;                 /* 5   */
+    float cameraPixelNoise2;          /* 16  */
+    float depthSmoothingFactor;       /* 1   */
+    int   allowNegativeIdepths;       /* 1   */
+    int   useSubpixelStereo;          /* 1   */
+    int   useAffineLightningEstimation; /* 1 (settings.cpp:88); cfg/LSDParams.cfg:28 sets 0 under ROS */
+    int   multiThreading;             /* 1: DepthMap row ranges on MAPPING_THREADS=4 workers */
+    int   useSSE;                     /* 0: scalar parity path; 1: the reference's SSE loops (timing flavour) */
+} lsdo_globals;
+
+/* DenseDepthTrackerSettings, util/settings.h:355-402 */
+typedef struct {
+    float lambdaSuccessFac, lambdaFailFac;
+    float lambdaInitial[LSDO_LEVELS];
+    float stepSizeMin[LSDO_LEVELS];
+    float convergenceEps[LSDO_LEVELS];
+    int   maxItsPerLvl[LSDO_LEVELS];
+    float huber_d, var_weight;
+} lsdo_track_settings;
+
+/* everything SlamSystem reads back from the tracker, Tracking/SE3Tracker.h:82-93 */
+typedef struct {
+    double frameToRef_qt[7];          /* (qx,qy,qz,qw, tx,ty,tz) */
+    float  pointUsage, lastGoodCount, lastBadCount, lastMeanRes, lastResidual;
+    float  affineEstimation_a, affineEstimation_b;
+    int    diverged, trackingWasGood;
+    int    numCalcResidualCalls[LSDO_LEVELS];
+    int    numCalcWarpUpdateCalls[LSDO_LEVELS];
+    float  initialTrackedResidual;    /* frame->initialTrackedResidual, SE3Tracker.cpp:482 */
+} lsdo_track_result;
+
+/* one fused evaluation: calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate */
+typedef struct {
+    float A[36];                      /* row-major 6x6, divided by num_constraints (LGSX.h:319-325) */
+    float b[6];
+    float lsError;                    /* LGS6::error after finish */
+    float meanWeightedRes;            /* return value of calcWeightsAndResidual */
+    float meanUnweightedRes;          /* return value of calcResidualAndBuffers */
+    int   warpedSize;                 /* buf_warped_size */
+    float pointUsage, goodCount, badCount, meanRes;
+    float affine_a_lastIt, affine_b_lastIt;
+    float sxx, syy, sx, sy, sw;
+} lsdo_eval_result;
+
+typedef struct lsdo_frame lsdo_frame;
+typedef struct lsdo_depthmap lsdo_depthmap;
+
+void lsdo_default_globals(lsdo_globals* g);
+void lsdo_set_globals(const lsdo_globals* g);
+void lsdo_get_globals(lsdo_globals* g);
+void lsdo_default_track_settings(lsdo_track_settings* s);
+
+/* ---- SE3 / Sim3 host math (thirdparty/Sophus/sophus/se3.hpp, so3.hpp) ---- */
+void lsdo_se3d_exp(const double a[6], double qt[7]);
+void lsdo_se3d_mul(const double a[7], const double b[7], double out[7]);
+void lsdo_se3d_inverse(const double a[7], double out[7]);
+void lsdo_se3d_matrix(const double a[7], double R[9], double t[3]);
+void lsdo_se3f_exp(const float a[6], float qt[7]);
+void lsdo_se3f_mul(const float a[7], const float b[7], float out[7]);
+void lsdo_se3f_inverse(const float a[7], float out[7]);
+void lsdo_se3f_matrix(const float a[7], float R[9], float t[3]);
+void lsdo_se3d_log(const double a[7], double out[6]);
+int  lsdo_ldlt6_solve(const float A[36], const float b[6], float x[6]);
+void lsdo_mat3_inverse(const float K[9], float Kinv[9]);
+
+/* ---- Frame (DataStructures/Frame.{h,cpp}) ---- */
+lsdo_frame* lsdo_frame_create_u8(int id, int w, int h, const float K[9], const uint8_t* image);
+void  lsdo_frame_destroy(lsdo_frame* f);
+int   lsdo_frame_id(const lsdo_frame* f);
+int   lsdo_frame_width(const lsdo_frame* f, int level);
+int   lsdo_frame_height(const lsdo_frame* f, int level);
+const float* lsdo_frame_image(lsdo_frame* f, int level);
+const float* lsdo_frame_gradients(lsdo_frame* f, int level);      /* 4 floats / px */
+const float* lsdo_frame_maxGradients(lsdo_frame* f, int level);
+const float* lsdo_frame_idepth(lsdo_frame* f, int level);
+const float* lsdo_frame_idepthVar(lsdo_frame* f, int level);
+void  lsdo_frame_K(const lsdo_frame* f, int level, float K[9], float Kinv[9]);
+uint8_t* lsdo_frame_refPixelWasGood(lsdo_frame* f);                /* creates (all true) */
+uint8_t* lsdo_frame_refPixelWasGoodNoCreate(lsdo_frame* f);
+void  lsdo_frame_clear_refPixelWasGood(lsdo_frame* f);
+void  lsdo_frame_setDepthFromGroundTruth(lsdo_frame* f, const float* depth, float cov_scale);
+void  lsdo_frame_setDepth(lsdo_frame* f, const lsdo_hyp* newDepth);
+int   lsdo_frame_numMappablePixels(lsdo_frame* f);
+float lsdo_frame_meanIdepth(const lsdo_frame* f);
+int   lsdo_frame_numPoints(const lsdo_frame* f);
+int   lsdo_frame_depthHasBeenUpdatedFlag(const lsdo_frame* f);
+void  lsdo_frame_set_depthHasBeenUpdatedFlag(lsdo_frame* f, int v);
+float lsdo_frame_initialTrackedResidual(const lsdo_frame* f);
+void  lsdo_frame_get_thisToParent(const lsdo_frame* f, double qts[8]);  /* Sim3: q(4) t(3) s */
+void  lsdo_frame_set_thisToParent(lsdo_frame* f, const double qts[8], lsdo_frame* parent);
+int   lsdo_frame_numFramesTrackedOnThis(const lsdo_frame* f);
+int   lsdo_frame_numMappedOnThis(const lsdo_frame* f);
+void  lsdo_frame_set_counters(lsdo_frame* f, int tracked, int mapped);
+
+/* ---- TrackingReference point cloud (Tracking/TrackingReference.cpp:96-147) ---- */
+/* returns numData[level]; out arrays sized w_l*h_l by the caller (NULL = skip) */
+int lsdo_make_point_cloud(lsdo_frame* kf, int level, float* posData /*3/pt*/, float* gradData /*2/pt*/,
+                          float* colorAndVarData /*2/pt*/, int* pointPosInXYGrid);
+
+/* ---- SE3Tracker (Tracking/SE3Tracker.cpp) ---- */
+int lsdo_se3_eval(lsdo_frame* kf, lsdo_frame* frame, int level, const float refToFrame_qt[7],
+                  float affine_a, float affine_b, const lsdo_track_settings* s,
+                  int writeGoodMask, lsdo_eval_result* out);
+int lsdo_se3_track(lsdo_frame* kf, lsdo_frame* frame, const double frameToRef_init_qt[7],
+                   const lsdo_track_settings* s, lsdo_track_result* out);
+
+/* ---- DepthMap (DepthEstimation/DepthMap.cpp) ---- */
+lsdo_depthmap* lsdo_depthmap_create(int w, int h, const float K[9]);
+void lsdo_depthmap_destroy(lsdo_depthmap* d);
+void lsdo_depthmap_reset(lsdo_depthmap* d);
+void lsdo_depthmap_initializeFromGTDepth(lsdo_depthmap* d, lsdo_frame* f);
+void lsdo_depthmap_initializeRandomly(lsdo_depthmap* d, lsdo_frame* f);
+void lsdo_depthmap_updateKeyframe(lsdo_depthmap* d, lsdo_frame** refs, int n_refs);
+void lsdo_depthmap_createKeyFrame(lsdo_depthmap* d, lsdo_frame* new_kf);
+void lsdo_depthmap_finalizeKeyFrame(lsdo_depthmap* d);
+const lsdo_hyp* lsdo_depthmap_current(const lsdo_depthmap* d);
+void lsdo_depthmap_set_current(lsdo_depthmap* d, const lsdo_hyp* h);
+const int* lsdo_depthmap_integral(const lsdo_depthmap* d);
+lsdo_frame* lsdo_depthmap_activeKeyFrame(lsdo_depthmap* d);
+/* individual passes, for per-kernel parity tests */
+void lsdo_depthmap_observeDepth(lsdo_depthmap* d, lsdo_frame** refs, int n_refs);
+void lsdo_depthmap_regularizeFillHoles(lsdo_depthmap* d);
+void lsdo_depthmap_regularize(lsdo_depthmap* d, int removeOcclusions, int validityTH);
+void lsdo_depthmap_propagateDepth(lsdo_depthmap* d, lsdo_frame* new_kf);
+/* per-stage EMA timers of the reference (DepthMap.cpp:1126-1162), ms of the last call */
+void lsdo_depthmap_last_timings(const lsdo_depthmap* d, float out_ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
