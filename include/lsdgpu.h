@@ -1,0 +1,187 @@
+/*
+ * lsdgpu.h -- C ABI of the B200-native LSD-SLAM hot path (liblsdgpu.so).
+ *
+ * The reference has no plugin / FFI layer: the seam is three public C++ methods
+ *     SE3  SE3Tracker::trackFrame(TrackingReference*, Frame*, const SE3&)    Tracking/SE3Tracker.h:65-68
+ *     void DepthMap::updateKeyframe(std::deque<std::shared_ptr<Frame>>)      DepthEstimation/DepthMap.h:58
+ *     void DepthMap::createKeyFrame(Frame*)                                  DepthEstimation/DepthMap.h:63
+ * plus the state-touching siblings of DepthMap and the Frame builders below them.  Every entry point
+ * here names the reference interface it replaces (paths relative to lsd_slam_core/src/).  The C++
+ * adapter classes in lsd_slam_b200/host/ keep the reference's method names on top of this ABI;
+ * INTEGRATION.md shows the binding a maintainer adds to lsd_slam_core.
+ *
+ * Conventions: extern "C", POD only, caller-owned HOST buffers, opaque context, int return
+ * (0 = ok, negative = error, text via lsdgpu_last_error), never throws.  One context owns one CUDA
+ * stream and all device state of one SlamSystem (one tracker + one depth map); contexts are independent
+ * and thread-compatible (SlamSystem runs tracking and mapping on different threads: calls into ONE
+ * context must be serialised by the caller, or use two contexts' worth of locking as the adapter does).
+ *
+ * Poses: SE3 as double qt[7] = (qx,qy,qz,qw, tx,ty,tz) (Eigen coefficient order of Sophus::SE3d);
+ *        Sim3 as double qts[8] = qt[7] + scale.
+ */
+#ifndef LSDGPU_H
+#define LSDGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSDGPU_LEVELS 5                 /* PYRAMID_LEVELS, util/settings.h:106 */
+#define LSDGPU_ABI_VERSION 1
+
+typedef struct lsdgpu_ctx lsdgpu_ctx;
+
+/* DepthMapPixelHypothesis, DepthEstimation/DepthMapPixelHypothesis.h:37-61 (sizeof == 32, same field order) */
+typedef struct {
+    uint8_t isValid;
+    uint8_t _pad[3];
+    int32_t blacklisted;
+    float   nextStereoFrameMinID;
+    int32_t validity_counter;
+    float   idepth;
+    float   idepth_var;
+    float   idepth_smoothed;
+    float   idepth_var_smoothed;
+} lsdgpu_hyp;
+
+/* run-time globals of util/settings.cpp:77-88 that the path reads */
+typedef struct {
+    float minUseGrad;                   /* 5  */
+    float cameraPixelNoise2;            /* 16 */
+    float depthSmoothingFactor;         /* 1  */
+    int   allowNegativeIdepths;         /* 1  */
+    int   useSubpixelStereo;            /* 1  */
+    int   useAffineLightningEstimation; /* 1 (settings.cpp:88; cfg/LSDParams.cfg:28 sets 0 under ROS) */
+} lsdgpu_globals;
+
+/* DenseDepthTrackerSettings, util/settings.h:355-402 (the fields trackFrame reads) */
+typedef struct {
+    float lambdaSuccessFac, lambdaFailFac;
+    float lambdaInitial[LSDGPU_LEVELS];
+    float stepSizeMin[LSDGPU_LEVELS];
+    float convergenceEps[LSDGPU_LEVELS];
+    int   maxItsPerLvl[LSDGPU_LEVELS];
+    float huber_d, var_weight;
+} lsdgpu_track_settings;
+
+/* public fields of SE3Tracker after trackFrame, Tracking/SE3Tracker.h:82-93 + the Frame side effects */
+typedef struct {
+    double frameToRef_qt[7];            /* return value of trackFrame (identity when diverged) */
+    float  pointUsage, lastGoodCount, lastBadCount, lastMeanRes, lastResidual;
+    float  affineEstimation_a, affineEstimation_b;
+    int    diverged, trackingWasGood;
+    int    numCalcResidualCalls[LSDGPU_LEVELS];
+    int    numCalcWarpUpdateCalls[LSDGPU_LEVELS];
+    float  initialTrackedResidual;      /* frame->initialTrackedResidual, SE3Tracker.cpp:482 */
+} lsdgpu_track_result;
+
+/* one fused evaluation = calcResidualAndBuffers + calcWeightsAndResidual + calculateWarpUpdate
+ * (SE3Tracker.cpp:885-1029, 749-790, 1258-1299 + LGS6, LGSX.h:184-402) at a given pose */
+typedef struct {
+    float A[36];                        /* row-major, normalised by num_constraints like LGS6::finish */
+    float b[6];
+    float lsError;
+    float meanWeightedRes;              /* calcWeightsAndResidual return value */
+    float meanUnweightedRes;            /* calcResidualAndBuffers return value */
+    int   warpedSize;                   /* buf_warped_size */
+    float pointUsage, goodCount, badCount, meanRes;
+    float affine_a_lastIt, affine_b_lastIt;
+    float sxx, syy, sx, sy, sw;
+} lsdgpu_eval_result;
+
+/* what lsdgpu_frame_download can fetch (parity hooks for the Frame builders) */
+enum {
+    LSDGPU_BUF_IMAGE = 0,               /* Frame::image(level),        float  w_l*h_l            */
+    LSDGPU_BUF_GRADIENTS = 1,           /* Frame::gradients(level),    float4 w_l*h_l (dx,dy,I,0) */
+    LSDGPU_BUF_MAXGRAD = 2,             /* Frame::maxGradients(0),     float  w*h  (level 0 only) */
+    LSDGPU_BUF_IDEPTH = 3,              /* Frame::idepth(level)                                   */
+    LSDGPU_BUF_IDEPTH_VAR = 4,          /* Frame::idepthVar(level)                                */
+    LSDGPU_BUF_GOODMASK = 5             /* Frame::refPixelWasGood(), uint8 w_1*h_1                */
+};
+
+/* ---- context ------------------------------------------------------------------------------------ */
+/* replaces SE3Tracker::SE3Tracker(w,h,K) Tracking/SE3Tracker.cpp:46-94 and DepthMap::DepthMap(w,h,K)
+ * DepthEstimation/DepthMap.cpp:41-83.  max_frames = number of frame slots resident in HBM. */
+int  lsdgpu_create(int device, int width, int height, const float K[9], int max_frames, lsdgpu_ctx** out);
+void lsdgpu_destroy(lsdgpu_ctx* ctx);
+const char* lsdgpu_last_error(const lsdgpu_ctx* ctx);
+int  lsdgpu_abi_version(void);
+int  lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g);      /* util/settings.cpp:77-88 */
+void lsdgpu_default_globals(lsdgpu_globals* g);
+void lsdgpu_default_track_settings(lsdgpu_track_settings* s);            /* util/settings.h:358-386 */
+int  lsdgpu_synchronize(lsdgpu_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches claim) */
+long long lsdgpu_launch_count(const lsdgpu_ctx* ctx);
+/* CUDA-event timers on the context's stream (bench.py: roofline / per-stage times) */
+int  lsdgpu_timer_begin(lsdgpu_ctx* ctx, int slot);
+int  lsdgpu_timer_end(lsdgpu_ctx* ctx, int slot);
+int  lsdgpu_timer_elapsed_ms(lsdgpu_ctx* ctx, int slot, float* ms);      /* synchronises on the end event */
+/* accumulated device time (ms) and launch count of the warp/residual kernel since the last reset */
+int  lsdgpu_track_kernel_stats(lsdgpu_ctx* ctx, int reset, double* ms, long long* launches, double* algorithmic_bytes);
+
+/* ---- Frame: DataStructures/Frame.{h,cpp} -------------------------------------------------------- */
+/* Frame::Frame(id,w,h,K,ts,const uchar*) Frame.cpp:35-54 + buildImage :491-630 + buildGradients :643-680
+ * + buildMaxGradients :690-767, all levels, once per frame.  gray = HOST buffer of w*h bytes. */
+int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray);
+int lsdgpu_frame_release(lsdgpu_ctx* ctx, int frame_id);                 /* Frame::~Frame */
+int lsdgpu_frame_download(lsdgpu_ctx* ctx, int frame_id, int what, int level, void* out_host);
+/* Frame::setDepthFromGroundTruth(depth, cov_scale) Frame.cpp:245-293 */
+int lsdgpu_frame_set_depth_gt(lsdgpu_ctx* ctx, int frame_id, const float* depth, float cov_scale);
+/* raw level-0 idepth / idepthVar import (Frame::setDepth output of a host-side DepthMap) */
+int lsdgpu_frame_set_idepth(lsdgpu_ctx* ctx, int frame_id, const float* idepth, const float* idepthVar);
+/* FramePoseStruct::thisToParent_raw / trackingParent + Frame::initialTrackedResidual (written by
+ * lsdgpu_se3_track; the setter lets a host pose-graph override them) */
+int lsdgpu_frame_set_pose(lsdgpu_ctx* ctx, int frame_id, const double thisToParent_qts[8], int parent_id, float initialTrackedResidual);
+int lsdgpu_frame_get_pose(lsdgpu_ctx* ctx, int frame_id, double thisToParent_qts[8], int* parent_id, float* initialTrackedResidual);
+/* Frame::numFramesTrackedOnThis / numMappedOnThis (DepthMap.cpp:454, SE3Tracker.cpp:480) */
+int lsdgpu_frame_get_counters(lsdgpu_ctx* ctx, int frame_id, int* numFramesTrackedOnThis, int* numMappedOnThis);
+int lsdgpu_frame_set_counters(lsdgpu_ctx* ctx, int frame_id, int numFramesTrackedOnThis, int numMappedOnThis);
+/* Frame::meanIdepth / numPoints / depthHasBeenUpdatedFlag (Frame.cpp:234-242) */
+int lsdgpu_frame_get_depth_stats(lsdgpu_ctx* ctx, int frame_id, float* meanIdepth, int* numPoints, int* depthHasBeenUpdatedFlag);
+/* Frame::clear_refPixelWasGood (SlamSystem.cpp:573) */
+int lsdgpu_frame_clear_good_mask(lsdgpu_ctx* ctx, int frame_id);
+
+/* ---- Tracking: Tracking/TrackingReference.cpp + Tracking/SE3Tracker.cpp -------------------------- */
+/* TrackingReference::importFrame :71-87 (+ the depthHasBeenUpdatedFlag=false of SlamSystem.cpp:907-912):
+ * (re)builds the keyframe's idepth pyramids (Frame::buildIDepthAndIDepthVar, Frame.cpp:775-877) that
+ * makePointCloud :96-147 reads; the point cloud itself is never materialised on the device. */
+int lsdgpu_ref_import(lsdgpu_ctx* ctx, int kf_id);
+/* single fused evaluation at `level` for pose refToFrame (float qt[7]); parity hook for hot loops A+B+C */
+int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int level, const float refToFrame_qt[7],
+                    float affine_a, float affine_b, const lsdgpu_track_settings* s, int write_good_mask,
+                    lsdgpu_eval_result* out);
+/* SE3Tracker::trackFrame :280-486.  Whole coarse-to-fine LM loop; mode 0 = host-driven LM (one kernel
+ * per evaluation, 6x6 solve on the host), mode 1 = device-resident LM (one persistent kernel per frame). */
+int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double frameToRef_init_qt[7],
+                     const lsdgpu_track_settings* s, int mode, lsdgpu_track_result* out);
+
+/* ---- DepthMap: DepthEstimation/DepthMap.cpp ------------------------------------------------------ */
+int lsdgpu_depth_reset(lsdgpu_ctx* ctx);                                  /* DepthMap::reset :102-108 */
+int lsdgpu_depth_is_valid(lsdgpu_ctx* ctx);                               /* DepthMap::isValid, DepthMap.h:71 */
+int lsdgpu_depth_invalidate(lsdgpu_ctx* ctx);                             /* DepthMap::invalidate :1215-1220 */
+int lsdgpu_depth_init_from_gt(lsdgpu_ctx* ctx, int kf_id);                /* initializeFromGTDepth :965-1018 */
+/* initializeRandomly :883-916 (host draws rand()) and setFromExistingKF :920-962 both reduce to
+ * "load these hypotheses for keyframe kf_id"; reactivated != 0 also runs the regularizeDepthMap(false,24)
+ * of :961 and sets activeKeyFrameIsReactivated.  do_set_depth mirrors the trailing setDepth of :915. */
+int lsdgpu_depth_set_hypotheses(lsdgpu_ctx* ctx, int kf_id, const lsdgpu_hyp* aos, int reactivated, int do_set_depth);
+/* DepthMap::updateKeyframe(referenceFrames) :1072-1213; ref_ids oldest first, all tracked on the active KF */
+int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs);
+/* DepthMap::createKeyFrame(new_keyframe) :1222-1327; writes the rescaled thisToParent_raw of the new KF */
+int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, double new_thisToParent_qts[8]);
+int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx);                      /* finalizeKeyFrame :1363-1395 */
+int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx);                        /* id or -1 */
+/* currentDepthMap in the reference's 32-byte AoS layout (Frame::setDepth / takeReActivationData input) */
+int lsdgpu_depth_download(lsdgpu_ctx* ctx, lsdgpu_hyp* aos_out);
+int lsdgpu_depth_download_integral(lsdgpu_ctx* ctx, int32_t* out);        /* validityIntegralBuffer */
+/* individual passes (per-kernel parity hooks; same order of operations as the drivers above) */
+int lsdgpu_depth_observe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs);            /* observeDepth :147-178 */
+int lsdgpu_depth_regularize_fill_holes(lsdgpu_ctx* ctx);                              /* :706-718 */
+int lsdgpu_depth_regularize(lsdgpu_ctx* ctx, int removeOcclusions, int validityTH);   /* :853-880 */
+int lsdgpu_depth_propagate(lsdgpu_ctx* ctx, int new_kf_id);                           /* :475-653 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,365 @@
+"""ctypes binding of the C ABI (include/lsdgpu.h -> liblsdgpu.so) plus thin Python mirrors of the reference's
+public interface for the hot path (``SE3Tracker.trackFrame``, ``DepthMap.updateKeyframe`` /
+``createKeyFrame`` -- Tracking/SE3Tracker.h:65-68, DepthEstimation/DepthMap.h:58,63).
+
+This is the product path: it loads the CUDA library and nothing else.  There is NO CPU fallback -- a missing
+or unloadable ``liblsdgpu.so`` raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblsdgpu.so")
+LEVELS = 5
+
+BUF_IMAGE, BUF_GRADIENTS, BUF_MAXGRAD, BUF_IDEPTH, BUF_IDEPTH_VAR, BUF_GOODMASK = range(6)
+
+
+class Hyp(C.Structure):
+    _fields_ = [("isValid", C.c_uint8), ("_pad", C.c_uint8 * 3), ("blacklisted", C.c_int32),
+                ("nextStereoFrameMinID", C.c_float), ("validity_counter", C.c_int32),
+                ("idepth", C.c_float), ("idepth_var", C.c_float),
+                ("idepth_smoothed", C.c_float), ("idepth_var_smoothed", C.c_float)]
+
+
+HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, 3), ("blacklisted", np.int32),
+                      ("nextStereoFrameMinID", np.float32), ("validity_counter", np.int32),
+                      ("idepth", np.float32), ("idepth_var", np.float32),
+                      ("idepth_smoothed", np.float32), ("idepth_var_smoothed", np.float32)])
+
+
+class Globals(C.Structure):
+    _fields_ = [("minUseGrad", C.c_float), ("cameraPixelNoise2", C.c_float), ("depthSmoothingFactor", C.c_float),
+                ("allowNegativeIdepths", C.c_int), ("useSubpixelStereo", C.c_int),
+                ("useAffineLightningEstimation", C.c_int)]
+
+
+class TrackSettings(C.Structure):
+    _fields_ = [("lambdaSuccessFac", C.c_float), ("lambdaFailFac", C.c_float),
+                ("lambdaInitial", C.c_float * LEVELS), ("stepSizeMin", C.c_float * LEVELS),
+                ("convergenceEps", C.c_float * LEVELS), ("maxItsPerLvl", C.c_int * LEVELS),
+                ("huber_d", C.c_float), ("var_weight", C.c_float)]
+
+
+class TrackResult(C.Structure):
+    _fields_ = [("frameToRef_qt", C.c_double * 7),
+                ("pointUsage", C.c_float), ("lastGoodCount", C.c_float), ("lastBadCount", C.c_float),
+                ("lastMeanRes", C.c_float), ("lastResidual", C.c_float),
+                ("affineEstimation_a", C.c_float), ("affineEstimation_b", C.c_float),
+                ("diverged", C.c_int), ("trackingWasGood", C.c_int),
+                ("numCalcResidualCalls", C.c_int * LEVELS), ("numCalcWarpUpdateCalls", C.c_int * LEVELS),
+                ("initialTrackedResidual", C.c_float)]
+
+
+class EvalResult(C.Structure):
+    _fields_ = [("A", C.c_float * 36), ("b", C.c_float * 6), ("lsError", C.c_float),
+                ("meanWeightedRes", C.c_float), ("meanUnweightedRes", C.c_float), ("warpedSize", C.c_int),
+                ("pointUsage", C.c_float), ("goodCount", C.c_float), ("badCount", C.c_float), ("meanRes", C.c_float),
+                ("affine_a_lastIt", C.c_float), ("affine_b_lastIt", C.c_float),
+                ("sxx", C.c_float), ("syy", C.c_float), ("sx", C.c_float), ("sy", C.c_float), ("sw", C.c_float)]
+
+
+# every symbol include/lsdgpu.h declares: (name, restype, argtypes)
+_vp, _fp, _dp, _ip, _u8p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint8)
+SYMBOLS = [
+    ("lsdgpu_create", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.POINTER(_vp)]),
+    ("lsdgpu_destroy", None, [_vp]),
+    ("lsdgpu_last_error", C.c_char_p, [_vp]),
+    ("lsdgpu_abi_version", C.c_int, []),
+    ("lsdgpu_set_globals", C.c_int, [_vp, C.POINTER(Globals)]),
+    ("lsdgpu_default_globals", None, [C.POINTER(Globals)]),
+    ("lsdgpu_default_track_settings", None, [C.POINTER(TrackSettings)]),
+    ("lsdgpu_synchronize", C.c_int, [_vp]),
+    ("lsdgpu_launch_count", C.c_longlong, [_vp]),
+    ("lsdgpu_timer_begin", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_timer_end", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_timer_elapsed_ms", C.c_int, [_vp, C.c_int, _fp]),
+    ("lsdgpu_track_kernel_stats", C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_longlong), _dp]),
+    ("lsdgpu_frame_upload_u8", C.c_int, [_vp, C.c_int, _u8p]),
+    ("lsdgpu_frame_release", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_frame_download", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
+    ("lsdgpu_frame_set_depth_gt", C.c_int, [_vp, C.c_int, _fp, C.c_float]),
+    ("lsdgpu_frame_set_idepth", C.c_int, [_vp, C.c_int, _fp, _fp]),
+    ("lsdgpu_frame_set_pose", C.c_int, [_vp, C.c_int, _dp, C.c_int, C.c_float]),
+    ("lsdgpu_frame_get_pose", C.c_int, [_vp, C.c_int, _dp, _ip, _fp]),
+    ("lsdgpu_frame_get_counters", C.c_int, [_vp, C.c_int, _ip, _ip]),
+    ("lsdgpu_frame_set_counters", C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    ("lsdgpu_frame_get_depth_stats", C.c_int, [_vp, C.c_int, _fp, _ip, _ip]),
+    ("lsdgpu_frame_clear_good_mask", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_ref_import", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
+    ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
+    ("lsdgpu_depth_reset", C.c_int, [_vp]),
+    ("lsdgpu_depth_is_valid", C.c_int, [_vp]),
+    ("lsdgpu_depth_invalidate", C.c_int, [_vp]),
+    ("lsdgpu_depth_init_from_gt", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_depth_set_hypotheses", C.c_int, [_vp, C.c_int, C.POINTER(Hyp), C.c_int, C.c_int]),
+    ("lsdgpu_depth_update_keyframe", C.c_int, [_vp, _ip, C.c_int]),
+    ("lsdgpu_depth_create_keyframe", C.c_int, [_vp, C.c_int, _dp]),
+    ("lsdgpu_depth_finalize_keyframe", C.c_int, [_vp]),
+    ("lsdgpu_depth_active_keyframe", C.c_int, [_vp]),
+    ("lsdgpu_depth_download", C.c_int, [_vp, C.POINTER(Hyp)]),
+    ("lsdgpu_depth_download_integral", C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    ("lsdgpu_depth_observe", C.c_int, [_vp, _ip, C.c_int]),
+    ("lsdgpu_depth_regularize_fill_holes", C.c_int, [_vp]),
+    ("lsdgpu_depth_regularize", C.c_int, [_vp, C.c_int, C.c_int]),
+    ("lsdgpu_depth_propagate", C.c_int, [_vp, C.c_int]),
+]
+
+_lib = None
+
+
+def load():
+    """Load liblsdgpu.so (loudly: raises if the extension is missing)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m lsd_slam_b200.build` "
+                           "(the product path has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+class LsdGpuError(RuntimeError):
+    pass
+
+
+def default_track_settings(main_tracker: bool = True) -> TrackSettings:
+    s = TrackSettings()
+    load().lsdgpu_default_track_settings(C.byref(s))
+    if main_tracker:                      # SlamSystem.cpp:80-81
+        for lvl in range(4, LEVELS):
+            s.maxItsPerLvl[lvl] = 0
+    return s
+
+
+class Context:
+    """One device context = the device state of one SlamSystem (frames + one tracker + one depth map)."""
+
+    def __init__(self, w: int, h: int, K: np.ndarray, device: int = 0, max_frames: int = 8, **globals_kw):
+        self.L = load()
+        self.w, self.h = w, h
+        self.K = np.ascontiguousarray(K, np.float32).reshape(3, 3)
+        p = _vp()
+        rc = self.L.lsdgpu_create(device, w, h, self.K.ctypes.data_as(_fp), max_frames, C.byref(p))
+        self.ptr = p
+        if rc != 0:
+            msg = self.L.lsdgpu_last_error(p).decode() if p else "lsdgpu_create failed"
+            if p:
+                self.L.lsdgpu_destroy(p)
+            self.ptr = None
+            raise LsdGpuError(f"lsdgpu_create({w}x{h}) -> {rc}: {msg}")
+        if globals_kw:
+            self.set_globals(**globals_kw)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            self.L.lsdgpu_destroy(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LsdGpuError(f"rc={rc}: {self.L.lsdgpu_last_error(self.ptr).decode()}")
+
+    def set_globals(self, **kw):
+        g = Globals()
+        self.L.lsdgpu_default_globals(C.byref(g))
+        for k, v in kw.items():
+            setattr(g, k, v)
+        self._ck(self.L.lsdgpu_set_globals(self.ptr, C.byref(g)))
+
+    def synchronize(self):
+        self._ck(self.L.lsdgpu_synchronize(self.ptr))
+
+    def launch_count(self) -> int:
+        return int(self.L.lsdgpu_launch_count(self.ptr))
+
+    def timer_begin(self, slot=0):
+        self._ck(self.L.lsdgpu_timer_begin(self.ptr, slot))
+
+    def timer_end(self, slot=0) -> None:
+        self._ck(self.L.lsdgpu_timer_end(self.ptr, slot))
+
+    def timer_ms(self, slot=0) -> float:
+        ms = C.c_float()
+        self._ck(self.L.lsdgpu_timer_elapsed_ms(self.ptr, slot, C.byref(ms)))
+        return ms.value
+
+    def track_kernel_stats(self, reset=0):
+        ms, n, b = C.c_double(), C.c_longlong(), C.c_double()
+        self._ck(self.L.lsdgpu_track_kernel_stats(self.ptr, reset, C.byref(ms), C.byref(n), C.byref(b)))
+        return ms.value, n.value, b.value
+
+    # ---- Frame ----
+    def upload(self, fid: int, image_u8: np.ndarray):
+        img = np.ascontiguousarray(image_u8, np.uint8)
+        assert img.shape == (self.h, self.w)
+        self._ck(self.L.lsdgpu_frame_upload_u8(self.ptr, fid, img.ctypes.data_as(_u8p)))
+
+    def release(self, fid: int):
+        self._ck(self.L.lsdgpu_frame_release(self.ptr, fid))
+
+    def download(self, fid: int, what: int, level: int = 0) -> np.ndarray:
+        w, h = self.w >> level, self.h >> level
+        if what == BUF_GRADIENTS:
+            out = np.empty((h, w, 4), np.float32)
+        elif what == BUF_GOODMASK:
+            out = np.empty((self.h >> 1, self.w >> 1), np.uint8)
+        else:
+            out = np.empty((h, w), np.float32)
+        self._ck(self.L.lsdgpu_frame_download(self.ptr, fid, what, level, out.ctypes.data_as(_vp)))
+        return out
+
+    def set_depth_gt(self, fid: int, depth: np.ndarray, cov_scale: float = 1.0):
+        d = np.ascontiguousarray(depth, np.float32)
+        self._ck(self.L.lsdgpu_frame_set_depth_gt(self.ptr, fid, d.ctypes.data_as(_fp), cov_scale))
+
+    def set_idepth(self, fid: int, idepth: np.ndarray, var: np.ndarray):
+        a = np.ascontiguousarray(idepth, np.float32)
+        b = np.ascontiguousarray(var, np.float32)
+        self._ck(self.L.lsdgpu_frame_set_idepth(self.ptr, fid, a.ctypes.data_as(_fp), b.ctypes.data_as(_fp)))
+
+    def set_pose(self, fid: int, qts, parent_id: int, initialTrackedResidual: float = 0.0):
+        q = np.ascontiguousarray(qts, np.float64)
+        self._ck(self.L.lsdgpu_frame_set_pose(self.ptr, fid, q.ctypes.data_as(_dp), parent_id, initialTrackedResidual))
+
+    def get_pose(self, fid: int):
+        q = np.zeros(8, np.float64)
+        pid, itr = C.c_int(), C.c_float()
+        self._ck(self.L.lsdgpu_frame_get_pose(self.ptr, fid, q.ctypes.data_as(_dp), C.byref(pid), C.byref(itr)))
+        return q, pid.value, itr.value
+
+    def get_counters(self, fid: int):
+        a, b = C.c_int(), C.c_int()
+        self._ck(self.L.lsdgpu_frame_get_counters(self.ptr, fid, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def set_counters(self, fid: int, tracked: int, mapped: int):
+        self._ck(self.L.lsdgpu_frame_set_counters(self.ptr, fid, tracked, mapped))
+
+    def depth_stats(self, fid: int):
+        m, n, f = C.c_float(), C.c_int(), C.c_int()
+        self._ck(self.L.lsdgpu_frame_get_depth_stats(self.ptr, fid, C.byref(m), C.byref(n), C.byref(f)))
+        return m.value, n.value, bool(f.value)
+
+    def clear_good_mask(self, fid: int):
+        self._ck(self.L.lsdgpu_frame_clear_good_mask(self.ptr, fid))
+
+
+class SE3Tracker:
+    """Mirror of lsd_slam::SE3Tracker (Tracking/SE3Tracker.h): ``trackFrame`` + the public result fields."""
+
+    def __init__(self, ctx: Context, mode: int = 1):
+        self.ctx = ctx
+        self.mode = mode
+        self.settings = default_track_settings()
+        self.pointUsage = 0.0
+        self.lastGoodCount = self.lastBadCount = 0.0
+        self.lastMeanRes = self.lastResidual = 0.0
+        self.affineEstimation_a, self.affineEstimation_b = 1.0, 0.0
+        self.diverged = False
+        self.trackingWasGood = False
+        self.last = None
+
+    def importFrame(self, kf_id: int):
+        """TrackingReference::importFrame + depthHasBeenUpdatedFlag=false (SlamSystem.cpp:907-912)."""
+        self.ctx._ck(self.ctx.L.lsdgpu_ref_import(self.ctx.ptr, kf_id))
+
+    def trackFrame(self, kf_id: int, frame_id: int, frameToReference_initialEstimate) -> np.ndarray:
+        q = np.ascontiguousarray(frameToReference_initialEstimate, np.float64)
+        r = TrackResult()
+        self.ctx._ck(self.ctx.L.lsdgpu_se3_track(self.ctx.ptr, kf_id, frame_id, q.ctypes.data_as(_dp),
+                                                 C.byref(self.settings), self.mode, C.byref(r)))
+        self.last = r
+        self.pointUsage, self.lastGoodCount, self.lastBadCount = r.pointUsage, r.lastGoodCount, r.lastBadCount
+        self.lastMeanRes, self.lastResidual = r.lastMeanRes, r.lastResidual
+        self.affineEstimation_a, self.affineEstimation_b = r.affineEstimation_a, r.affineEstimation_b
+        self.diverged, self.trackingWasGood = bool(r.diverged), bool(r.trackingWasGood)
+        return np.array(r.frameToRef_qt, np.float64)
+
+    def eval(self, kf_id: int, frame_id: int, level: int, refToFrame_qt, a=1.0, b=0.0, write_mask=False) -> EvalResult:
+        q = np.ascontiguousarray(refToFrame_qt, np.float32)
+        r = EvalResult()
+        self.ctx._ck(self.ctx.L.lsdgpu_se3_eval(self.ctx.ptr, kf_id, frame_id, level, q.ctypes.data_as(_fp), a, b,
+                                                C.byref(self.settings), int(write_mask), C.byref(r)))
+        return r
+
+
+class DepthMap:
+    """Mirror of lsd_slam::DepthMap (DepthEstimation/DepthMap.h)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def _ids(self, ids):
+        a = np.ascontiguousarray(ids, np.int32)
+        return a, a.ctypes.data_as(_ip), len(a)
+
+    def reset(self):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_reset(self.ctx.ptr))
+
+    def isValid(self) -> bool:
+        return bool(self.ctx.L.lsdgpu_depth_is_valid(self.ctx.ptr))
+
+    def invalidate(self):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_invalidate(self.ctx.ptr))
+
+    def activeKeyFrame(self) -> int:
+        return self.ctx.L.lsdgpu_depth_active_keyframe(self.ctx.ptr)
+
+    def initializeFromGTDepth(self, kf_id: int):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_init_from_gt(self.ctx.ptr, kf_id))
+
+    def setHypotheses(self, kf_id: int, hyp: np.ndarray, reactivated=False, do_set_depth=True):
+        a = np.ascontiguousarray(hyp)
+        assert a.dtype == HYP_DTYPE
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_set_hypotheses(self.ctx.ptr, kf_id, a.ctypes.data_as(C.POINTER(Hyp)),
+                                                            int(reactivated), int(do_set_depth)))
+
+    def updateKeyframe(self, referenceFrames):
+        a, p, n = self._ids(referenceFrames)
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_update_keyframe(self.ctx.ptr, p, n))
+
+    def createKeyFrame(self, new_kf_id: int) -> np.ndarray:
+        q = np.zeros(8, np.float64)
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_create_keyframe(self.ctx.ptr, new_kf_id, q.ctypes.data_as(_dp)))
+        return q
+
+    def finalizeKeyFrame(self):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_finalize_keyframe(self.ctx.ptr))
+
+    def observeDepth(self, referenceFrames):
+        a, p, n = self._ids(referenceFrames)
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_observe(self.ctx.ptr, p, n))
+
+    def regularizeFillHoles(self):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_regularize_fill_holes(self.ctx.ptr))
+
+    def regularize(self, removeOcclusions: bool, validityTH: int = 24):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_regularize(self.ctx.ptr, int(removeOcclusions), validityTH))
+
+    def propagateDepth(self, new_kf_id: int):
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_propagate(self.ctx.ptr, new_kf_id))
+
+    def current(self) -> np.ndarray:
+        out = np.zeros((self.ctx.h, self.ctx.w), HYP_DTYPE)
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_download(self.ctx.ptr, out.ctypes.data_as(C.POINTER(Hyp))))
+        return out
+
+    def integral(self) -> np.ndarray:
+        out = np.zeros((self.ctx.h, self.ctx.w), np.int32)
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_download_integral(self.ctx.ptr, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out

@@ -1,0 +1,820 @@
+// depth.cuh -- per-pixel kernels of DepthMap (semi-dense inverse-depth filter).
+//
+// Replaces (paths relative to lsd_slam_core/src/DepthEstimation/DepthMap.cpp):
+//   observeDepthRow / Create / Update      :111-146, 237-292, 294-473      -> k_observe
+//   makeAndCheckEPL                        :184-234
+//   doLineStereo                           :1442-1972   (NDEBUG semantics: enablePrintDebugInfo == false)
+//   buildRegIntegralBuffer + FillHolesRow  :722-754, 656-703               -> k_fill_holes (5x5 validity sum
+//                                          taken directly; the integral image is never needed on the GPU)
+//   regularizeDepthMapRow<removeOcclusions>:758-848                        -> k_regularize<bool>
+//   propagateDepth                         :475-653                        -> k_prop_project + k_prop_resolve
+//   createKeyFrame rescale                 :1285-1304                      -> k_sum_idepth + k_rescale
+//   Frame::setDepth                        DataStructures/Frame.cpp:199-243 -> k_set_depth
+// The reference's memcpy(other <- current) + read other / write current (:713, :862) is a ping-pong here:
+// every kernel reads `src` and writes every pixel of `dst`.
+//
+// Arithmetic is kept in the reference's order and the library is compiled with --fmad=false, so per-pixel
+// results are bit-identical to a strict-IEEE CPU evaluation (threshold decisions included).
+#pragma once
+#include "internal.cuh"
+
+#define DIVISION_EPS 1e-10f
+#define VALIDITY_COUNTER_MAX (5.0f)
+#define VALIDITY_COUNTER_MAX_VARIABLE (250.0f)
+#define VALIDITY_COUNTER_INC 5
+#define VALIDITY_COUNTER_DEC 5
+#define VALIDITY_COUNTER_INITIAL_OBSERVE 5
+#define VAL_SUM_MIN_FOR_CREATE (30)
+#define VAL_SUM_MIN_FOR_KEEP (24)
+#define VAL_SUM_MIN_FOR_UNBLACKLIST (100)
+#define MIN_BLACKLIST -1
+#define SUCC_VAR_INC_FAC (1.01f)
+#define FAIL_VAR_INC_FAC 1.1f
+#define MAX_VAR (0.5f*0.5f)
+#define VAR_RANDOM_INIT_INITIAL (0.5f*MAX_VAR)
+#define MIN_DEPTH 0.05f
+#define MAX_EPL_LENGTH_CROP 30.0f
+#define MIN_EPL_LENGTH_CROP (3.0f)
+#define GRADIENT_SAMPLE_DIST 1.0f
+#define SAMPLE_POINT_TO_BORDER 7
+#define MAX_ERROR_STEREO (1300.0f)
+#define MIN_DISTANCE_ERROR_STEREO (1.5f)
+#define STEREO_EPL_VAR_FAC 2.0f
+#define DIFF_FAC_SMOOTHING (1.0f*1.0f)
+#define DIFF_FAC_OBSERVE (1.0f*1.0f)
+#define DIFF_FAC_PROP_MERGE (1.0f*1.0f)
+#define MIN_EPL_GRAD_SQUARED (2.0f*2.0f)
+#define MIN_EPL_LENGTH_SQUARED (1.0f*1.0f)
+#define MIN_EPL_ANGLE_SQUARED (0.3f*0.3f)
+#define MAX_DIFF_CONSTANT (40.0f*40.0f)
+#define MAX_DIFF_GRAD_MULT (0.5f*0.5f)
+
+struct DepthCam {
+    int w, h;
+    float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
+};
+struct DepthGlobals {
+    float minUseGrad, cameraPixelNoise2, regDistVar;
+    int allowNegativeIdepths, useSubpixelStereo;
+};
+
+// hypothesis record in registers; hf/hi planes, see internal.cuh
+struct Hyp {
+    int isValid, blacklisted, validity_counter;
+    float nextStereoFrameMinID;
+    float idepth, idepth_var, idepth_smoothed, idepth_var_smoothed;
+};
+__device__ __forceinline__ Hyp loadHyp(const HypField& f, int i)
+{
+    float4 a = f.hf[i];
+    int4 b = f.hi[i];
+    Hyp h;
+    h.idepth = a.x; h.idepth_var = a.y; h.idepth_smoothed = a.z; h.idepth_var_smoothed = a.w;
+    h.isValid = b.x; h.blacklisted = b.y; h.validity_counter = b.z; h.nextStereoFrameMinID = __int_as_float(b.w);
+    return h;
+}
+__device__ __forceinline__ void storeHyp(const HypField& f, int i, const Hyp& h)
+{
+    f.hf[i] = make_float4(h.idepth, h.idepth_var, h.idepth_smoothed, h.idepth_var_smoothed);
+    f.hi[i] = make_int4(h.isValid, h.blacklisted, h.validity_counter, __float_as_int(h.nextStereoFrameMinID));
+}
+// DepthMapPixelHypothesis(idepth, var, validity), DepthMapPixelHypothesis.h:80-91
+__device__ __forceinline__ void hypCtor3(Hyp& h, float idepth, float var, int validity)
+{
+    h.isValid = 1; h.blacklisted = 0; h.nextStereoFrameMinID = 0; h.validity_counter = validity;
+    h.idepth = idepth; h.idepth_var = var; h.idepth_smoothed = -1; h.idepth_var_smoothed = -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// doLineStereo, DepthMap.cpp:1442-1972.  Returns the reference's error code / SSD.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __noinline__ float doLineStereo(
+    const DepthCam& cam, const DepthGlobals& G, const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
+    const float u, const float v, const float epxn, const float epyn,
+    const float min_idepth, const float prior_idepth, float max_idepth,
+    const RefConst& ref, float& result_idepth, float& result_var, float& result_eplLength)
+{
+    const int width = cam.w, height = cam.h;
+    const float fxi = cam.fxi, fyi = cam.fyi, cxi = cam.cxi, cyi = cam.cyi;
+    const float* __restrict__ refImage = ref.image;
+    const float* KR = ref.K_otherToThis_R;
+    const float* Kt = ref.K_otherToThis_t;
+
+    float KinvP[3] = { fxi * u + cxi, fyi * v + cyi, 1.0f };
+    float pInf[3], pReal[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) pInf[i] = (KR[i * 3 + 0] * KinvP[0] + KR[i * 3 + 1] * KinvP[1]) + KR[i * 3 + 2] * KinvP[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) pReal[i] = pInf[i] / prior_idepth + Kt[i];
+
+    float rescaleFactor = pReal[2] * prior_idepth;
+
+    float firstX = u - 2 * epxn * rescaleFactor;
+    float firstY = v - 2 * epyn * rescaleFactor;
+    float lastX = u + 2 * epxn * rescaleFactor;
+    float lastY = v + 2 * epyn * rescaleFactor;
+    if (firstX <= 0 || firstX >= width - 2 || firstY <= 0 || firstY >= height - 2
+        || lastX <= 0 || lastX >= width - 2 || lastY <= 0 || lastY >= height - 2)
+        return -1;
+    if (!(rescaleFactor > 0.7f && rescaleFactor < 1.4f)) return -1;
+
+    float realVal_p1 = interpF(kfImage, u + epxn * rescaleFactor, v + epyn * rescaleFactor, width);
+    float realVal_m1 = interpF(kfImage, u - epxn * rescaleFactor, v - epyn * rescaleFactor, width);
+    float realVal = interpF(kfImage, u, v, width);
+    float realVal_m2 = interpF(kfImage, u - 2 * epxn * rescaleFactor, v - 2 * epyn * rescaleFactor, width);
+    float realVal_p2 = interpF(kfImage, u + 2 * epxn * rescaleFactor, v + 2 * epyn * rescaleFactor, width);
+
+    float pClose[3], pFar[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) pClose[i] = pInf[i] + Kt[i] * max_idepth;
+    if (pClose[2] < 0.001f) {
+        max_idepth = (0.001f - pInf[2]) / Kt[2];
+#pragma unroll
+        for (int i = 0; i < 3; i++) pClose[i] = pInf[i] + Kt[i] * max_idepth;
+    }
+    { float z = pClose[2]; pClose[0] = pClose[0] / z; pClose[1] = pClose[1] / z; pClose[2] = pClose[2] / z; }
+
+#pragma unroll
+    for (int i = 0; i < 3; i++) pFar[i] = pInf[i] + Kt[i] * min_idepth;
+    if (pFar[2] < 0.001f || max_idepth < min_idepth) return -1;
+    { float z = pFar[2]; pFar[0] = pFar[0] / z; pFar[1] = pFar[1] / z; pFar[2] = pFar[2] / z; }
+
+    if (isnan((float)(pFar[0] + pClose[0]))) return -4;
+
+    float incx = pClose[0] - pFar[0];
+    float incy = pClose[1] - pFar[1];
+    float eplLength = sqrtf(incx * incx + incy * incy);
+    if ((eplLength == 0.0f) || isinf(eplLength)) return -4;       // `!eplLength > 0` parses as (!eplLength) > 0, :1518
+
+    if (eplLength > MAX_EPL_LENGTH_CROP) {
+        pClose[0] = pFar[0] + incx * MAX_EPL_LENGTH_CROP / eplLength;
+        pClose[1] = pFar[1] + incy * MAX_EPL_LENGTH_CROP / eplLength;
+    }
+
+    incx *= GRADIENT_SAMPLE_DIST / eplLength;
+    incy *= GRADIENT_SAMPLE_DIST / eplLength;
+
+    pFar[0] -= incx; pFar[1] -= incy;
+    pClose[0] += incx; pClose[1] += incy;
+
+    if (eplLength < MIN_EPL_LENGTH_CROP) {
+        float pad = (MIN_EPL_LENGTH_CROP - (eplLength)) / 2.0f;
+        pFar[0] -= incx * pad; pFar[1] -= incy * pad;
+        pClose[0] += incx * pad; pClose[1] += incy * pad;
+    }
+
+    if (pFar[0] <= SAMPLE_POINT_TO_BORDER || pFar[0] >= width - SAMPLE_POINT_TO_BORDER ||
+        pFar[1] <= SAMPLE_POINT_TO_BORDER || pFar[1] >= height - SAMPLE_POINT_TO_BORDER)
+        return -1;
+
+    if (pClose[0] <= SAMPLE_POINT_TO_BORDER || pClose[0] >= width - SAMPLE_POINT_TO_BORDER ||
+        pClose[1] <= SAMPLE_POINT_TO_BORDER || pClose[1] >= height - SAMPLE_POINT_TO_BORDER) {
+        if (pClose[0] <= SAMPLE_POINT_TO_BORDER) {
+            float toAdd = (SAMPLE_POINT_TO_BORDER - pClose[0]) / incx;
+            pClose[0] += toAdd * incx; pClose[1] += toAdd * incy;
+        } else if (pClose[0] >= width - SAMPLE_POINT_TO_BORDER) {
+            float toAdd = (width - SAMPLE_POINT_TO_BORDER - pClose[0]) / incx;
+            pClose[0] += toAdd * incx; pClose[1] += toAdd * incy;
+        }
+        if (pClose[1] <= SAMPLE_POINT_TO_BORDER) {
+            float toAdd = (SAMPLE_POINT_TO_BORDER - pClose[1]) / incy;
+            pClose[0] += toAdd * incx; pClose[1] += toAdd * incy;
+        } else if (pClose[1] >= height - SAMPLE_POINT_TO_BORDER) {
+            float toAdd = (height - SAMPLE_POINT_TO_BORDER - pClose[1]) / incy;
+            pClose[0] += toAdd * incx; pClose[1] += toAdd * incy;
+        }
+        float fincx = pClose[0] - pFar[0];
+        float fincy = pClose[1] - pFar[1];
+        float newEplLength = sqrtf(fincx * fincx + fincy * fincy);
+        if (pClose[0] <= SAMPLE_POINT_TO_BORDER || pClose[0] >= width - SAMPLE_POINT_TO_BORDER ||
+            pClose[1] <= SAMPLE_POINT_TO_BORDER || pClose[1] >= height - SAMPLE_POINT_TO_BORDER ||
+            newEplLength < 8.0f)
+            return -1;
+    }
+
+    float cpx = pFar[0];
+    float cpy = pFar[1];
+
+    float val_cp_m2 = interpF(refImage, cpx - 2.0f * incx, cpy - 2.0f * incy, width);
+    float val_cp_m1 = interpF(refImage, cpx - incx, cpy - incy, width);
+    float val_cp = interpF(refImage, cpx, cpy, width);
+    float val_cp_p1 = interpF(refImage, cpx + incx, cpy + incy, width);
+    float val_cp_p2;
+
+    const float fNAN = __int_as_float(0x7fc00000);
+    const float fINF = __int_as_float(0x7f800000);
+    int loopCounter = 0;
+    float best_match_x = -1;
+    float best_match_y = -1;
+    float best_match_err = fINF;                 // `float x = 1e50` -> +inf, :1658-1659
+    float second_best_match_err = fINF;
+    float best_match_errPre = fNAN, best_match_errPost = fNAN, best_match_DiffErrPre = fNAN, best_match_DiffErrPost = fNAN;
+    bool bestWasLastLoop = false;
+    float eeLast = -1;
+    float e1A = fNAN, e1B = fNAN, e2A = fNAN, e2B = fNAN, e3A = fNAN, e3B = fNAN, e4A = fNAN, e4B = fNAN, e5A = fNAN, e5B = fNAN;
+    int loopCBest = -1, loopCSecond = -1;
+
+    // the reference loop has no bound; with finite inputs it ends after <= ~40 steps (30-px crop + padding).
+    // 4096 only protects the GPU from a NaN-poisoned frame (where the reference would spin forever).
+    while ((((incx < 0) == (cpx > pClose[0]) && (incy < 0) == (cpy > pClose[1])) || loopCounter == 0) && loopCounter < 4096) {
+        val_cp_p2 = interpF(refImage, cpx + 2 * incx, cpy + 2 * incy, width);
+        float ee = 0;
+        if (loopCounter % 2 == 0) {
+            e1A = val_cp_p2 - realVal_p2; ee += e1A * e1A;
+            e2A = val_cp_p1 - realVal_p1; ee += e2A * e2A;
+            e3A = val_cp - realVal;       ee += e3A * e3A;
+            e4A = val_cp_m1 - realVal_m1; ee += e4A * e4A;
+            e5A = val_cp_m2 - realVal_m2; ee += e5A * e5A;
+        } else {
+            e1B = val_cp_p2 - realVal_p2; ee += e1B * e1B;
+            e2B = val_cp_p1 - realVal_p1; ee += e2B * e2B;
+            e3B = val_cp - realVal;       ee += e3B * e3B;
+            e4B = val_cp_m1 - realVal_m1; ee += e4B * e4B;
+            e5B = val_cp_m2 - realVal_m2; ee += e5B * e5B;
+        }
+        if (ee < best_match_err) {
+            second_best_match_err = best_match_err;
+            loopCSecond = loopCBest;
+            best_match_err = ee;
+            loopCBest = loopCounter;
+            best_match_errPre = eeLast;
+            best_match_DiffErrPre = e1A * e1B + e2A * e2B + e3A * e3B + e4A * e4B + e5A * e5B;
+            best_match_errPost = -1;
+            best_match_DiffErrPost = -1;
+            best_match_x = cpx;
+            best_match_y = cpy;
+            bestWasLastLoop = true;
+        } else {
+            if (bestWasLastLoop) {
+                best_match_errPost = ee;
+                best_match_DiffErrPost = e1A * e1B + e2A * e2B + e3A * e3B + e4A * e4B + e5A * e5B;
+                bestWasLastLoop = false;
+            }
+            if (ee < second_best_match_err) {
+                second_best_match_err = ee;
+                loopCSecond = loopCounter;
+            }
+        }
+        eeLast = ee;
+        val_cp_m2 = val_cp_m1; val_cp_m1 = val_cp; val_cp = val_cp_p1; val_cp_p1 = val_cp_p2;
+        cpx += incx;
+        cpy += incy;
+        loopCounter++;
+    }
+
+    if (best_match_err > 4.0f * (float)MAX_ERROR_STEREO) return -3;
+
+    if (abs(loopCBest - loopCSecond) > 1.0f && MIN_DISTANCE_ERROR_STEREO * best_match_err > second_best_match_err) return -2;
+
+    bool didSubpixel = false;
+    if (G.useSubpixelStereo) {
+        float gradPre_pre = -(best_match_errPre - best_match_DiffErrPre);
+        float gradPre_this = +(best_match_err - best_match_DiffErrPre);
+        float gradPost_this = -(best_match_err - best_match_DiffErrPost);
+        float gradPost_post = +(best_match_errPost - best_match_DiffErrPost);
+        bool interpPost = false, interpPre = false;
+        if ((gradPost_this < 0) ^ (gradPre_this < 0)) {
+        } else if ((gradPre_pre < 0) ^ (gradPre_this < 0)) {
+            if ((gradPost_post < 0) ^ (gradPost_this < 0)) {
+            } else
+                interpPre = true;
+        } else if ((gradPost_post < 0) ^ (gradPost_this < 0)) {
+            interpPost = true;
+        }
+        if (interpPre) {
+            float d = gradPre_this / (gradPre_this - gradPre_pre);
+            best_match_x -= d * incx;
+            best_match_y -= d * incy;
+            best_match_err = best_match_err - 2 * d * gradPre_this - (gradPre_pre - gradPre_this) * d * d;
+            didSubpixel = true;
+        } else if (interpPost) {
+            float d = gradPost_this / (gradPost_this - gradPost_post);
+            best_match_x += d * incx;
+            best_match_y += d * incy;
+            best_match_err = best_match_err + 2 * d * gradPost_this + (gradPost_post - gradPost_this) * d * d;
+            didSubpixel = true;
+        }
+    }
+
+    float sampleDist = GRADIENT_SAMPLE_DIST * rescaleFactor;
+
+    float gradAlongLine = 0;
+    float tmp = realVal_p2 - realVal_p1; gradAlongLine += tmp * tmp;
+    tmp = realVal_p1 - realVal; gradAlongLine += tmp * tmp;
+    tmp = realVal - realVal_m1; gradAlongLine += tmp * tmp;
+    tmp = realVal_m1 - realVal_m2; gradAlongLine += tmp * tmp;
+    gradAlongLine /= sampleDist * sampleDist;
+
+    if (best_match_err > (float)MAX_ERROR_STEREO + sqrtf(gradAlongLine) * 20) return -3;
+
+    float idnew_best_match, alpha;
+    const float* oTt = ref.otherToThis_t;
+#define DOT3(a, b) ((a)[0] * (b)[0] + ((a)[1] * (b)[1] + (a)[2] * (b)[2]))
+    if (incx * incx > incy * incy) {
+        float oldX = fxi * best_match_x + cxi;
+        float nominator = (oldX * oTt[2] - oTt[0]);
+        float dot0 = DOT3(KinvP, ref.row0);
+        float dot2 = DOT3(KinvP, ref.row2);
+        idnew_best_match = (dot0 - oldX * dot2) / nominator;
+        alpha = incx * fxi * (dot0 * oTt[2] - dot2 * oTt[0]) / (nominator * nominator);
+    } else {
+        float oldY = fyi * best_match_y + cyi;
+        float nominator = (oldY * oTt[2] - oTt[1]);
+        float dot1 = DOT3(KinvP, ref.row1);
+        float dot2 = DOT3(KinvP, ref.row2);
+        idnew_best_match = (dot1 - oldY * dot2) / nominator;
+        alpha = incy * fyi * (dot1 * oTt[2] - dot2 * oTt[1]) / (nominator * nominator);
+    }
+#undef DOT3
+
+    if (idnew_best_match < 0) {
+        if (!G.allowNegativeIdepths) return -2;
+    }
+
+    float photoDispError = 4.0f * G.cameraPixelNoise2 / (gradAlongLine + DIVISION_EPS);
+    float trackingErrorFac = 0.25f * (1.0f + ref.initialTrackedResidual);
+
+    // getInterpolatedElement42(gradients(0), u, v): u, v are integer pixel coordinates here, the bilinear
+    // weights are (0,0,0,1); evaluated in the reference's order so that the value is bit-identical
+    float gI0, gI1;
+    {
+        int ix = (int)u, iy = (int)v;
+        float dx = u - ix, dy = v - iy;
+        float dxdy = dx * dy;
+        const float4* bp = kfGrad + ix + iy * width;
+        float4 br = __ldg(bp + 1 + width), bl = __ldg(bp + width), tr = __ldg(bp + 1), tl = __ldg(bp);
+        gI0 = dxdy * br.x + (dy - dxdy) * bl.x + (dx - dxdy) * tr.x + (1 - dx - dy + dxdy) * tl.x;
+        gI1 = dxdy * br.y + (dy - dxdy) * bl.y + (dx - dxdy) * tr.y + (1 - dx - dy + dxdy) * tl.y;
+    }
+    float geoDispError = (gI0 * epxn + gI1 * epyn) + DIVISION_EPS;
+    geoDispError = trackingErrorFac * trackingErrorFac * (gI0 * gI0 + gI1 * gI1) / (geoDispError * geoDispError);
+
+    result_var = alpha * alpha * ((didSubpixel ? 0.05f : 0.5f) * sampleDist * sampleDist + geoDispError + photoDispError);
+    result_idepth = idnew_best_match;
+    result_eplLength = eplLength;
+    return best_match_err;
+}
+
+// makeAndCheckEPL, DepthMap.cpp:184-234
+__device__ __forceinline__ bool makeAndCheckEPL(const DepthCam& cam, const float* __restrict__ kfImage, int x, int y,
+                                                const RefConst& ref, float& pepx, float& pepy)
+{
+    int idx = x + y * cam.w;
+    float epx = -cam.fx * ref.thisToOther_t[0] + ref.thisToOther_t[2] * (x - cam.cx);
+    float epy = -cam.fy * ref.thisToOther_t[1] + ref.thisToOther_t[2] * (y - cam.cy);
+    if (isnan(epx + epy)) return false;
+    float eplLengthSquared = epx * epx + epy * epy;
+    if (eplLengthSquared < MIN_EPL_LENGTH_SQUARED) return false;
+    float gx = kfImage[idx + 1] - kfImage[idx - 1];
+    float gy = kfImage[idx + cam.w] - kfImage[idx - cam.w];
+    float eplGradSquared = gx * epx + gy * epy;
+    eplGradSquared = eplGradSquared * eplGradSquared / eplLengthSquared;
+    if (eplGradSquared < MIN_EPL_GRAD_SQUARED) return false;
+    if (eplGradSquared / (gx * gx + gy * gy) < MIN_EPL_ANGLE_SQUARED) return false;
+    float fac = GRADIENT_SAMPLE_DIST / sqrtf(eplLengthSquared);
+    pepx = epx * fac;
+    pepy = epy * fac;
+    return true;
+}
+
+// observeDepthRow + Create + Update, DepthMap.cpp:111-146, 237-292, 294-473.  In place on `cur`: every
+// pixel touches only its own record.
+__global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, DepthGlobals G,
+                                                 const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
+                                                 const float* __restrict__ kfMaxGrad, const ObserveParams* __restrict__ OP)
+{
+    const int x = 3 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = 3 + blockIdx.y;
+    if (x >= cam.w - 3 || y >= cam.h - 3) return;
+    const int idx = x + y * cam.w;
+
+    int4 hiv = cur.hi[idx];
+    const bool hasHypothesis = hiv.x != 0;
+    const float mg = kfMaxGrad[idx];
+    if (hasHypothesis && mg < G.minUseGrad) {              // :125-129
+        hiv.x = 0;
+        cur.hi[idx] = hiv;
+        return;
+    }
+    if (mg < G.minUseGrad || hiv.y < MIN_BLACKLIST) return;   // :131-132
+
+    Hyp t = loadHyp(cur, idx);
+    int refIdx;
+    if (!hasHypothesis) {
+        refIdx = OP->reactivated ? OP->newestIdx : OP->oldestIdx;                 // :241
+    } else {
+        if (!OP->reactivated) {                                                   // :300-317
+            int rel = (int)t.nextStereoFrameMinID - OP->byIdOffset;
+            if (rel >= OP->byIdSize) return;
+            refIdx = rel < 0 ? OP->oldestIdx : OP->byId[rel];
+        } else
+            refIdx = OP->newestIdx;
+    }
+    const RefConst& ref = OP->refs[refIdx];
+
+    if (ref.trackedOnActive && ref.goodMask != nullptr &&
+        !ref.goodMask[(x >> SE3TRACKING_MIN_LEVEL) + (cam.w >> SE3TRACKING_MIN_LEVEL) * (y >> SE3TRACKING_MIN_LEVEL)])
+        return;                                                                    // :243-252 / :320-329
+
+    float epx, epy;
+    if (!makeAndCheckEPL(cam, kfImage, x, y, ref, epx, epy)) return;
+
+    float result_idepth = 0, result_var = 0, result_eplLength = 0;
+    if (!hasHypothesis) {
+        // observeDepthCreate :254-291
+        float error = doLineStereo(cam, G, kfImage, kfGrad, (float)x, (float)y, epx, epy, 0.0f, 1.0f, 1.0f / MIN_DEPTH,
+                                   ref, result_idepth, result_var, result_eplLength);
+        if (error == -3 || error == -2) {
+            t.blacklisted--;
+            hiv.y = t.blacklisted;
+            cur.hi[idx] = hiv;
+        }
+        if (error < 0 || result_var > MAX_VAR) return;
+        result_idepth = unzero_f(result_idepth);
+        hypCtor3(t, result_idepth, result_var, VALIDITY_COUNTER_INITIAL_OBSERVE);
+        storeHyp(cur, idx, t);
+        return;
+    }
+
+    // observeDepthUpdate :335-472
+    float sv = sqrtf(t.idepth_var_smoothed);
+    float min_idepth = t.idepth_smoothed - sv * STEREO_EPL_VAR_FAC;
+    float max_idepth = t.idepth_smoothed + sv * STEREO_EPL_VAR_FAC;
+    if (min_idepth < 0) min_idepth = 0;
+    if (max_idepth > 1 / MIN_DEPTH) max_idepth = 1 / MIN_DEPTH;
+
+    float error = doLineStereo(cam, G, kfImage, kfGrad, (float)x, (float)y, epx, epy, min_idepth, t.idepth_smoothed, max_idepth,
+                               ref, result_idepth, result_var, result_eplLength);
+    float diff = result_idepth - t.idepth_smoothed;
+
+    if (error == -1) return;
+    else if (error == -2) {
+        t.validity_counter -= VALIDITY_COUNTER_DEC;
+        if (t.validity_counter < 0) t.validity_counter = 0;
+        t.nextStereoFrameMinID = 0;
+        t.idepth_var *= FAIL_VAR_INC_FAC;
+        if (t.idepth_var > MAX_VAR) { t.isValid = 0; t.blacklisted--; }
+        storeHyp(cur, idx, t);
+        return;
+    } else if (error == -3) return;
+    else if (error == -4) return;
+    else if (DIFF_FAC_OBSERVE * diff * diff > result_var + t.idepth_var_smoothed) {
+        t.idepth_var *= FAIL_VAR_INC_FAC;
+        if (t.idepth_var > MAX_VAR) t.isValid = 0;
+        storeHyp(cur, idx, t);
+        return;
+    } else {
+        float id_var = t.idepth_var * SUCC_VAR_INC_FAC;
+        float w = result_var / (result_var + id_var);
+        float new_idepth = (1 - w) * result_idepth + w * t.idepth;
+        t.idepth = unzero_f(new_idepth);
+        id_var = id_var * w;
+        if (id_var < t.idepth_var) t.idepth_var = id_var;
+        t.validity_counter += VALIDITY_COUNTER_INC;
+        float absGrad = mg;
+        if (t.validity_counter > VALIDITY_COUNTER_MAX + absGrad * (VALIDITY_COUNTER_MAX_VARIABLE) / 255.0f)
+            t.validity_counter = VALIDITY_COUNTER_MAX + absGrad * (VALIDITY_COUNTER_MAX_VARIABLE) / 255.0f;
+        if (result_eplLength < MIN_EPL_LENGTH_CROP) {
+            float inc = OP->kfNumTracked / (float)(OP->kfNumMapped + 5);
+            if (inc < 3) inc = 3;
+            inc += ((int)(result_eplLength * 10000) % 2);
+            if (result_eplLength < 0.5 * MIN_EPL_LENGTH_CROP) inc *= 3;
+            t.nextStereoFrameMinID = ref.id + inc;
+        }
+        storeHyp(cur, idx, t);
+    }
+}
+
+// regularizeDepthMapFillHoles, DepthMap.cpp:656-718.  dst = src + created hypotheses.
+__global__ void __launch_bounds__(256) k_fill_holes(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
+                                                    const float* __restrict__ kfMaxGrad)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= cam.w || y >= cam.h) return;
+    const int width = cam.w;
+    const int idx = x + y * width;
+    float4 hf = src.hf[idx];
+    int4 hi = src.hi[idx];
+    if (x >= 3 && x < width - 2 && y >= 3 && y < cam.h - 2 && !hi.x && !(kfMaxGrad[idx] < G.minUseGrad)) {
+        // val = 5x5 sum of (isValid ? validity_counter : 0) == the integral-image lookup of :670-671
+        int val = 0;
+        for (int dy = -2; dy <= 2; dy++)
+            for (int dx = -2; dx <= 2; dx++) {
+                int4 s = src.hi[idx + dx + dy * width];
+                if (s.x) val += s.z;
+            }
+        if ((hi.y >= MIN_BLACKLIST && val > VAL_SUM_MIN_FOR_CREATE) || val > VAL_SUM_MIN_FOR_UNBLACKLIST) {
+            float sumIdepthObs = 0, sumIVarObs = 0;
+            for (int dy = -2; dy <= 2; dy++)             // row-major source order, :679-688
+                for (int dx = -2; dx <= 2; dx++) {
+                    int o = idx + dx + dy * width;
+                    if (!src.hi[o].x) continue;
+                    float4 s = src.hf[o];
+                    sumIdepthObs += s.x / s.y;
+                    sumIVarObs += 1.0f / s.y;
+                }
+            float idepthObs = sumIdepthObs / sumIVarObs;
+            idepthObs = unzero_f(idepthObs);
+            hf = make_float4(idepthObs, VAR_RANDOM_INIT_INITIAL, -1.f, -1.f);
+            hi = make_int4(1, 0, 0, __float_as_int(0.f));
+        }
+    }
+    dst.hf[idx] = hf;
+    dst.hi[idx] = hi;
+}
+
+// regularizeDepthMapRow<removeOcclusions>, DepthMap.cpp:758-848.  dst = src with smoothed values / removals.
+template <bool removeOcclusions>
+__global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G, int validityTH)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= cam.w || y >= cam.h) return;
+    const int width = cam.w;
+    const int idx = x + y * width;
+    float4 hf = src.hf[idx];
+    int4 hi = src.hi[idx];
+    if (x >= 2 && x < width - 2 && y >= 2 && y < cam.h - 2 && hi.x) {
+        const float regDistVar = G.regDistVar;
+        float sum = 0, val_sum = 0, sumIvar = 0;
+        int numOccluding = 0, numNotOccluding = 0;
+        for (int dx = -2; dx <= 2; dx++)                 // dx outer, dy inner as in the reference (:782-783)
+            for (int dy = -2; dy <= 2; dy++) {
+                int o = idx + dx + dy * width;
+                int4 si = src.hi[o];
+                if (!si.x) continue;
+                float4 s = src.hf[o];
+                float diff = s.x - hf.x;
+                if (DIFF_FAC_SMOOTHING * diff * diff > s.y + hf.y) {
+                    if (removeOcclusions) {
+                        if (s.x > hf.x) numOccluding++;
+                    }
+                    continue;
+                }
+                val_sum += si.z;
+                if (removeOcclusions) numNotOccluding++;
+                float distFac = (float)(dx * dx + dy * dy) * regDistVar;
+                float ivar = 1.0f / (s.y + distFac);
+                sum += s.x * ivar;
+                sumIvar += ivar;
+            }
+        if (val_sum < validityTH) {
+            hi.x = 0;
+            hi.y--;
+        } else if (removeOcclusions && numOccluding > numNotOccluding) {
+            hi.x = 0;
+        } else {
+            sum = sum / sumIvar;
+            sum = unzero_f(sum);
+            hf.z = sum;
+            hf.w = 1.0f / sumIvar;
+        }
+    }
+    dst.hf[idx] = hf;
+    dst.hi[idx] = hi;
+}
+
+// Frame::setDepth, Frame.cpp:199-243 (+ per-CTA partial sums of idepth_smoothed / count, combined in order)
+__global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restrict__ idepth, float* __restrict__ idepthVar,
+                                                   int n, double* __restrict__ partials)
+{
+    __shared__ double ssum[8];
+    __shared__ int scnt[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    int c = 0;
+    if (i < n) {
+        float4 hf = cur.hf[i];
+        int4 hi = cur.hi[i];
+        if (hi.x && hf.z >= -0.05) {
+            idepth[i] = hf.z;
+            idepthVar[i] = hf.w;
+            s = hf.z;
+            c = 1;
+        } else {
+            idepth[i] = -1;
+            idepthVar[i] = -1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0; int tc = 0;
+        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
+        partials[2 * blockIdx.x] = t;
+        partials[2 * blockIdx.x + 1] = (double)tc;
+    }
+}
+// sum of idepth_smoothed over valid hypotheses (createKeyFrame :1286-1293), same partial layout
+__global__ void __launch_bounds__(256) k_sum_idepth(HypField cur, int n, double* __restrict__ partials)
+{
+    __shared__ double ssum[8];
+    __shared__ int scnt[8];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0.0;
+    int c = 0;
+    if (i < n && cur.hi[i].x) { s = cur.hf[i].z; c = 1; }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0; int tc = 0;
+        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
+        partials[2 * blockIdx.x] = t;
+        partials[2 * blockIdx.x + 1] = (double)tc;
+    }
+}
+// ordered combine of the partials; out[0] = sum, out[1] = count, out[2] = rescaleFactor (float bits in double)
+__global__ void k_combine_partials(const double* __restrict__ partials, int nBlocks, double* __restrict__ out)
+{
+    __shared__ double ss[32], sc[32];
+    double s = 0, c = 0;
+    for (int b = threadIdx.x; b < nBlocks; b += 32) { s += partials[2 * b]; c += partials[2 * b + 1]; }
+    ss[threadIdx.x] = s; sc[threadIdx.x] = c;
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        double S = 0, Cn = 0;
+        for (int k = 0; k < 32; k++) { S += ss[k]; Cn += sc[k]; }
+        out[0] = S; out[1] = Cn;
+        float rescaleFactor = (float)Cn / (float)S;       // :1294 (float division of the float-typed sums)
+        out[2] = (double)rescaleFactor;
+    }
+}
+// createKeyFrame :1295-1304
+__global__ void __launch_bounds__(256) k_rescale(HypField cur, int n, const double* __restrict__ scal)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!cur.hi[i].x) return;
+    const float rescaleFactor = (float)scal[2];
+    const float rescaleFactor2 = rescaleFactor * rescaleFactor;
+    float4 hf = cur.hf[i];
+    hf.x *= rescaleFactor; hf.z *= rescaleFactor; hf.y *= rescaleFactor2; hf.w *= rescaleFactor2;
+    cur.hf[i] = hf;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// propagateDepth, DepthMap.cpp:475-653.  The reference is a serial raster scan whose result depends on the
+// ORDER in which sources hit a target.  Phase 1 projects every source and threads it onto a per-target list;
+// phase 2 (one thread per target) replays its sources in ascending source index == raster order.
+// ---------------------------------------------------------------------------------------------------------
+struct PropParams {
+    float R[9], t[3];
+    const uint8_t* trackingWasGood;   // new keyframe's refPixelWasGood (or nullptr)
+    const float* activeKFImage;
+    const float* newKFMaxGrad;
+    const float* newKFImage;
+};
+__global__ void __launch_bounds__(256) k_prop_project(HypField src, DepthCam cam, DepthGlobals G, PropParams P,
+                                                      int* __restrict__ head, int* __restrict__ next, float4* __restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int width = cam.w, height = cam.h;
+    if (i >= width * height) return;
+    int4 hi = src.hi[i];
+    if (!hi.x) return;
+    const int x = i % width, y = i / width;
+    float4 hf = src.hf[i];
+    float p0 = x * cam.fxi + cam.cxi, p1 = y * cam.fyi + cam.cyi, p2 = 1.0f;
+    float pn0 = ((P.R[0] * p0 + P.R[1] * p1) + P.R[2] * p2) / hf.z + P.t[0];
+    float pn1 = ((P.R[3] * p0 + P.R[4] * p1) + P.R[5] * p2) / hf.z + P.t[1];
+    float pn2 = ((P.R[6] * p0 + P.R[7] * p1) + P.R[8] * p2) / hf.z + P.t[2];
+    float new_idepth = 1.0f / pn2;
+    float u_new = pn0 * new_idepth * cam.fx + cam.cx;
+    float v_new = pn1 * new_idepth * cam.fy + cam.cy;
+    if (!(u_new > 2.1f && v_new > 2.1f && u_new < width - 3.1f && v_new < height - 3.1f)) return;
+    int newIDX = (int)(u_new + 0.5f) + ((int)(v_new + 0.5f)) * width;
+    float destAbsGrad = P.newKFMaxGrad[newIDX];
+    if (P.trackingWasGood != nullptr) {
+        if (!P.trackingWasGood[(x >> SE3TRACKING_MIN_LEVEL) + (width >> SE3TRACKING_MIN_LEVEL) * (y >> SE3TRACKING_MIN_LEVEL)]
+            || destAbsGrad < G.minUseGrad)
+            return;
+    } else {
+        float sourceColor = P.activeKFImage[i];
+        float destColor = interpF(P.newKFImage, u_new, v_new, width);
+        float residual = destColor - sourceColor;
+        if (residual * residual / (MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT * destAbsGrad * destAbsGrad) > 1.0f || destAbsGrad < G.minUseGrad)
+            return;
+    }
+    float idepth_ratio_4 = new_idepth / hf.z;
+    idepth_ratio_4 *= idepth_ratio_4;
+    idepth_ratio_4 *= idepth_ratio_4;
+    float new_var = idepth_ratio_4 * hf.y;
+    val[i] = make_float4(new_idepth, new_var, __int_as_float(hi.z), 0.f);
+    next[i] = atomicExch(head + newIDX, i);
+}
+__global__ void __launch_bounds__(256) k_prop_resolve(HypField dst, int n, const int* __restrict__ head,
+                                                      const int* __restrict__ next, const float4* __restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Hyp t;
+    t.isValid = 0; t.blacklisted = 0; t.validity_counter = 0; t.nextStereoFrameMinID = 0;      // :496-500
+    t.idepth = 0; t.idepth_var = 0; t.idepth_smoothed = 0; t.idepth_var_smoothed = 0;
+    const int h0 = head[i];
+    int last = -1;
+    while (h0 >= 0) {
+        // next source in raster order: the smallest list entry larger than `last`
+        int best = 0x7fffffff;
+        for (int s = h0; s >= 0; s = next[s])
+            if (s > last && s < best) best = s;
+        if (best == 0x7fffffff) break;
+        last = best;
+        const float4 sv = val[best];
+        const float new_idepth = sv.x, new_var = sv.y;
+        const int src_validity = __float_as_int(sv.z);
+        bool skip = false;
+        if (t.isValid) {                                                         // :584-603
+            float diff = t.idepth - new_idepth;
+            if (DIFF_FAC_PROP_MERGE * diff * diff > new_var + t.idepth_var) {
+                if (new_idepth < t.idepth) skip = true;
+                else t.isValid = 0;
+            }
+        }
+        if (skip) continue;
+        if (!t.isValid) {
+            hypCtor3(t, new_idepth, new_var, src_validity);                      // :606-615
+        } else {
+            float w = new_var / (t.idepth_var + new_var);                        // :616-633
+            float merged_new_idepth = w * t.idepth + (1.0f - w) * new_idepth;
+            int merged_validity = src_validity + t.validity_counter;
+            if (merged_validity > VALIDITY_COUNTER_MAX + (VALIDITY_COUNTER_MAX_VARIABLE))
+                merged_validity = VALIDITY_COUNTER_MAX + (VALIDITY_COUNTER_MAX_VARIABLE);
+            float mv = 1.0f / (1.0f / t.idepth_var + 1.0f / new_var);
+            hypCtor3(t, merged_new_idepth, mv, merged_validity);
+        }
+    }
+    storeHyp(dst, i, t);
+}
+
+// initializeFromGTDepth, DepthMap.cpp:993-1014: hypotheses from the keyframe's level-0 idepth
+__global__ void __launch_bounds__(256) k_init_from_gt(HypField cur, const float* __restrict__ idepth, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = idepth[i];
+    int4 hi = cur.hi[i];
+    float4 hf = cur.hf[i];
+    if (!isnan(v) && v > 0) {
+        hf = make_float4(v, 0.01f * 0.01f, v, 0.01f * 0.01f);
+        hi = make_int4(1, 0, 20, __float_as_int(0.f));
+    } else {
+        hi.x = 0;
+        hi.y = 0;
+    }
+    cur.hf[i] = hf;
+    cur.hi[i] = hi;
+}
+
+// AoS (reference layout) <-> the two 16-byte planes
+__global__ void __launch_bounds__(256) k_hyp_from_aos(const lsdgpu_hyp* __restrict__ aos, HypField f, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    lsdgpu_hyp h = aos[i];
+    f.hf[i] = make_float4(h.idepth, h.idepth_var, h.idepth_smoothed, h.idepth_var_smoothed);
+    f.hi[i] = make_int4(h.isValid ? 1 : 0, h.blacklisted, h.validity_counter, __float_as_int(h.nextStereoFrameMinID));
+}
+__global__ void __launch_bounds__(256) k_hyp_to_aos(HypField f, lsdgpu_hyp* __restrict__ aos, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = f.hf[i];
+    int4 b = f.hi[i];
+    lsdgpu_hyp h;
+    h.isValid = b.x ? 1 : 0; h._pad[0] = h._pad[1] = h._pad[2] = 0;
+    h.blacklisted = b.y; h.nextStereoFrameMinID = __int_as_float(b.w); h.validity_counter = b.z;
+    h.idepth = a.x; h.idepth_var = a.y; h.idepth_smoothed = a.z; h.idepth_var_smoothed = a.w;
+    aos[i] = h;
+}
+
+// validityIntegralBuffer on demand (parity hook only; the hot path never builds it), DepthMap.cpp:722-754
+__global__ void k_integral_rows(HypField cur, int* __restrict__ integral, int w, int h)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y >= h) return;
+    int s = 0;
+    for (int x = 0; x < w; x++) {
+        int4 hi = cur.hi[y * w + x];
+        if (hi.x) s += hi.z;
+        integral[y * w + x] = s;
+    }
+}
+__global__ void k_integral_cols(int* __restrict__ integral, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= w) return;
+    int s = integral[x];
+    for (int y = 1; y < h; y++) {
+        s += integral[y * w + x];
+        integral[y * w + x] = s;
+    }
+}

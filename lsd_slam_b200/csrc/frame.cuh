@@ -1,0 +1,184 @@
+// frame.cuh -- per-frame staging kernels: u8 -> f32 image pyramid, gradient pyramid, maxGradients,
+// ground-truth depth import and the idepth / idepthVar pyramids.
+//
+// Replaces (paths relative to lsd_slam_core/src/):
+//   Frame::Frame(.., const uchar*)        DataStructures/Frame.cpp:35-54
+//   Frame::buildImage                     DataStructures/Frame.cpp:491-630
+//   Frame::buildGradients                 DataStructures/Frame.cpp:643-680
+//   Frame::buildMaxGradients              DataStructures/Frame.cpp:690-767
+//   Frame::setDepthFromGroundTruth        DataStructures/Frame.cpp:245-293
+//   Frame::buildIDepthAndIDepthVar        DataStructures/Frame.cpp:775-877
+// All of these are streaming, HBM-bound passes over at most 16 B/px; the whole pyramid of one frame is built
+// by ONE launch per pass (the reference builds level by level, lazily).
+#pragma once
+#include "internal.cuh"
+
+struct PyrPtrs {
+    float* l[LSD_LEVELS];
+};
+struct GradPtrs {
+    const float* img[LSD_LEVELS];
+    float4* grad[LSD_LEVELS];
+    int w[LSD_LEVELS], h[LSD_LEVELS];
+};
+
+// One CTA = one 16x16 level-0 tile -> 8x8, 4x4, 2x2, 1x1 on levels 1..4 (w, h are multiples of 16,
+// SlamSystem.cpp:55).  The 2x2 box sum is exact in fp32 for u8-origin data and is
+// associated like the scalar loop (Frame.cpp:621-624).
+__global__ void __launch_bounds__(256) k_image_pyramid(const uint8_t* __restrict__ src, PyrPtrs p, int w, int h)
+{
+    __shared__ float s0[16][17], s1[8][9], s2[4][5], s3[2][3];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const int x = bx * 16 + tx, y = by * 16 + ty;
+    float v = (float)src[y * w + x];
+    p.l[0][y * w + x] = v;
+    s0[ty][tx] = v;
+    __syncthreads();
+    if (tx < 8 && ty < 8) {
+        float a = (s0[2 * ty][2 * tx] + s0[2 * ty][2 * tx + 1] + s0[2 * ty + 1][2 * tx] + s0[2 * ty + 1][2 * tx + 1]) * 0.25f;
+        s1[ty][tx] = a;
+        p.l[1][(by * 8 + ty) * (w >> 1) + bx * 8 + tx] = a;
+    }
+    __syncthreads();
+    if (tx < 4 && ty < 4) {
+        float a = (s1[2 * ty][2 * tx] + s1[2 * ty][2 * tx + 1] + s1[2 * ty + 1][2 * tx] + s1[2 * ty + 1][2 * tx + 1]) * 0.25f;
+        s2[ty][tx] = a;
+        p.l[2][(by * 4 + ty) * (w >> 2) + bx * 4 + tx] = a;
+    }
+    __syncthreads();
+    if (tx < 2 && ty < 2) {
+        float a = (s2[2 * ty][2 * tx] + s2[2 * ty][2 * tx + 1] + s2[2 * ty + 1][2 * tx] + s2[2 * ty + 1][2 * tx + 1]) * 0.25f;
+        s3[ty][tx] = a;
+        p.l[3][(by * 2 + ty) * (w >> 3) + bx * 2 + tx] = a;
+    }
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+        float a = (s3[0][0] + s3[0][1] + s3[1][0] + s3[1][1]) * 0.25f;
+        p.l[4][by * (w >> 4) + bx] = a;
+    }
+}
+
+// Gradients of all levels in one launch (blockIdx.y = level).  The reference sweeps the LINEAR index range
+// [w, w*(h-1)) so x = 0 and x = w-1 wrap across rows (Frame.cpp:658-677); rows 0 and h-1 are defined as zero.
+__global__ void __launch_bounds__(256) k_gradients(const __grid_constant__ GradPtrs p)
+{
+    const int lvl = blockIdx.y;
+    const int w = p.w[lvl], h = p.h[lvl];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const float* __restrict__ img = p.img[lvl];
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i >= w && i < w * (h - 1)) {
+        g.x = 0.5f * (img[i + 1] - img[i - 1]);
+        g.y = 0.5f * (img[i + w] - img[i - w]);
+        g.z = img[i];
+    }
+    p.grad[lvl][i] = g;
+}
+
+// maxGradients at level 0: |grad| then a 3x1 vertical and a 1x3 horizontal max, all over LINEAR index ranges
+// (Frame.cpp:708-759) with never-written cells defined as zero.
+__device__ __forceinline__ float absGradAt(const float4* __restrict__ grad, int j, int w, int h)
+{
+    if (j < w || j >= w * (h - 1)) return 0.f;
+    float4 g = __ldg(grad + j);
+    return sqrtf(g.x * g.x + g.y * g.y);
+}
+__device__ __forceinline__ float vmax3At(const float4* __restrict__ grad, int t, int w, int h)
+{
+    if (t < w + 1 || t >= w * (h - 1) - 1) return 0.f;
+    float g1 = absGradAt(grad, t - w, w, h), g2 = absGradAt(grad, t, w, h), g3 = absGradAt(grad, t + w, w, h);
+    if (g1 < g2) g1 = g2;
+    return (g1 < g3) ? g3 : g1;
+}
+__global__ void __launch_bounds__(256) k_maxgrad(const float4* __restrict__ grad, float* __restrict__ out, int w, int h)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    float r;
+    if (i >= w + 1 && i < w * (h - 1) - 1) {
+        float g1 = vmax3At(grad, i - 1, w, h), g2 = vmax3At(grad, i, w, h), g3 = vmax3At(grad, i + 1, w, h);
+        if (g1 < g2) g1 = g2;
+        r = (g1 < g3) ? g3 : g1;
+    } else {
+        r = absGradAt(grad, i, w, h);    // cells w and w*(h-1)-1 keep the raw |grad| of pass 1
+    }
+    out[i] = r;
+}
+
+// Frame::setDepthFromGroundTruth, Frame.cpp:264-285
+__global__ void __launch_bounds__(256) k_set_depth_gt(const float* __restrict__ depth, const float* __restrict__ maxgrad,
+                                                      float* __restrict__ idepth, float* __restrict__ idepthVar,
+                                                      int w, int h, float minUseGrad, float cov_scale)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w * h) return;
+    const int x = i % w, y = i / w;
+    const float d = depth[i];
+    if (x > 0 && x < w - 1 && y > 0 && y < h - 1 && maxgrad[i] >= minUseGrad && !isnan(d) && d > 0) {
+        idepth[i] = 1.0f / d;
+        idepthVar[i] = 0.01f * 0.01f * cov_scale;     // VAR_GT_INIT_INITIAL * cov_scale
+    } else {
+        idepth[i] = -1;
+        idepthVar[i] = -1;
+    }
+}
+
+// Frame::buildIDepthAndIDepthVar for levels 1..4 in one launch: one CTA = one 16x16 level-0 tile.
+__device__ __forceinline__ float2 mergeIdepth4(float2 a, float2 b, float2 c, float2 d)
+{   // Frame.cpp:819-871, sources visited in the order idx, idx+1, idx+sw, idx+sw+1; .x = idepth, .y = var
+    float idepthSumsSum = 0, ivarSumsSum = 0;
+    int num = 0;
+    float2 s[4] = { a, b, c, d };
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float var = s[k].y;
+        if (var > 0) {
+            float ivar = 1.0f / var;
+            ivarSumsSum += ivar;
+            idepthSumsSum += ivar * s[k].x;
+            num++;
+        }
+    }
+    if (num > 0) {
+        float depth = ivarSumsSum / idepthSumsSum;
+        return make_float2(1.0f / depth, num / ivarSumsSum);
+    }
+    return make_float2(-1.f, -1.f);
+}
+__global__ void __launch_bounds__(256) k_idepth_pyramid(PyrPtrs id, PyrPtrs var, int w, int h)
+{
+    __shared__ float2 s0[16][17], s1[8][9], s2[4][5], s3[2][3];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int bx = blockIdx.x, by = blockIdx.y;
+    const int x = bx * 16 + tx, y = by * 16 + ty;
+    s0[ty][tx] = make_float2(id.l[0][y * w + x], var.l[0][y * w + x]);
+    __syncthreads();
+    if (tx < 8 && ty < 8) {
+        float2 r = mergeIdepth4(s0[2 * ty][2 * tx], s0[2 * ty][2 * tx + 1], s0[2 * ty + 1][2 * tx], s0[2 * ty + 1][2 * tx + 1]);
+        s1[ty][tx] = r;
+        int o = (by * 8 + ty) * (w >> 1) + bx * 8 + tx;
+        id.l[1][o] = r.x; var.l[1][o] = r.y;
+    }
+    __syncthreads();
+    if (tx < 4 && ty < 4) {
+        float2 r = mergeIdepth4(s1[2 * ty][2 * tx], s1[2 * ty][2 * tx + 1], s1[2 * ty + 1][2 * tx], s1[2 * ty + 1][2 * tx + 1]);
+        s2[ty][tx] = r;
+        int o = (by * 4 + ty) * (w >> 2) + bx * 4 + tx;
+        id.l[2][o] = r.x; var.l[2][o] = r.y;
+    }
+    __syncthreads();
+    if (tx < 2 && ty < 2) {
+        float2 r = mergeIdepth4(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1], s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]);
+        s3[ty][tx] = r;
+        int o = (by * 2 + ty) * (w >> 3) + bx * 2 + tx;
+        id.l[3][o] = r.x; var.l[3][o] = r.y;
+    }
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+        float2 r = mergeIdepth4(s3[0][0], s3[0][1], s3[1][0], s3[1][1]);
+        int o = by * (w >> 4) + bx;
+        id.l[4][o] = r.x; var.l[4][o] = r.y;
+    }
+}

@@ -1,0 +1,213 @@
+// hostmath.h -- Eigen-free host/device math for the LSD-SLAM hot path: SE3 (unit quaternion + translation)
+// in float and double, Sim3 helpers, 3x3 inverse, pivoted 6x6 LDL^T.
+//
+// Mirrors what the reference gets from Sophus/Eigen:
+//   SE3Group::exp / operator* / inverse      thirdparty/Sophus/sophus/se3.hpp:406-428, 239-259, 167-172
+//   SO3Group::expAndTheta / normalize        thirdparty/Sophus/sophus/so3.hpp:342-369, 196-202
+//   A.ldlt().solve(b)                        Tracking/SE3Tracker.cpp:359 (Eigen LDLT, diagonal pivoting)
+//   K.inverse()                              Tracking/SE3Tracker.cpp:60, DataStructures/Frame.cpp:409,453
+// Usable from host and device code (the device-resident LM loop solves and updates the pose on the GPU).
+#pragma once
+
+#include <math.h>
+
+#ifdef __CUDACC__
+#define LSD_HD __host__ __device__ __forceinline__
+#else
+#define LSD_HD inline
+#endif
+
+namespace lsd {
+
+template <typename T> struct MathFn;
+template <> struct MathFn<float> {
+    static LSD_HD float sqrt_(float x) { return sqrtf(x); }
+    static LSD_HD float sin_(float x) { return sinf(x); }
+    static LSD_HD float cos_(float x) { return cosf(x); }
+    static LSD_HD float eps() { return 1e-5f; }          // SophusConstants<float>::epsilon, sophus.hpp:52-56
+};
+template <> struct MathFn<double> {
+    static LSD_HD double sqrt_(double x) { return sqrt(x); }
+    static LSD_HD double sin_(double x) { return sin(x); }
+    static LSD_HD double cos_(double x) { return cos(x); }
+    static LSD_HD double eps() { return 1e-10; }          // sophus.hpp:43-47
+};
+
+// q = (x, y, z, w) like Eigen::Quaternion::coeffs()
+template <typename T> struct SE3 {
+    T q[4];
+    T t[3];
+    LSD_HD SE3() { q[0] = q[1] = q[2] = 0; q[3] = 1; t[0] = t[1] = t[2] = 0; }
+};
+
+template <typename T> LSD_HD void quatNormalize(T q[4])
+{
+    T len = MathFn<T>::sqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= len; q[1] /= len; q[2] /= len; q[3] /= len;
+}
+
+template <typename T> LSD_HD void quatMul(const T a[4], const T b[4], T o[4])
+{
+    T w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    T x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    T y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    T z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+
+// v' = q v q*   (Eigen's _transformVector: two cross products)
+template <typename T> LSD_HD void quatRotate(const T q[4], const T v[3], T o[3])
+{
+    T ux = q[1] * v[2] - q[2] * v[1], uy = q[2] * v[0] - q[0] * v[2], uz = q[0] * v[1] - q[1] * v[0];
+    ux += ux; uy += uy; uz += uz;
+    T cx = q[1] * uz - q[2] * uy, cy = q[2] * ux - q[0] * uz, cz = q[0] * uy - q[1] * ux;
+    o[0] = v[0] + q[3] * ux + cx;
+    o[1] = v[1] + q[3] * uy + cy;
+    o[2] = v[2] + q[3] * uz + cz;
+}
+
+template <typename T> LSD_HD void quatToMatrix(const T q[4], T R[9])
+{
+    T tx = 2 * q[0], ty = 2 * q[1], tz = 2 * q[2];
+    T twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+    T txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+    T tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+template <typename T> LSD_HD SE3<T> se3Mul(const SE3<T>& a, const SE3<T>& b)
+{
+    SE3<T> r;
+    T rt[3];
+    quatRotate(a.q, b.t, rt);
+    quatMul(a.q, b.q, r.q);
+    quatNormalize(r.q);
+    r.t[0] = a.t[0] + rt[0]; r.t[1] = a.t[1] + rt[1]; r.t[2] = a.t[2] + rt[2];
+    return r;
+}
+
+template <typename T> LSD_HD SE3<T> se3Inverse(const SE3<T>& a)
+{
+    SE3<T> r;
+    r.q[0] = -a.q[0]; r.q[1] = -a.q[1]; r.q[2] = -a.q[2]; r.q[3] = a.q[3];
+    quatNormalize(r.q);
+    T nt[3] = { a.t[0] * (T)-1, a.t[1] * (T)-1, a.t[2] * (T)-1 };
+    quatRotate(r.q, nt, r.t);
+    return r;
+}
+
+// exp of a twist a = [upsilon | omega]
+template <typename T> LSD_HD SE3<T> se3Exp(const T a[6])
+{
+    typedef MathFn<T> M;
+    const T* om = a + 3;
+    T theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    T theta = M::sqrt_(theta_sq);
+    T half_theta = (T)0.5 * theta;
+    T imag, real;
+    if (theta < M::eps()) {
+        T theta_po4 = theta_sq * theta_sq;
+        imag = (T)0.5 - (T)(1.0 / 48.0) * theta_sq + (T)(1.0 / 3840.0) * theta_po4;
+        real = (T)1 - (T)0.5 * theta_sq + (T)(1.0 / 384.0) * theta_po4;
+    } else {
+        imag = M::sin_(half_theta) / theta;
+        real = M::cos_(half_theta);
+    }
+    SE3<T> r;
+    r.q[0] = imag * om[0]; r.q[1] = imag * om[1]; r.q[2] = imag * om[2]; r.q[3] = real;
+    quatNormalize(r.q);
+    T Om[9] = { 0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0 };
+    T Om2[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            Om2[i * 3 + j] = (Om[i * 3 + 0] * Om[0 * 3 + j] + Om[i * 3 + 1] * Om[1 * 3 + j]) + Om[i * 3 + 2] * Om[2 * 3 + j];
+    T V[9];
+    if (theta < M::eps()) {
+        quatToMatrix(r.q, V);
+    } else {
+        T c1 = ((T)1 - M::cos_(theta)) / theta_sq;
+        T c2 = (theta - M::sin_(theta)) / (theta_sq * theta);
+        for (int i = 0; i < 9; i++) V[i] = (((i % 4) == 0 ? (T)1 : (T)0) + c1 * Om[i]) + c2 * Om2[i];
+    }
+    for (int i = 0; i < 3; i++) r.t[i] = (V[i * 3 + 0] * a[0] + V[i * 3 + 1] * a[1]) + V[i * 3 + 2] * a[2];
+    return r;
+}
+
+// SE3::cast<>() : component-wise cast followed by the normalising constructor
+template <typename To, typename From> LSD_HD SE3<To> se3Cast(const SE3<From>& a)
+{
+    SE3<To> r;
+    for (int i = 0; i < 4; i++) r.q[i] = (To)a.q[i];
+    quatNormalize(r.q);
+    for (int i = 0; i < 3; i++) r.t[i] = (To)a.t[i];
+    return r;
+}
+
+// cofactor inverse of a row-major 3x3 (what Eigen does for fixed size 3)
+LSD_HD void mat3Inverse(const float m[9], float r[9])
+{
+    float c00 = m[4] * m[8] - m[5] * m[7];
+    float c10 = m[7] * m[2] - m[8] * m[1];   // cofactor (1,0): rows 2,0 / cols 1,2
+    float c20 = m[1] * m[5] - m[2] * m[4];
+    float det = (c00 * m[0] + c10 * m[3]) + c20 * m[6];
+    float inv = 1.0f / det;
+    r[0] = c00 * inv; r[1] = c10 * inv; r[2] = c20 * inv;
+    r[3] = (m[5] * m[6] - m[3] * m[8]) * inv;
+    r[4] = (m[8] * m[0] - m[6] * m[2]) * inv;
+    r[5] = (m[2] * m[3] - m[0] * m[5]) * inv;
+    r[6] = (m[3] * m[7] - m[4] * m[6]) * inv;
+    r[7] = (m[6] * m[1] - m[7] * m[0]) * inv;
+    r[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
+}
+
+// x = A^-1 b for a symmetric 6x6 via LDL^T with largest-diagonal pivoting (float)
+LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6])
+{
+    const int N = 6;
+    float A[6][6];
+    int tr[6];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) A[i][j] = Ain[i * N + j];
+    for (int k = 0; k < N; k++) {
+        int p = k;
+        float big = fabsf(A[k][k]);
+        for (int i = k + 1; i < N; i++)
+            if (fabsf(A[i][i]) > big) { big = fabsf(A[i][i]); p = i; }
+        tr[k] = p;
+        if (p != k) {
+            for (int j = 0; j < k; j++) { float t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
+            for (int i = p + 1; i < N; i++) { float t = A[i][k]; A[i][k] = A[i][p]; A[i][p] = t; }
+            for (int i = k + 1; i < p; i++) { float t = A[i][k]; A[i][k] = A[p][i]; A[p][i] = t; }
+            float t = A[k][k]; A[k][k] = A[p][p]; A[p][p] = t;
+        }
+        if (k > 0) {
+            float temp[6];
+            for (int j = 0; j < k; j++) temp[j] = A[j][j] * A[k][j];
+            float s = 0;
+            for (int j = 0; j < k; j++) s += A[k][j] * temp[j];
+            A[k][k] -= s;
+            for (int i = k + 1; i < N; i++) {
+                float u = 0;
+                for (int j = 0; j < k; j++) u += A[i][j] * temp[j];
+                A[i][k] -= u;
+            }
+        }
+        float d = A[k][k];
+        if (fabsf(d) > 0)
+            for (int i = k + 1; i < N; i++) A[i][k] /= d;
+    }
+    float y[6];
+    for (int i = 0; i < N; i++) y[i] = bin[i];
+    for (int k = 0; k < N; k++)
+        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < N; i++) { float s = y[i]; for (int j = 0; j < i; j++) s -= A[i][j] * y[j]; y[i] = s; }
+    for (int i = 0; i < N; i++) { float d = A[i][i]; y[i] = (fabsf(d) > 1.17549435e-38f) ? y[i] / d : 0.0f; }
+    for (int i = N - 1; i >= 0; i--) { float s = y[i]; for (int j = i + 1; j < N; j++) s -= A[j][i] * y[j]; y[i] = s; }
+    for (int k = N - 1; k >= 0; k--)
+        if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
+    for (int i = 0; i < N; i++) x[i] = y[i];
+}
+
+}  // namespace lsd

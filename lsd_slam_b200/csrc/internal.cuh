@@ -1,0 +1,176 @@
+// internal.cuh -- context, device layouts and launch helpers of liblsdgpu (not part of the ABI).
+//
+// Data layout in HBM:
+//   * one arena per context, carved into `max_frames` frame slots + one depth map + tracker scratch;
+//   * frame slot: image pyramid f32 planar L0..L4, gradient pyramid float4 (dx,dy,I,0) L0..L4,
+//     maxGradients L0 f32, idepth / idepthVar pyramids f32 L0..L4, refPixelWasGood u8 at L1;
+//   * depth map: two ping-pong copies (current / other) of the hypothesis field, each as two 16-byte planes
+//       hf = float4(idepth, idepth_var, idepth_smoothed, idepth_var_smoothed)
+//       hi = int4  (isValid, blacklisted, validity_counter, bits(nextStereoFrameMinID))
+//     (the reference's 32-byte AoS record split in halves, so that every access is one 128-bit transaction),
+//     plus the int32 validity integral image.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/lsdgpu.h"
+#include "hostmath.h"
+
+#define LSD_LEVELS LSDGPU_LEVELS
+#define SE3TRACKING_MIN_LEVEL 1
+#define SE3TRACKING_MAX_LEVEL 5
+
+struct LevelCam {
+    int w, h;
+    float fx, fy, cx, cy;
+    float fxi, fyi, cxi, cyi;
+    float K[9], KInv[9];
+};
+
+struct FrameSlot {
+    int id = -1;
+    bool used = false;
+    float* image[LSD_LEVELS];
+    float4* grad[LSD_LEVELS];
+    float* maxgrad;
+    float* idepth[LSD_LEVELS];
+    float* idepthVar[LSD_LEVELS];
+    uint8_t* goodMask;
+    bool hasDepth = false, idepthPyrValid = false, hasGoodMask = false;
+    bool depthHasBeenUpdatedFlag = false;
+    float meanIdepth = 1.f;
+    int numPoints = 0;
+    double thisToParent[8];
+    int parentId = -1;
+    float initialTrackedResidual = 0.f;
+    int numFramesTrackedOnThis = 0, numMappedOnThis = 0;
+};
+
+struct HypField {
+    float4* hf;
+    int4* hi;
+};
+
+// per reference-frame constants of Frame::prepareForStereoWith (Frame.cpp:295-317) + what observeDepth reads
+struct RefConst {
+    float K_otherToThis_R[9];
+    float K_otherToThis_t[3];
+    float otherToThis_t[3];
+    float thisToOther_t[3];
+    float row0[3], row1[3], row2[3];
+    float initialTrackedResidual;
+    int id;
+    int trackedOnActive;          // refFrame->getTrackingParent() == activeKeyFrame
+    const float* image;           // level 0
+    const uint8_t* goodMask;      // refPixelWasGoodNoCreate() or nullptr
+};
+#define LSD_MAX_REFS 64
+struct ObserveParams {
+    RefConst refs[LSD_MAX_REFS];
+    int nRefs;
+    int byIdOffset, byIdSize;     // referenceFrameByID_offset / size
+    int byId[256];                // id - offset -> index into refs
+    int oldestIdx, newestIdx;
+    int reactivated;
+    int kfNumTracked, kfNumMapped;
+};
+
+// number of reduction channels of one tracker evaluation (see track.cuh)
+#define EV_NCH 44
+
+struct lsdgpu_ctx {
+    int device = 0;
+    int w = 0, h = 0;
+    LevelCam cam[LSD_LEVELS];
+    lsdgpu_globals g;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    long long launches = 0;
+    int smCount = 148;
+
+    char* arena = nullptr;
+    size_t arenaBytes = 0;
+    std::vector<FrameSlot> slots;
+
+    // depth map
+    HypField cur, oth;
+    int* integral = nullptr;
+    int activeKf = -1;
+    bool activeKfReactivated = false;
+    ObserveParams* dObs = nullptr;       // device copy
+    ObserveParams* hObs = nullptr;       // pinned host staging
+    int* propHead = nullptr;             // per-target list heads (propagateDepth)
+    int* propNext = nullptr;
+    float4* propVal = nullptr;           // per-source (new_idepth, new_var, validity, -)
+    double* dScalars = nullptr;          // small device scratch for reductions (sum, count)
+    double* hScalars = nullptr;          // pinned mirror
+
+    // tracker scratch
+    float* evPartials = nullptr;         // [maxBlocks][EV_NCH]
+    unsigned int* evCounter = nullptr;
+    float* dEvOut = nullptr;             // EV_NCH floats (device)
+    float* hEvOut = nullptr;             // pinned host mirror
+    void* dTrackState = nullptr;         // persistent-kernel state block (device)
+    void* hTrackState = nullptr;         // pinned mirror
+    uint8_t* hStage = nullptr;           // pinned staging for the u8 frame upload
+    uint8_t* dStageU8 = nullptr;
+    float* hStageF = nullptr;            // pinned float staging (depth / idepth uploads)
+    float* dStageF = nullptr;
+
+    // timers
+    cudaEvent_t tBegin[8], tEnd[8];
+    cudaEvent_t kBegin, kEnd;
+    double trackKernelMs = 0;
+    long long trackKernelLaunches = 0;
+    double trackKernelBytes = 0;
+    bool profileTrackKernel = false;
+};
+
+#define LSD_CHECK(ctx, expr)                                                                              \
+    do {                                                                                                  \
+        cudaError_t _e = (expr);                                                                          \
+        if (_e != cudaSuccess) {                                                                          \
+            char _b[512];                                                                                 \
+            snprintf(_b, sizeof(_b), "%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            (ctx)->err = _b;                                                                              \
+            return -1;                                                                                    \
+        }                                                                                                 \
+    } while (0)
+
+static inline int lsd_fail(lsdgpu_ctx* ctx, const char* msg)
+{
+    ctx->err = msg;
+    return -2;
+}
+
+static inline FrameSlot* findSlot(lsdgpu_ctx* ctx, int id)
+{
+    for (auto& s : ctx->slots)
+        if (s.used && s.id == id) return &s;
+    return nullptr;
+}
+
+static inline int divUp(int a, int b) { return (a + b - 1) / b; }
+
+// ---- device helpers shared by all kernels --------------------------------------------------------------
+// util/settings.h:34-35.  UNZERO mixes float and double literals; every use converts back to float.
+__device__ __forceinline__ float unzero_f(float val)
+{
+    double r = (val < 0 ? (val > -1e-10 ? -1e-10 : (double)val) : (val < 1e-10 ? 1e-10 : (double)val));
+    return (float)r;
+}
+
+// util/globalFuncs.h:43-61 -- weights formed and summed in the reference's order (br, bl, tr, tl)
+__device__ __forceinline__ float interpF(const float* __restrict__ mat, float x, float y, int width)
+{
+    int ix = (int)x, iy = (int)y;
+    float dx = x - ix, dy = y - iy;
+    float dxdy = dx * dy;
+    const float* bp = mat + ix + iy * width;
+    return dxdy * __ldg(bp + 1 + width) + (dy - dxdy) * __ldg(bp + width) + (dx - dxdy) * __ldg(bp + 1) + (1 - dx - dy + dxdy) * __ldg(bp);
+}

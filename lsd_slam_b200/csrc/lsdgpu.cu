@@ -1,0 +1,909 @@
+// lsdgpu.cu -- C ABI (include/lsdgpu.h) over the sm_100a kernels in frame.cuh / track.cuh / depth.cuh.
+// Host-side control flow mirrors SE3Tracker::trackFrame (Tracking/SE3Tracker.cpp:280-486) and
+// DepthMap::updateKeyframe / createKeyFrame / finalizeKeyFrame (DepthEstimation/DepthMap.cpp:1072-1395).
+#include "internal.cuh"
+#include "frame.cuh"
+#include "track.cuh"
+#include "depth.cuh"
+#include "track_persistent.cuh"
+
+#include <algorithm>
+#include <new>
+
+#define LAUNCH(ctx) ((ctx)->launches++)
+
+// ------------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lsdgpu_abi_version(void) { return LSDGPU_ABI_VERSION; }
+
+extern "C" void lsdgpu_default_globals(lsdgpu_globals* g)
+{
+    g->minUseGrad = 5; g->cameraPixelNoise2 = 4 * 4; g->depthSmoothingFactor = 1;
+    g->allowNegativeIdepths = 1; g->useSubpixelStereo = 1; g->useAffineLightningEstimation = 1;
+}
+
+extern "C" void lsdgpu_default_track_settings(lsdgpu_track_settings* s)
+{
+    static const int maxIterations[6] = { 5, 20, 50, 100, 100, 100 };
+    s->lambdaSuccessFac = 0.5f; s->lambdaFailFac = 2.0f;
+    for (int l = 0; l < LSD_LEVELS; l++) {
+        s->lambdaInitial[l] = 0; s->stepSizeMin[l] = 1e-8f; s->convergenceEps[l] = 0.999f;
+        s->maxItsPerLvl[l] = maxIterations[l];
+    }
+    s->var_weight = 1.0f; s->huber_d = 3;
+}
+
+static size_t alignUp(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static void setupCams(lsdgpu_ctx* ctx, const float K[9])
+{   // Frame::initialize, DataStructures/Frame.cpp:403-459
+    LevelCam& c0 = ctx->cam[0];
+    memcpy(c0.K, K, 36);
+    c0.w = ctx->w; c0.h = ctx->h;
+    c0.fx = K[0]; c0.fy = K[4]; c0.cx = K[2]; c0.cy = K[5];
+    lsd::mat3Inverse(c0.K, c0.KInv);
+    c0.fxi = c0.KInv[0]; c0.fyi = c0.KInv[4]; c0.cxi = c0.KInv[2]; c0.cyi = c0.KInv[5];
+    for (int l = 1; l < LSD_LEVELS; l++) {
+        LevelCam& c = ctx->cam[l];
+        c.w = ctx->w >> l; c.h = ctx->h >> l;
+        c.fx = (float)(ctx->cam[l - 1].fx * 0.5);
+        c.fy = (float)(ctx->cam[l - 1].fy * 0.5);
+        c.cx = (float)((c0.cx + 0.5) / ((int)1 << l) - 0.5);
+        c.cy = (float)((c0.cy + 0.5) / ((int)1 << l) - 0.5);
+        float Kl[9] = { c.fx, 0.f, c.cx, 0.f, c.fy, c.cy, 0.f, 0.f, 1.f };
+        memcpy(c.K, Kl, 36);
+        lsd::mat3Inverse(c.K, c.KInv);
+        c.fxi = c.KInv[0]; c.fyi = c.KInv[4]; c.cxi = c.KInv[2]; c.cyi = c.KInv[5];
+    }
+}
+
+extern "C" int lsdgpu_create(int device, int width, int height, const float K[9], int max_frames, lsdgpu_ctx** out)
+{
+    if (!out) return -2;
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || (width % 16) || (height % 16) || max_frames < 2) return -2;   // SlamSystem.cpp:55
+    lsdgpu_ctx* ctx = new (std::nothrow) lsdgpu_ctx();
+    if (!ctx) return -3;
+    *out = ctx;      // returned even on failure so that lsdgpu_last_error can be read
+    ctx->device = device; ctx->w = width; ctx->h = height;
+    lsdgpu_default_globals(&ctx->g);
+    setupCams(ctx, K);
+    LSD_CHECK(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LSD_CHECK(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->smCount = prop.multiProcessorCount;
+    LSD_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+
+    const size_t n0 = (size_t)width * height;
+    size_t perFrame = 0;
+    for (int l = 0; l < LSD_LEVELS; l++) {
+        size_t n = n0 >> (2 * l);
+        perFrame += alignUp(n * 4, 256) + alignUp(n * 16, 256) + 2 * alignUp(n * 4, 256);
+    }
+    perFrame += alignUp(n0 * 4, 256) + alignUp(n0 / 4, 256);
+    size_t depthBytes = 2 * (alignUp(n0 * 16, 256) * 2) + alignUp(n0 * 4, 256)           // cur/oth hf+hi, integral
+                        + 2 * alignUp(n0 * 4, 256) + alignUp(n0 * 16, 256);              // prop head/next/val
+    const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
+    size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
+                     + alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256)
+                     + alignUp(sizeof(TrackState), 256) + 4096;
+    ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
+    LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arenaBytes, ctx->stream));
+    char* p = ctx->arena;
+    auto take = [&](size_t bytes) { char* r = p; p += alignUp(bytes, 256); return r; };
+    ctx->slots.resize(max_frames);
+    for (auto& s : ctx->slots) {
+        for (int l = 0; l < LSD_LEVELS; l++) {
+            size_t n = n0 >> (2 * l);
+            s.image[l] = (float*)take(n * 4);
+            s.grad[l] = (float4*)take(n * 16);
+            s.idepth[l] = (float*)take(n * 4);
+            s.idepthVar[l] = (float*)take(n * 4);
+        }
+        s.maxgrad = (float*)take(n0 * 4);
+        s.goodMask = (uint8_t*)take(n0 / 4);
+        memset(s.thisToParent, 0, sizeof(s.thisToParent));
+        s.thisToParent[3] = 1; s.thisToParent[7] = 1;
+    }
+    ctx->cur.hf = (float4*)take(n0 * 16); ctx->cur.hi = (int4*)take(n0 * 16);
+    ctx->oth.hf = (float4*)take(n0 * 16); ctx->oth.hi = (int4*)take(n0 * 16);
+    ctx->integral = (int*)take(n0 * 4);
+    ctx->propHead = (int*)take(n0 * 4);
+    ctx->propNext = (int*)take(n0 * 4);
+    ctx->propVal = (float4*)take(n0 * 16);
+    ctx->evPartials = (float*)take((size_t)maxBlocks * EV_NCH * 4);
+    ctx->evCounter = (unsigned int*)take(256);
+    ctx->dEvOut = (float*)take(EV_NCH * 4);
+    ctx->dObs = (ObserveParams*)take(sizeof(ObserveParams));
+    ctx->dStageU8 = (uint8_t*)take(n0);
+    ctx->dStageF = (float*)take(n0 * 32);
+    ctx->dScalars = (double*)take((size_t)maxBlocks * 2 * 8 + 64);
+    ctx->dTrackState = take(sizeof(TrackState));
+    if ((size_t)(p - ctx->arena) > ctx->arenaBytes) return lsd_fail(ctx, "arena overflow");
+
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hEvOut, EV_NCH * 4, cudaHostAllocDefault));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hObs, sizeof(ObserveParams), cudaHostAllocDefault));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStage, n0, cudaHostAllocDefault));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStageF, n0 * 32, cudaHostAllocDefault));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hScalars, 64, cudaHostAllocDefault));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hTrackState, sizeof(TrackState), cudaHostAllocDefault));
+    for (int i = 0; i < 8; i++) {
+        LSD_CHECK(ctx, cudaEventCreate(&ctx->tBegin[i]));
+        LSD_CHECK(ctx, cudaEventCreate(&ctx->tEnd[i]));
+    }
+    LSD_CHECK(ctx, cudaEventCreate(&ctx->kBegin));
+    LSD_CHECK(ctx, cudaEventCreate(&ctx->kEnd));
+    LSD_CHECK(ctx, trackPersistentSetup(ctx));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->arena);
+    cudaFreeHost(ctx->hEvOut); cudaFreeHost(ctx->hObs); cudaFreeHost(ctx->hStage); cudaFreeHost(ctx->hStageF);
+    cudaFreeHost(ctx->hScalars); cudaFreeHost(ctx->hTrackState);
+    for (int i = 0; i < 8; i++) { if (ctx->tBegin[i]) cudaEventDestroy(ctx->tBegin[i]); if (ctx->tEnd[i]) cudaEventDestroy(ctx->tEnd[i]); }
+    if (ctx->kBegin) cudaEventDestroy(ctx->kBegin);
+    if (ctx->kEnd) cudaEventDestroy(ctx->kEnd);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* lsdgpu_last_error(const lsdgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" int lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g) { ctx->g = *g; return 0; }
+extern "C" int lsdgpu_synchronize(lsdgpu_ctx* ctx)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" long long lsdgpu_launch_count(const lsdgpu_ctx* ctx) { return ctx->launches; }
+
+extern "C" int lsdgpu_timer_begin(lsdgpu_ctx* ctx, int slot)
+{
+    if (slot < 0 || slot >= 8) return -2;
+    LSD_CHECK(ctx, cudaEventRecord(ctx->tBegin[slot], ctx->stream));
+    return 0;
+}
+extern "C" int lsdgpu_timer_end(lsdgpu_ctx* ctx, int slot)
+{
+    if (slot < 0 || slot >= 8) return -2;
+    LSD_CHECK(ctx, cudaEventRecord(ctx->tEnd[slot], ctx->stream));
+    return 0;
+}
+extern "C" int lsdgpu_timer_elapsed_ms(lsdgpu_ctx* ctx, int slot, float* ms)
+{
+    if (slot < 0 || slot >= 8) return -2;
+    LSD_CHECK(ctx, cudaEventSynchronize(ctx->tEnd[slot]));
+    LSD_CHECK(ctx, cudaEventElapsedTime(ms, ctx->tBegin[slot], ctx->tEnd[slot]));
+    return 0;
+}
+extern "C" int lsdgpu_track_kernel_stats(lsdgpu_ctx* ctx, int reset, double* ms, long long* launches, double* bytes)
+{
+    if (ms) *ms = ctx->trackKernelMs;
+    if (launches) *launches = ctx->trackKernelLaunches;
+    if (bytes) *bytes = ctx->trackKernelBytes;
+    if (reset == 1) { ctx->trackKernelMs = 0; ctx->trackKernelLaunches = 0; ctx->trackKernelBytes = 0; ctx->profileTrackKernel = true; }
+    if (reset == 2) ctx->profileTrackKernel = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// frames
+// ------------------------------------------------------------------------------------------------------
+static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
+{
+    FrameSlot* s = findSlot(ctx, id);
+    if (s) return s;
+    for (auto& c : ctx->slots)
+        if (!c.used) {
+            FrameSlot fresh = c;          // keep the pointers
+            fresh.id = id; fresh.used = true;
+            fresh.hasDepth = fresh.idepthPyrValid = fresh.hasGoodMask = false;
+            fresh.depthHasBeenUpdatedFlag = false;
+            fresh.meanIdepth = 1.f; fresh.numPoints = 0;
+            memset(fresh.thisToParent, 0, sizeof(fresh.thisToParent));
+            fresh.thisToParent[3] = 1; fresh.thisToParent[7] = 1;
+            fresh.parentId = -1; fresh.initialTrackedResidual = 0;
+            fresh.numFramesTrackedOnThis = fresh.numMappedOnThis = 0;
+            c = fresh;
+            return &c;
+        }
+    return nullptr;
+}
+
+extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* s = acquireSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
+    const int w = ctx->w, h = ctx->h;
+    const size_t n0 = (size_t)w * h;
+    // the staging buffer may still be in flight from the previous upload
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hStage, gray, n0);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8, ctx->hStage, n0, cudaMemcpyHostToDevice, ctx->stream));
+    PyrPtrs pp;
+    for (int l = 0; l < LSD_LEVELS; l++) pp.l[l] = s->image[l];
+    k_image_pyramid<<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(ctx->dStageU8, pp, w, h);
+    LAUNCH(ctx);
+    GradPtrs gp;
+    for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }
+    k_gradients<<<dim3(divUp((int)n0, 256), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);
+    LAUNCH(ctx);
+    k_maxgrad<<<divUp((int)n0, 256), 256, 0, ctx->stream>>>(s->grad[0], s->maxgrad, w, h);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    s->hasDepth = false; s->idepthPyrValid = false; s->hasGoodMask = false;
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_release(lsdgpu_ctx* ctx, int frame_id)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    if (ctx->activeKf == frame_id) return lsd_fail(ctx, "frame is the active keyframe of the depth map");
+    s->used = false; s->id = -1;
+    return 0;
+}
+
+static int ensureIdepthPyramid(lsdgpu_ctx* ctx, FrameSlot* s)
+{
+    if (!s->hasDepth) return lsd_fail(ctx, "keyframe has no depth");
+    if (s->idepthPyrValid) return 0;
+    PyrPtrs id, var;
+    for (int l = 0; l < LSD_LEVELS; l++) { id.l[l] = s->idepth[l]; var.l[l] = s->idepthVar[l]; }
+    k_idepth_pyramid<<<dim3(ctx->w / 16, ctx->h / 16), 256, 0, ctx->stream>>>(id, var, ctx->w, ctx->h);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    s->idepthPyrValid = true;
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_download(lsdgpu_ctx* ctx, int frame_id, int what, int level, void* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    if (level < 0 || level >= LSD_LEVELS) return lsd_fail(ctx, "bad level");
+    const size_t n = ((size_t)ctx->w * ctx->h) >> (2 * level);
+    const void* src = nullptr;
+    size_t bytes = 0;
+    switch (what) {
+    case LSDGPU_BUF_IMAGE: src = s->image[level]; bytes = n * 4; break;
+    case LSDGPU_BUF_GRADIENTS: src = s->grad[level]; bytes = n * 16; break;
+    case LSDGPU_BUF_MAXGRAD: if (level != 0) return lsd_fail(ctx, "maxGradients exists at level 0 only"); src = s->maxgrad; bytes = n * 4; break;
+    case LSDGPU_BUF_IDEPTH:
+    case LSDGPU_BUF_IDEPTH_VAR:
+        if (!s->hasDepth) return lsd_fail(ctx, "frame has no depth");
+        if (level > 0) { int r = ensureIdepthPyramid(ctx, s); if (r) return r; }
+        src = (what == LSDGPU_BUF_IDEPTH) ? s->idepth[level] : s->idepthVar[level]; bytes = n * 4; break;
+    case LSDGPU_BUF_GOODMASK:
+        if (!s->hasGoodMask) { memset(out, 1, ((size_t)ctx->w * ctx->h) / 4); return 0; }   // Frame.h:433: initialised to true
+        src = s->goodMask; bytes = ((size_t)ctx->w * ctx->h) / 4; break;
+    default: return lsd_fail(ctx, "bad buffer selector");
+    }
+    LSD_CHECK(ctx, cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_set_depth_gt(lsdgpu_ctx* ctx, int frame_id, const float* depth, float cov_scale)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    const int n = ctx->w * ctx->h;
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hStageF, depth, (size_t)n * 4);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageF, ctx->hStageF, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k_set_depth_gt<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->dStageF, s->maxgrad, s->idepth[0], s->idepthVar[0], ctx->w, ctx->h,
+                                                           ctx->g.minUseGrad, cov_scale);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    s->hasDepth = true; s->idepthPyrValid = false;
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_set_idepth(lsdgpu_ctx* ctx, int frame_id, const float* idepth, const float* idepthVar)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    const size_t n = (size_t)ctx->w * ctx->h;
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hStageF, idepth, n * 4);
+    memcpy(ctx->hStageF + n, idepthVar, n * 4);
+    LSD_CHECK(ctx, cudaMemcpyAsync(s->idepth[0], ctx->hStageF, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LSD_CHECK(ctx, cudaMemcpyAsync(s->idepthVar[0], ctx->hStageF + n, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    s->hasDepth = true; s->idepthPyrValid = false;
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_set_pose(lsdgpu_ctx* ctx, int frame_id, const double qts[8], int parent_id, float itr)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    memcpy(s->thisToParent, qts, sizeof(s->thisToParent));
+    s->parentId = parent_id; s->initialTrackedResidual = itr;
+    return 0;
+}
+extern "C" int lsdgpu_frame_get_pose(lsdgpu_ctx* ctx, int frame_id, double qts[8], int* parent_id, float* itr)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    if (qts) memcpy(qts, s->thisToParent, sizeof(s->thisToParent));
+    if (parent_id) *parent_id = s->parentId;
+    if (itr) *itr = s->initialTrackedResidual;
+    return 0;
+}
+extern "C" int lsdgpu_frame_get_counters(lsdgpu_ctx* ctx, int frame_id, int* tracked, int* mapped)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    if (tracked) *tracked = s->numFramesTrackedOnThis;
+    if (mapped) *mapped = s->numMappedOnThis;
+    return 0;
+}
+extern "C" int lsdgpu_frame_set_counters(lsdgpu_ctx* ctx, int frame_id, int tracked, int mapped)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    s->numFramesTrackedOnThis = tracked; s->numMappedOnThis = mapped;
+    return 0;
+}
+extern "C" int lsdgpu_frame_get_depth_stats(lsdgpu_ctx* ctx, int frame_id, float* meanIdepth, int* numPoints, int* flag)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    if (meanIdepth) *meanIdepth = s->meanIdepth;
+    if (numPoints) *numPoints = s->numPoints;
+    if (flag) *flag = s->depthHasBeenUpdatedFlag ? 1 : 0;
+    return 0;
+}
+extern "C" int lsdgpu_frame_clear_good_mask(lsdgpu_ctx* ctx, int frame_id)
+{
+    FrameSlot* s = findSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "unknown frame id");
+    s->hasGoodMask = false;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tracking
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lsdgpu_ref_import(lsdgpu_ctx* ctx, int kf_id)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    int r = ensureIdepthPyramid(ctx, kf);
+    if (r) return r;
+    kf->depthHasBeenUpdatedFlag = false;       // SlamSystem.cpp:907-912
+    return 0;
+}
+
+static void fillEvalLevel(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, int level, bool writeMask, EvalLevel& L)
+{
+    const LevelCam& c = ctx->cam[level];
+    L.kfIdepth = kf->idepth[level]; L.kfVar = kf->idepthVar[level]; L.kfColor = kf->image[level];
+    L.frameGrad = fr->grad[level];
+    L.goodMask = writeMask ? fr->goodMask : nullptr;
+    L.w = c.w; L.h = c.h;
+    L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
+    L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+}
+
+// one evaluation launch + readback of the EV_NCH sums into ctx->hEvOut (synchronous)
+static int runEval(lsdgpu_ctx* ctx, const EvalLevel& L, const lsd::SE3<float>& refToFrame, float a, float b,
+                   const lsdgpu_track_settings* s)
+{
+    EvalPose P;
+    lsd::quatToMatrix(refToFrame.q, P.R);
+    P.t[0] = refToFrame.t[0]; P.t[1] = refToFrame.t[1]; P.t[2] = refToFrame.t[2];
+    P.a = a; P.b = b;
+    EvalConsts C;
+    C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; C.var_weight = s->var_weight; C.huber_half = s->huber_d / 2;
+    const int nBlocks = divUp(L.w * L.h, EVAL_THREADS);
+    if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
+    k_se3_eval<<<nBlocks, EVAL_THREADS, 0, ctx->stream>>>(L, P, C, ctx->evPartials, ctx->evCounter, ctx->dEvOut);
+    LAUNCH(ctx);
+    if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->hEvOut, ctx->dEvOut, EV_NCH * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->profileTrackKernel) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->kBegin, ctx->kEnd);
+        ctx->trackKernelMs += ms;
+        ctx->trackKernelLaunches++;
+        // B_fused(l) = 12 B/px keyframe planes + 16 B/px frame gradients (+1 B/px mask on L1) + EV_NCH*4
+        ctx->trackKernelBytes += (double)L.w * L.h * (12.0 + 16.0 + (L.goodMask ? 1.0 : 0.0)) + EV_NCH * 4.0;
+    }
+    return 0;
+}
+
+extern "C" int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int level, const float refToFrame_qt[7],
+                               float affine_a, float affine_b, const lsdgpu_track_settings* s, int write_good_mask,
+                               lsdgpu_eval_result* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    FrameSlot* fr = findSlot(ctx, frame_id);
+    if (!kf || !fr) return lsd_fail(ctx, "unknown frame id");
+    if (level < 0 || level >= LSD_LEVELS) return lsd_fail(ctx, "bad level");
+    int r = ensureIdepthPyramid(ctx, kf);
+    if (r) return r;
+    lsdgpu_track_settings ds;
+    if (!s) { lsdgpu_default_track_settings(&ds); s = &ds; }
+    EvalLevel L;
+    const bool wm = write_good_mask && level == SE3TRACKING_MIN_LEVEL;
+    fillEvalLevel(ctx, kf, fr, level, wm, L);
+    lsd::SE3<float> T;
+    for (int i = 0; i < 4; i++) T.q[i] = refToFrame_qt[i];
+    for (int i = 0; i < 3; i++) T.t[i] = refToFrame_qt[4 + i];
+    r = runEval(ctx, L, T, affine_a, affine_b, s);
+    if (r) return r;
+    if (wm) fr->hasGoodMask = true;
+    evalFinish(ctx->hEvOut, out);
+    return 0;
+}
+
+// SE3Tracker::trackFrame with the LM loop on the host (mode 0): a line-by-line mirror of SE3Tracker.cpp:280-486
+static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
+                       const lsdgpu_track_settings* st, lsdgpu_track_result* out)
+{
+    memset(out, 0, sizeof(*out));
+    bool diverged = false;
+    float affine_a = 1, affine_b = 0;
+    lsd::SE3<double> init;
+    for (int i = 0; i < 4; i++) init.q[i] = init_qt[i];
+    for (int i = 0; i < 3; i++) init.t[i] = init_qt[4 + i];
+    lsd::SE3<float> referenceToFrame = lsd::se3Cast<float>(lsd::se3Inverse(init));      // :306
+    lsdgpu_eval_result ev, lsq;
+    memset(&ev, 0, sizeof(ev));
+    float last_residual = 0;
+    const int W = ctx->w, H = ctx->h;
+
+    for (int lvl = SE3TRACKING_MAX_LEVEL - 1; lvl >= SE3TRACKING_MIN_LEVEL && !diverged; lvl--) {
+        EvalLevel L;
+        fillEvalLevel(ctx, kf, fr, lvl, lvl == SE3TRACKING_MIN_LEVEL, L);
+        int r = runEval(ctx, L, referenceToFrame, affine_a, affine_b, st);
+        if (r) return r;
+        evalFinish(ctx->hEvOut, &ev);
+        if (ev.warpedSize < 0.01f * (W >> lvl) * (H >> lvl)) { diverged = true; break; }   // :324-329
+        if (ctx->g.useAffineLightningEstimation) { affine_a = ev.affine_a_lastIt; affine_b = ev.affine_b_lastIt; }
+        // NB: the weights of calcWeightsAndResidual (:336) do not depend on the affine parameters just
+        // updated (the residual buffer was filled before), so one fused pass yields lastErr and ls
+        float lastErr = ev.meanWeightedRes;
+        lsq = ev;
+        out->numCalcResidualCalls[lvl]++;
+        float LM_lambda = st->lambdaInitial[lvl];
+
+        for (int iteration = 0; iteration < st->maxItsPerLvl[lvl] && !diverged; iteration++) {
+            out->numCalcWarpUpdateCalls[lvl]++;         // calculateWarpUpdate(ls): lsq already holds it
+            int incTry = 0;
+            while (true) {
+                float b[6], A[36], inc[6];
+                for (int i = 0; i < 6; i++) b[i] = -lsq.b[i];
+                memcpy(A, lsq.A, sizeof(A));
+                for (int i = 0; i < 6; i++) A[i * 6 + i] *= 1 + LM_lambda;
+                lsd::ldlt6Solve(A, b, inc);
+                incTry++;
+                lsd::SE3<float> new_referenceToFrame = lsd::se3Mul(lsd::se3Exp(inc), referenceToFrame);   // :363
+                r = runEval(ctx, L, new_referenceToFrame, affine_a, affine_b, st);
+                if (r) return r;
+                evalFinish(ctx->hEvOut, &ev);
+                if (ev.warpedSize < 0.01f * (W >> lvl) * (H >> lvl)) { diverged = true; break; }
+                float error = ev.meanWeightedRes;
+                out->numCalcResidualCalls[lvl]++;
+                if (error < lastErr) {
+                    referenceToFrame = new_referenceToFrame;
+                    if (ctx->g.useAffineLightningEstimation) { affine_a = ev.affine_a_lastIt; affine_b = ev.affine_b_lastIt; }
+                    if (error / lastErr > st->convergenceEps[lvl]) iteration = st->maxItsPerLvl[lvl];
+                    last_residual = lastErr = error;
+                    lsq = ev;                         // buffers now belong to the accepted pose
+                    if (LM_lambda <= 0.2) LM_lambda = 0;
+                    else LM_lambda *= st->lambdaSuccessFac;
+                    break;
+                } else {
+                    float dot = 0;
+                    for (int i = 0; i < 6; i++) dot += inc[i] * inc[i];
+                    if (!(dot > st->stepSizeMin[lvl])) { iteration = st->maxItsPerLvl[lvl]; break; }
+                    if (LM_lambda == 0) LM_lambda = 0.2;
+                    else LM_lambda *= pow((double)st->lambdaFailFac, incTry);
+                }
+            }
+        }
+    }
+    fr->hasGoodMask = true;
+    out->pointUsage = ev.pointUsage; out->lastGoodCount = ev.goodCount; out->lastBadCount = ev.badCount;
+    out->lastMeanRes = ev.meanRes;
+    out->affineEstimation_a = affine_a; out->affineEstimation_b = affine_b;
+    if (diverged) {
+        out->frameToRef_qt[3] = 1;
+        out->diverged = 1; out->trackingWasGood = 0;
+        return 0;
+    }
+    out->lastResidual = last_residual;
+    out->trackingWasGood = ev.goodCount / ((W >> SE3TRACKING_MIN_LEVEL) * (H >> SE3TRACKING_MIN_LEVEL)) > 0.04f
+                           && ev.goodCount / (ev.goodCount + ev.badCount) > 0.5f;                         // :475-477
+    out->initialTrackedResidual = out->lastResidual / out->pointUsage;                                    // :482
+    lsd::SE3<double> f2r = lsd::se3Cast<double>(lsd::se3Inverse(referenceToFrame));                        // :483-485
+    for (int i = 0; i < 4; i++) out->frameToRef_qt[i] = f2r.q[i];
+    for (int i = 0; i < 3; i++) out->frameToRef_qt[4 + i] = f2r.t[i];
+    return 0;
+}
+
+extern "C" int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double init_qt[7],
+                                const lsdgpu_track_settings* s, int mode, lsdgpu_track_result* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    FrameSlot* fr = findSlot(ctx, frame_id);
+    if (!kf || !fr) return lsd_fail(ctx, "unknown frame id");
+    int r = ensureIdepthPyramid(ctx, kf);      // reference->makePointCloud(lvl), SE3Tracker.cpp:321
+    if (r) return r;
+    lsdgpu_track_settings ds;
+    if (!s) { lsdgpu_default_track_settings(&ds); ds.maxItsPerLvl[4] = 0; s = &ds; }
+    if (mode == 1) r = trackPersistent(ctx, kf, fr, init_qt, s, out);
+    else r = trackHostLM(ctx, kf, fr, init_qt, s, out);
+    if (r) return r;
+    if (!out->diverged) {
+        if (out->trackingWasGood) kf->numFramesTrackedOnThis++;                   // :479-480
+        fr->initialTrackedResidual = out->initialTrackedResidual;                 // :482
+        for (int i = 0; i < 7; i++) fr->thisToParent[i] = out->frameToRef_qt[i];  // :483 sim3FromSE3(.., 1)
+        fr->thisToParent[7] = 1.0;
+        fr->parentId = kf->id;                                                    // :484
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// depth map
+// ------------------------------------------------------------------------------------------------------
+static DepthCam depthCam(const lsdgpu_ctx* ctx)
+{
+    const LevelCam& c = ctx->cam[0];
+    DepthCam d;
+    d.w = c.w; d.h = c.h; d.fx = c.fx; d.fy = c.fy; d.cx = c.cx; d.cy = c.cy;
+    d.fxi = c.fxi; d.fyi = c.fyi; d.cxi = c.cxi; d.cyi = c.cyi;
+    return d;
+}
+static DepthGlobals depthGlobals(const lsdgpu_ctx* ctx)
+{
+    DepthGlobals g;
+    g.minUseGrad = ctx->g.minUseGrad; g.cameraPixelNoise2 = ctx->g.cameraPixelNoise2;
+    g.regDistVar = 0.075f * 0.075f * ctx->g.depthSmoothingFactor * ctx->g.depthSmoothingFactor;   // REG_DIST_VAR, settings.h:139
+    g.allowNegativeIdepths = ctx->g.allowNegativeIdepths; g.useSubpixelStereo = ctx->g.useSubpixelStereo;
+    return g;
+}
+
+extern "C" int lsdgpu_depth_reset(lsdgpu_ctx* ctx)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->w * ctx->h;
+    // isValid = false everywhere (the int4 plane: isValid, blacklisted, validity, nextId)
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->cur.hi, 0, n * 16, ctx->stream));
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->oth.hi, 0, n * 16, ctx->stream));
+    return 0;
+}
+extern "C" int lsdgpu_depth_is_valid(lsdgpu_ctx* ctx) { return ctx->activeKf >= 0 ? 1 : 0; }
+extern "C" int lsdgpu_depth_invalidate(lsdgpu_ctx* ctx) { ctx->activeKf = -1; return 0; }
+extern "C" int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx) { return ctx->activeKf; }
+
+// Frame::setDepth(currentDepthMap) of the active keyframe
+static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf)
+{
+    const int n = ctx->w * ctx->h;
+    const int nb = divUp(n, 256);
+    k_set_depth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, kf->idepth[0], kf->idepthVar[0], n, ctx->dScalars + 8);
+    LAUNCH(ctx);
+    k_combine_partials<<<1, 32, 0, ctx->stream>>>(ctx->dScalars + 8, nb, ctx->dScalars);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->hScalars, ctx->dScalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    kf->numPoints = (int)ctx->hScalars[1];
+    kf->meanIdepth = (float)ctx->hScalars[0] / (float)kf->numPoints;
+    kf->hasDepth = true; kf->idepthPyrValid = false;
+    kf->depthHasBeenUpdatedFlag = true;
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_init_from_gt(lsdgpu_ctx* ctx, int kf_id)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (!kf->hasDepth) return lsd_fail(ctx, "initializeFromGTDepth: frame has no idepth (call lsdgpu_frame_set_depth_gt)");
+    const int n = ctx->w * ctx->h;
+    ctx->activeKf = kf_id; ctx->activeKfReactivated = false;
+    k_init_from_gt<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->cur, kf->idepth[0], n);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    return setDepthOnKeyframe(ctx, kf);
+}
+
+static int runRegularize(lsdgpu_ctx* ctx, bool removeOcclusions, int validityTH)
+{
+    DepthCam cam = depthCam(ctx);
+    DepthGlobals G = depthGlobals(ctx);
+    dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
+    std::swap(ctx->cur, ctx->oth);         // oth = previous current (the memcpy of :862), cur = output
+    if (removeOcclusions) k_regularize<true><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH);
+    else k_regularize<false><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+static int runFillHoles(lsdgpu_ctx* ctx)
+{
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "no active keyframe");
+    DepthCam cam = depthCam(ctx);
+    DepthGlobals G = depthGlobals(ctx);
+    dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
+    std::swap(ctx->cur, ctx->oth);
+    k_fill_holes<<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_set_hypotheses(lsdgpu_ctx* ctx, int kf_id, const lsdgpu_hyp* aos, int reactivated, int do_set_depth)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    const int n = ctx->w * ctx->h;
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hStageF, aos, (size_t)n * 32);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageF, ctx->hStageF, (size_t)n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    k_hyp_from_aos<<<divUp(n, 256), 256, 0, ctx->stream>>>((const lsdgpu_hyp*)ctx->dStageF, ctx->cur, n);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    ctx->activeKf = kf_id; ctx->activeKfReactivated = reactivated != 0;
+    if (reactivated) {
+        kf->numMappedOnThis = 0; kf->numFramesTrackedOnThis = 0;                   // :932-933
+        int r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);                   // :961
+        if (r) return r;
+    }
+    if (do_set_depth) return setDepthOnKeyframe(ctx, kf);
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_download(lsdgpu_ctx* ctx, lsdgpu_hyp* aos_out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    const int n = ctx->w * ctx->h;
+    k_hyp_to_aos<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->cur, (lsdgpu_hyp*)ctx->dStageF, n);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(aos_out, ctx->dStageF, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_download_integral(lsdgpu_ctx* ctx, int32_t* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    k_integral_rows<<<divUp(ctx->h, 64), 64, 0, ctx->stream>>>(ctx->cur, ctx->integral, ctx->w, ctx->h);
+    LAUNCH(ctx);
+    k_integral_cols<<<divUp(ctx->w, 64), 64, 0, ctx->stream>>>(ctx->integral, ctx->w, ctx->h);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(out, ctx->integral, (size_t)ctx->w * ctx->h * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// Frame::prepareForStereoWith, DataStructures/Frame.cpp:295-317 (host, double -> float like the reference)
+static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, RefConst& rc)
+{
+    const double* q = fr->thisToParent;
+    const double* t = fr->thisToParent + 4;
+    const double s = fr->thisToParent[7];
+    const float* K = ctx->cam[0].K;
+    double qi[4] = { -q[0], -q[1], -q[2], q[3] };
+    const double si = 1.0 / s;
+    double nt[3] = { t[0] * -1.0, t[1] * -1.0, t[2] * -1.0 }, rt[3];
+    lsd::quatRotate(qi, nt, rt);
+    const double oTt[3] = { si * rt[0], si * rt[1], si * rt[2] };      // otherToThis.translation()
+    double Ri[9], R[9];
+    lsd::quatToMatrix(qi, Ri);
+    lsd::quatToMatrix(q, R);
+    float Rif[9];
+    for (int i = 0; i < 9; i++) Rif[i] = (float)Ri[i];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float kr = (K[i * 3 + 0] * Rif[0 * 3 + j] + K[i * 3 + 1] * Rif[1 * 3 + j]) + K[i * 3 + 2] * Rif[2 * 3 + j];
+            rc.K_otherToThis_R[i * 3 + j] = kr * (float)si;
+        }
+    for (int i = 0; i < 3; i++) rc.otherToThis_t[i] = (float)oTt[i];
+    for (int i = 0; i < 3; i++)
+        rc.K_otherToThis_t[i] = (K[i * 3 + 0] * rc.otherToThis_t[0] + K[i * 3 + 1] * rc.otherToThis_t[1]) + K[i * 3 + 2] * rc.otherToThis_t[2];
+    for (int i = 0; i < 3; i++) rc.thisToOther_t[i] = (float)t[i];
+    float tR[9];
+    for (int i = 0; i < 9; i++) tR[i] = (float)R[i] * (float)s;       // thisToOther_R
+    for (int i = 0; i < 3; i++) { rc.row0[i] = tR[i * 3 + 0]; rc.row1[i] = tR[i * 3 + 1]; rc.row2[i] = tR[i * 3 + 2]; }
+}
+
+static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
+{   // DepthMap.cpp:1079-1105
+    if (n_refs <= 0 || n_refs > LSD_MAX_REFS) return lsd_fail(ctx, "bad number of reference frames");
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // hObs may still be in flight
+    ObserveParams& OP = *ctx->hObs;
+    OP.nRefs = n_refs;
+    OP.byIdSize = 0;
+    for (int k = 0; k < n_refs; k++) {
+        FrameSlot* fr = findSlot(ctx, ref_ids[k]);
+        if (!fr) return lsd_fail(ctx, "unknown reference frame id");
+        if (fr->parentId != kf->id) return lsd_fail(ctx, "reference frame was not tracked on the active keyframe (needs the global pose graph: out of scope)");
+        RefConst& rc = OP.refs[k];
+        prepareForStereoWith(ctx, fr, rc);
+        rc.initialTrackedResidual = fr->initialTrackedResidual;
+        rc.id = fr->id;
+        rc.trackedOnActive = 1;
+        rc.image = fr->image[0];
+        rc.goodMask = fr->hasGoodMask ? fr->goodMask : nullptr;
+        if (k == 0) OP.byIdOffset = fr->id;
+        while (OP.byIdSize + OP.byIdOffset <= fr->id) {
+            if (OP.byIdSize >= 256) return lsd_fail(ctx, "reference id span too large");
+            OP.byId[OP.byIdSize++] = k;
+        }
+    }
+    OP.oldestIdx = 0; OP.newestIdx = n_refs - 1;
+    OP.reactivated = ctx->activeKfReactivated ? 1 : 0;
+    OP.kfNumTracked = kf->numFramesTrackedOnThis; OP.kfNumMapped = kf->numMappedOnThis;
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dObs, ctx->hObs, sizeof(ObserveParams), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
+{
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "no active keyframe");
+    int r = setupObserve(ctx, ref_ids, n_refs, kf);
+    if (r) return r;
+    DepthCam cam = depthCam(ctx);
+    DepthGlobals G = depthGlobals(ctx);
+    dim3 grid(divUp(cam.w - 6, 128), cam.h - 6);
+    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->dObs);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_observe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    return runObserve(ctx, ref_ids, n_refs);
+}
+extern "C" int lsdgpu_depth_regularize_fill_holes(lsdgpu_ctx* ctx)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    return runFillHoles(ctx);
+}
+extern "C" int lsdgpu_depth_regularize(lsdgpu_ctx* ctx, int removeOcclusions, int validityTH)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    return runRegularize(ctx, removeOcclusions != 0, validityTH);
+}
+
+extern "C" int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
+{   // DepthMap::updateKeyframe :1072-1213
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "updateKeyframe: depth map is not valid (no active keyframe)");
+    int r = runObserve(ctx, ref_ids, n_refs);                      // :1127
+    if (r) return r;
+    r = runFillHoles(ctx);                                         // :1135
+    if (r) return r;
+    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);           // :1143
+    if (r) return r;
+    if (!kf->depthHasBeenUpdatedFlag) {                            // :1150-1157
+        r = setDepthOnKeyframe(ctx, kf);
+        if (r) return r;
+    }
+    kf->numMappedOnThis++;                                         // :1165
+    return 0;
+}
+
+static int runPropagate(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* nk)
+{   // DepthMap::propagateDepth :475-653
+    const int n = ctx->w * ctx->h;
+    lsd::SE3<double> tp;
+    for (int i = 0; i < 4; i++) tp.q[i] = nk->thisToParent[i];
+    for (int i = 0; i < 3; i++) tp.t[i] = nk->thisToParent[4 + i];
+    lsd::quatNormalize(tp.q);                                      // se3FromSim3: SE3(quaternion, translation)
+    lsd::SE3<double> oldToNew = lsd::se3Inverse(tp);               // :503
+    double Rd[9];
+    lsd::quatToMatrix(oldToNew.q, Rd);
+    PropParams P;
+    for (int i = 0; i < 9; i++) P.R[i] = (float)Rd[i];
+    for (int i = 0; i < 3; i++) P.t[i] = (float)oldToNew.t[i];
+    P.trackingWasGood = (nk->parentId == kf->id && nk->hasGoodMask) ? nk->goodMask : nullptr;      // :508
+    P.activeKFImage = kf->image[0];
+    P.newKFMaxGrad = nk->maxgrad;
+    P.newKFImage = nk->image[0];
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->propHead, 0xff, (size_t)n * 4, ctx->stream));
+    DepthCam cam = depthCam(ctx);
+    DepthGlobals G = depthGlobals(ctx);
+    k_prop_project<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->cur, cam, G, P, ctx->propHead, ctx->propNext, ctx->propVal);
+    LAUNCH(ctx);
+    k_prop_resolve<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->oth, n, ctx->propHead, ctx->propNext, ctx->propVal);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    std::swap(ctx->cur, ctx->oth);                                 // :637
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_propagate(lsdgpu_ctx* ctx, int new_kf_id)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    FrameSlot* nk = findSlot(ctx, new_kf_id);
+    if (!kf || !nk) return lsd_fail(ctx, "propagateDepth: unknown keyframe");
+    return runPropagate(ctx, kf, nk);
+}
+
+extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, double new_qts[8])
+{   // DepthMap::createKeyFrame :1222-1327
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    FrameSlot* nk = findSlot(ctx, new_kf_id);
+    if (!kf) return lsd_fail(ctx, "createKeyFrame: depth map is not valid");
+    if (!nk) return lsd_fail(ctx, "createKeyFrame: unknown new keyframe");
+    if (nk->parentId < 0) return lsd_fail(ctx, "createKeyFrame: new keyframe has no tracking parent");
+    lsd::SE3<double> tp;
+    for (int i = 0; i < 4; i++) tp.q[i] = nk->thisToParent[i];
+    for (int i = 0; i < 3; i++) tp.t[i] = nk->thisToParent[4 + i];
+    lsd::quatNormalize(tp.q);
+    lsd::SE3<double> oldToNew = lsd::se3Inverse(tp);               // :1246
+    int r = runPropagate(ctx, kf, nk);                             // :1250
+    if (r) return r;
+    ctx->activeKf = new_kf_id; ctx->activeKfReactivated = false;   // :1255-1258
+    r = runRegularize(ctx, true, VAL_SUM_MIN_FOR_KEEP);            // :1263
+    if (r) return r;
+    r = runFillHoles(ctx);                                         // :1270
+    if (r) return r;
+    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);           // :1277
+    if (r) return r;
+    const int n = ctx->w * ctx->h;
+    const int nb = divUp(n, 256);
+    k_sum_idepth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars + 8);                   // :1286-1293
+    LAUNCH(ctx);
+    k_combine_partials<<<1, 32, 0, ctx->stream>>>(ctx->dScalars + 8, nb, ctx->dScalars);
+    LAUNCH(ctx);
+    k_rescale<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars);                          // :1295-1304
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->hScalars + 4, ctx->dScalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    const float rescaleFactor = (float)ctx->hScalars[4 + 2];
+    lsd::SE3<double> back = lsd::se3Inverse(oldToNew);             // :1305 sim3FromSE3(oldToNew_SE3.inverse(), rescaleFactor)
+    for (int i = 0; i < 4; i++) nk->thisToParent[i] = back.q[i];
+    for (int i = 0; i < 3; i++) nk->thisToParent[4 + i] = back.t[i];
+    nk->thisToParent[7] = rescaleFactor;
+    if (new_qts) memcpy(new_qts, nk->thisToParent, sizeof(nk->thisToParent));
+    return setDepthOnKeyframe(ctx, nk);                            // :1311
+}
+
+extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
+{   // DepthMap::finalizeKeyFrame :1363-1395
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "finalizeKeyFrame: depth map is not valid");
+    int r = runFillHoles(ctx);
+    if (r) return r;
+    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);
+    if (r) return r;
+    return setDepthOnKeyframe(ctx, kf);
+}
