@@ -389,6 +389,15 @@ extern "C" int lsdgpu_ref_import(lsdgpu_ctx* ctx, int kf_id)
     return 0;
 }
 
+// Frame::refPixelWasGood(): created on first use, initialised to true (DataStructures/Frame.h:421-437)
+static int ensureGoodMask(lsdgpu_ctx* ctx, FrameSlot* fr)
+{
+    if (fr->hasGoodMask) return 0;
+    LSD_CHECK(ctx, cudaMemsetAsync(fr->goodMask, 1, ((size_t)ctx->w * ctx->h) / 4, ctx->stream));
+    fr->hasGoodMask = true;
+    return 0;
+}
+
 static void fillEvalLevel(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, int level, bool writeMask, EvalLevel& L)
 {
     const LevelCam& c = ctx->cam[level];
@@ -444,13 +453,13 @@ extern "C" int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int lev
     if (!s) { lsdgpu_default_track_settings(&ds); s = &ds; }
     EvalLevel L;
     const bool wm = write_good_mask && level == SE3TRACKING_MIN_LEVEL;
+    if (wm) { r = ensureGoodMask(ctx, fr); if (r) return r; }
     fillEvalLevel(ctx, kf, fr, level, wm, L);
     lsd::SE3<float> T;
     for (int i = 0; i < 4; i++) T.q[i] = refToFrame_qt[i];
     for (int i = 0; i < 3; i++) T.t[i] = refToFrame_qt[4 + i];
     r = runEval(ctx, L, T, affine_a, affine_b, s);
     if (r) return r;
-    if (wm) fr->hasGoodMask = true;
     evalFinish(ctx->hEvOut, out);
     return 0;
 }
@@ -470,6 +479,7 @@ static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const doub
     memset(&ev, 0, sizeof(ev));
     float last_residual = 0;
     const int W = ctx->w, H = ctx->h;
+    { int r0 = ensureGoodMask(ctx, fr); if (r0) return r0; }
 
     for (int lvl = SE3TRACKING_MAX_LEVEL - 1; lvl >= SE3TRACKING_MIN_LEVEL && !diverged; lvl--) {
         EvalLevel L;
@@ -522,7 +532,6 @@ static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const doub
             }
         }
     }
-    fr->hasGoodMask = true;
     out->pointUsage = ev.pointUsage; out->lastGoodCount = ev.goodCount; out->lastBadCount = ev.badCount;
     out->lastMeanRes = ev.meanRes;
     out->affineEstimation_a = affine_a; out->affineEstimation_b = affine_b;
