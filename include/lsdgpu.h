@@ -126,6 +126,12 @@ int  lsdgpu_track_kernel_stats(lsdgpu_ctx* ctx, int reset, double* ms, long long
  * + buildMaxGradients :690-767, all levels, once per frame.  gray = HOST buffer of w*h bytes. */
 int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray);
 int lsdgpu_frame_release(lsdgpu_ctx* ctx, int frame_id);                 /* Frame::~Frame */
+/* Prefetch ring: raw u8 frames parked in HBM ahead of time (camera DMA / dataset prefetch), so that the
+ * Frame constructor above can run without touching the host: stage_put copies one HOST frame into ring
+ * entry `index`; frame_from_stage builds frame `frame_id` from it (same kernels as lsdgpu_frame_upload_u8). */
+int lsdgpu_stage_reserve(lsdgpu_ctx* ctx, int n_entries);
+int lsdgpu_stage_put(lsdgpu_ctx* ctx, int index, const uint8_t* gray);
+int lsdgpu_frame_from_stage(lsdgpu_ctx* ctx, int frame_id, int index);
 int lsdgpu_frame_download(lsdgpu_ctx* ctx, int frame_id, int what, int level, void* out_host);
 /* Frame::setDepthFromGroundTruth(depth, cov_scale) Frame.cpp:245-293 */
 int lsdgpu_frame_set_depth_gt(lsdgpu_ctx* ctx, int frame_id, const float* depth, float cov_scale);

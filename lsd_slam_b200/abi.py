@@ -81,6 +81,9 @@ SYMBOLS = [
     ("lsdgpu_track_kernel_stats", C.c_int, [_vp, C.c_int, _dp, C.POINTER(C.c_longlong), _dp]),
     ("lsdgpu_frame_upload_u8", C.c_int, [_vp, C.c_int, _u8p]),
     ("lsdgpu_frame_release", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_stage_reserve", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_stage_put", C.c_int, [_vp, C.c_int, _u8p]),
+    ("lsdgpu_frame_from_stage", C.c_int, [_vp, C.c_int, C.c_int]),
     ("lsdgpu_frame_download", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp]),
     ("lsdgpu_frame_set_depth_gt", C.c_int, [_vp, C.c_int, _fp, C.c_float]),
     ("lsdgpu_frame_set_idepth", C.c_int, [_vp, C.c_int, _fp, _fp]),
@@ -208,6 +211,16 @@ class Context:
         img = np.ascontiguousarray(image_u8, np.uint8)
         assert img.shape == (self.h, self.w)
         self._ck(self.L.lsdgpu_frame_upload_u8(self.ptr, fid, img.ctypes.data_as(_u8p)))
+
+    def stage_reserve(self, n: int):
+        self._ck(self.L.lsdgpu_stage_reserve(self.ptr, n))
+
+    def stage_put(self, index: int, image_u8: np.ndarray):
+        img = np.ascontiguousarray(image_u8, np.uint8)
+        self._ck(self.L.lsdgpu_stage_put(self.ptr, index, img.ctypes.data_as(_u8p)))
+
+    def frame_from_stage(self, fid: int, index: int):
+        self._ck(self.L.lsdgpu_frame_from_stage(self.ptr, fid, index))
 
     def release(self, fid: int):
         self._ck(self.L.lsdgpu_frame_release(self.ptr, fid))

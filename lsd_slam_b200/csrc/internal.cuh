@@ -117,6 +117,8 @@ struct lsdgpu_ctx {
     float* hEvOut = nullptr;             // pinned host mirror
     void* dTrackState = nullptr;         // persistent-kernel state block (device)
     void* hTrackState = nullptr;         // pinned mirror
+    uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
+    int stageEntries = 0;
     uint8_t* hStage = nullptr;           // pinned staging for the u8 frame upload
     uint8_t* dStageU8 = nullptr;
     float* hStageF = nullptr;            // pinned float staging (depth / idepth uploads)

@@ -146,6 +146,7 @@ extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->arena);
+    if (ctx->stageRing) cudaFree(ctx->stageRing);
     cudaFreeHost(ctx->hEvOut); cudaFreeHost(ctx->hObs); cudaFreeHost(ctx->hStage); cudaFreeHost(ctx->hStageF);
     cudaFreeHost(ctx->hScalars); cudaFreeHost(ctx->hTrackState);
     for (int i = 0; i < 8; i++) { if (ctx->tBegin[i]) cudaEventDestroy(ctx->tBegin[i]); if (ctx->tEnd[i]) cudaEventDestroy(ctx->tEnd[i]); }
@@ -218,20 +219,58 @@ static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
     return nullptr;
 }
 
+static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc);
+
 extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray)
 {
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = acquireSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
-    const int w = ctx->w, h = ctx->h;
-    const size_t n0 = (size_t)w * h;
+    const size_t n0 = (size_t)ctx->w * ctx->h;
     // the staging buffer may still be in flight from the previous upload
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->hStage, gray, n0);
     LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8, ctx->hStage, n0, cudaMemcpyHostToDevice, ctx->stream));
+    return buildFrameFromDeviceU8(ctx, s, ctx->dStageU8);
+}
+
+extern "C" int lsdgpu_stage_reserve(lsdgpu_ctx* ctx, int n_entries)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (n_entries <= 0) return lsd_fail(ctx, "bad ring size");
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->stageRing) { cudaFree(ctx->stageRing); ctx->stageRing = nullptr; ctx->stageEntries = 0; }
+    LSD_CHECK(ctx, cudaMalloc((void**)&ctx->stageRing, (size_t)n_entries * ctx->w * ctx->h));
+    ctx->stageEntries = n_entries;
+    return 0;
+}
+extern "C" int lsdgpu_stage_put(lsdgpu_ctx* ctx, int index, const uint8_t* gray)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (index < 0 || index >= ctx->stageEntries) return lsd_fail(ctx, "bad ring index");
+    const size_t n0 = (size_t)ctx->w * ctx->h;
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->hStage, gray, n0);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->stageRing + (size_t)index * n0, ctx->hStage, n0, cudaMemcpyHostToDevice, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int lsdgpu_frame_from_stage(lsdgpu_ctx* ctx, int frame_id, int index)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (index < 0 || index >= ctx->stageEntries) return lsd_fail(ctx, "bad ring index");
+    FrameSlot* s = acquireSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
+    return buildFrameFromDeviceU8(ctx, s, ctx->stageRing + (size_t)index * ctx->w * ctx->h);
+}
+
+static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc)
+{
+    const int w = ctx->w, h = ctx->h;
+    const size_t n0 = (size_t)w * h;
     PyrPtrs pp;
     for (int l = 0; l < LSD_LEVELS; l++) pp.l[l] = s->image[l];
-    k_image_pyramid<<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(ctx->dStageU8, pp, w, h);
+    k_image_pyramid<<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(dsrc, pp, w, h);
     LAUNCH(ctx);
     GradPtrs gp;
     for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }

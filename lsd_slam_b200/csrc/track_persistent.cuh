@@ -1,17 +1,528 @@
-// track_persistent.cuh -- device-resident LM loop of SE3Tracker::trackFrame (mode 1).  Placeholder: the
-// first milestone routes mode 1 through the host-driven loop; replaced by the persistent kernel next.
+// track_persistent.cuh -- SE3Tracker::trackFrame as ONE persistent cooperative kernel (mode 1).
+//
+// The whole coarse-to-fine Levenberg-Marquardt loop of Tracking/SE3Tracker.cpp:280-486 runs on the device:
+// every CTA evaluates its share of the keyframe pixels with evalPoint() (track.cuh), the CTAs exchange
+// EV_NCH partial sums through L2 behind ONE grid-wide barrier per evaluation, and then EVERY CTA redundantly
+// (and deterministically: same instructions on the same data) combines the partials in block order, solves
+// the damped 6x6 system (LDL^T), applies exp(inc) * T and takes the accept / reject / converge decision of
+// :381-446.  No host round trip, no second barrier, no float atomics.  The host sees one launch and one
+// 200-byte result per frame.
+//
+// Why this shape on B200: a 640x480 frame has <= 77k points on the finest tracked level, i.e. ~2 per resident
+// thread; one evaluation is a few microseconds of latency, so the reference's structure (3 passes per
+// evaluation, one host decision between evaluations, 15-60 evaluations per frame) is launch/latency bound by
+// two orders of magnitude.  Grid = one CTA per SM (148), co-residency guaranteed by the cooperative launch.
 #pragma once
 #include "internal.cuh"
 #include "track.cuh"
+#include <stdlib.h>
 
-struct TrackState {
-    float dummy[64];
+#define TP_THREADS 512
+#define TP_LOCAL_MAX_PIXELS 1024      // levels up to this many pixels are evaluated redundantly per CTA
+
+struct TrackLevelParams {
+    const float* kfIdepth;
+    const float* kfVar;
+    const float* kfColor;
+    const float4* frameGrad;
+    int w, h;
+    float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
 };
-static cudaError_t trackPersistentSetup(lsdgpu_ctx*) { return cudaSuccess; }
-static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
-                       const lsdgpu_track_settings* st, lsdgpu_track_result* out);
+
+struct TrackParams {
+    TrackLevelParams lvl[LSD_LEVELS];
+    uint8_t* goodMask;               // level-1 mask of the tracked frame
+    int maskFresh;                   // 1: initialise the mask to true first (Frame.h:433)
+    int maskBytes;
+    int W, H;                        // tracker construction size (diverge test uses width>>lvl, SE3Tracker.cpp:324)
+    float initRefToFrame[7];         // frameToReference_initialEstimate.inverse().cast<float>(), :306
+    lsdgpu_track_settings st;
+    EvalConsts C;
+    int useAffine;
+    float* partials;                 // [2][EV_NCH][gridDim]
+    unsigned int* barrier;           // monotonically increasing arrival counter
+};
+
+// what the kernel hands back (block 0 writes it)
+struct TrackState {
+    float refToFrame[7];
+    float pointUsage, goodCount, badCount, meanRes, lastResidual;
+    float affine_a, affine_b;
+    int diverged;
+    int numCalcResidualCalls[LSD_LEVELS];
+    int numCalcWarpUpdateCalls[LSD_LEVELS];
+    int totalEvals;
+    long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
+};
+
+// grid-wide barrier on a monotonically increasing counter; `target` = arrivals expected so far
+__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int target)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+struct LMShared {
+    float sums[EV_NCH];
+    EvalPose pose;                   // pose being evaluated
+    int action;
+    int lvl;                         // level of the next evaluation
+};
+
+enum { ACT_CONTINUE = 0, ACT_LEVEL_DONE = 1, ACT_DIVERGED = 2, ACT_RETRY = 3, ACT_ACCEPTED = 4 };
+
+__device__ __forceinline__ void setEvalPose(EvalPose& P, const lsd::SE3<float>& T, float a, float b)
+{
+    lsd::quatToMatrix(T.q, P.R);
+    P.t[0] = T.t[0]; P.t[1] = T.t[1]; P.t[2] = T.t[2];
+    P.a = a; P.b = b;
+}
+
+// ---- multi-value warp reduction -------------------------------------------------------------------------
+// K values per lane (K a power of two <= 32) are reduced across the warp with K-1 (+ log2(32/K)) shuffles
+// instead of 5K: at every step the lanes of a pair exchange HALF of their values.  On return v[0] holds the
+// warp total of channel  chan = sum over used masks of (lane & mask ? half : 0)  (for K = 32: chan == lane).
+// Fixed exchange pattern => bit-identical results wherever the same data is reduced.
+template <int K, typename T>
+__device__ __forceinline__ void warpReduceMulti(T (&v)[K], int lane)
+{
+    int mask = 16;
+#pragma unroll
+    for (int half = K / 2; half >= 1; half >>= 1, mask >>= 1) {
+        const bool upper = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            T keep = upper ? v[i + half] : v[i];
+            T send = upper ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+#pragma unroll
+    for (; mask >= 1; mask >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
+}
+// channel held in v[0] by `lane` after warpReduceMulti<K>
+template <int K> __device__ __forceinline__ int warpReduceChannel(int lane)
+{
+    int c = 0, mask = 16;
+#pragma unroll
+    for (int half = K / 2; half >= 1; half >>= 1, mask >>= 1)
+        if (lane & mask) c += half;
+    return c;
+}
+
+// all EV_NCH (= 32 + 8 + 4) channels of a thread's accumulator -> per-warp totals in sm[warp][*]
+__device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* smRow)
+{
+    float a32[32], a8[8], a4[4];
+#pragma unroll
+    for (int i = 0; i < 32; i++) a32[i] = acc.v[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a8[i] = acc.v[32 + i];
+#pragma unroll
+    for (int i = 0; i < 4; i++) a4[i] = acc.v[40 + i];
+    warpReduceMulti<32>(a32, lane);
+    warpReduceMulti<8>(a8, lane);
+    warpReduceMulti<4>(a4, lane);
+    smRow[lane] = a32[0];
+    if ((lane & 3) == 0) smRow[32 + warpReduceChannel<8>(lane)] = a8[0];
+    if ((lane & 7) == 0) smRow[40 + warpReduceChannel<4>(lane)] = a4[0];
+}
+
+#define TP_WARPS (TP_THREADS / 32)
+#define TP_MAXGRID 160               // combine code is unrolled for <= 160 CTAs (B200: 148 SMs)
+
+// One evaluation.  Levels with few pixels (local == true) are evaluated REDUNDANTLY by every CTA over the whole
+// level -- no grid barrier, no exchange; big levels are split over the grid with one barrier.  On return
+// sh.sums holds the EV_NCH totals, bit-identical in every CTA.
+__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool local, LMShared& sh, float (*sm)[EV_NCH],
+                                             unsigned int& epoch, long long* cyc)
+{
+    long long t0 = clock64();
+    const TrackLevelParams& L = p.lvl[lvl];
+    const EvalPose P = sh.pose;
+    PointAcc acc;
+#pragma unroll
+    for (int c = 0; c < EV_NCH; c++) acc.v[c] = 0.f;
+    const int w = L.w, h = L.h, n = w * h;
+    const float4* fg = L.frameGrad;
+    uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
+    const int first = local ? threadIdx.x : blockIdx.x * TP_THREADS + threadIdx.x;
+    const int stride = local ? TP_THREADS : gridDim.x * TP_THREADS;
+    for (int i = first; i < n; i += stride) {
+        const int x = i % w, y = i / w;
+        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+            const float idepth = __ldg(L.kfIdepth + i), var = __ldg(L.kfVar + i);
+            if (!(var <= 0 || idepth == 0)) {
+                const float sc = 1.0f / idepth;
+                const float px = sc * (L.fxi * x + L.cxi), py = sc * (L.fyi * y + L.cyi), pz = sc * 1;
+                auto tap = [fg, w](float u, float v, float& o0, float& o1, float& o2) { interp43(fg, u, v, w, o0, o1, o2); };
+                int good = evalPoint(px, py, pz, __ldg(L.kfColor + i), var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
+                if (mask) mask[i] = (uint8_t)good;
+            }
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    warpReduceAcc(acc, lane, sm[warp]);
+    __syncthreads();
+    float ctaSum = 0.f;
+    if (threadIdx.x < EV_NCH) {
+#pragma unroll
+        for (int wi = 0; wi < TP_WARPS; wi++) ctaSum += sm[wi][threadIdx.x];
+    }
+    if (local) {
+        if (threadIdx.x < EV_NCH) sh.sums[threadIdx.x] = ctaSum;
+        __syncthreads();
+        long long t2 = clock64();
+        cyc[0] += t1 - t0; cyc[1] += t2 - t1;
+        return;
+    }
+    const unsigned int parity = epoch & 1u;
+    float* part = p.partials + (size_t)parity * EV_NCH * gridDim.x;
+    if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
+    epoch++;
+    long long t2 = clock64();
+    gridBarrier(p.barrier, epoch * gridDim.x);
+    long long t3 = clock64();
+    // every CTA combines all partial rows in a fixed order: warp wi owns channels wi, wi+TP_WARPS, ... (<= 8 per
+    // warp); all loads are issued first, then one multi-value reduction in double.
+    {
+        double ch[8];
+        const int nb = (int)gridDim.x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int c = warp + k * TP_WARPS;
+            float v[TP_MAXGRID / 32];
+#pragma unroll
+            for (int j = 0; j < TP_MAXGRID / 32; j++) {
+                const int b = lane + 32 * j;
+                v[j] = (c < EV_NCH && b < nb) ? __ldcg(part + (size_t)c * nb + b) : 0.f;
+            }
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < TP_MAXGRID / 32; j++) s += (double)v[j];
+            ch[k] = s;
+        }
+        warpReduceMulti<8>(ch, lane);
+        if ((lane & 3) == 0) {
+            const int c = warp + warpReduceChannel<8>(lane) * TP_WARPS;
+            if (c < EV_NCH) sh.sums[c] = (float)ch[0];
+        }
+    }
+    __syncthreads();
+    long long t4 = clock64();
+    cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+}
+
+// Fully unrolled, register-resident LDL^T (no pivoting) for the damped 6x6 normal equations.  Returns false if
+// a pivot is not strictly positive (then the caller falls back to the pivoted routine, hostmath.h).
+__device__ __forceinline__ bool ldlt6SolveFast(const float* A, const float* b, float* x)
+{
+    float L[6][6], D[6];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        float d = A[j * 6 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k] * D[k];
+        D[j] = d;
+        ok = ok && (d > 0.f);
+        const float inv = 1.0f / d;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            float v = A[i * 6 + j];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * D[k];
+            L[i][j] = v * inv;
+        }
+    }
+    float y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        float s = b[i];
+#pragma unroll
+        for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+        y[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] = y[i] / D[i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        float s = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
+        x[i] = s;
+    }
+    return ok;
+}
+
+// LM state of SE3Tracker::trackFrame; lives in shared memory, touched by thread 0 only (keeps it out of the
+// register budget of the other threads)
+struct LMState {
+    lsd::SE3<float> refToFrame, cand;
+    float affine_a, affine_b, lastErr, last_residual, LM_lambda;
+    float inc[6];
+    float lsq[27];                   // accepted normal equations, RAW sums: 21 upper-triangle A + 6 (sum J r w)
+    int nRes[LSD_LEVELS], nUpd[LSD_LEVELS];
+    int lvl, iteration, phase, incTry, diverged;
+};
+enum { PH_INIT = 0, PH_TRY = 1 };
+
+// affine lighting estimate of the last evaluation, SE3Tracker.cpp:1023-1024
+__device__ __forceinline__ void affineFromSums(const float* s, float& a, float& b)
+{
+    const float sxx = s[CH_SXX], syy = s[CH_SYY], sx = s[CH_SX], sy = s[CH_SY], sw = s[CH_SW];
+    a = sqrtf((syy - sy * sy / sw) / (sxx - sx * sx / sw));
+    b = (sy - a * sx) / sw;
+}
+
+// solve the damped system of the accepted linearisation and set the candidate pose (SE3Tracker.cpp:356-363).
+// A and b are used un-normalised: LGS6::finish divides both by num_constraints (LGSX.h:319-325), which cancels
+// in A^-1 b (the damping is multiplicative), so the division is skipped on the device.
+__device__ __forceinline__ void lmSolveAndPropose(LMState& lm, LMShared& sh)
+{
+    static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
+                                            {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
+    float A[36], b[6], inc[6];
+#pragma unroll
+    for (int k = 0; k < 21; k++) {
+        const float v = lm.lsq[k];
+        A[ij[k][0] * 6 + ij[k][1]] = v;
+        A[ij[k][1] * 6 + ij[k][0]] = v;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) b[i] = lm.lsq[21 + i];
+    const float damp = 1 + lm.LM_lambda;
+#pragma unroll
+    for (int i = 0; i < 6; i++) A[i * 6 + i] *= damp;
+    if (!ldlt6SolveFast(A, b, inc)) lsd::ldlt6Solve(A, b, inc);
+#pragma unroll
+    for (int i = 0; i < 6; i++) lm.inc[i] = inc[i];
+    lm.incTry++;
+    lm.cand = lsd::se3Mul(lsd::se3Exp(inc), lm.refToFrame);
+    setEvalPose(sh.pose, lm.cand, lm.affine_a, lm.affine_b);
+    lm.phase = PH_TRY;
+}
+
+__device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, LMShared& sh)
+{
+    lm.lvl--;
+    if (lm.lvl < SE3TRACKING_MIN_LEVEL) { sh.action = ACT_LEVEL_DONE; return; }     // all levels done
+    lm.phase = PH_INIT;
+    setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+    sh.lvl = lm.lvl;
+}
+
+// start iteration lm.iteration of the current level, or leave the level when the budget is used up (:343)
+__device__ __forceinline__ void lmStartIteration(const TrackParams& p, LMState& lm, LMShared& sh)
+{
+    if (lm.iteration < p.st.maxItsPerLvl[lm.lvl]) {
+        lm.nUpd[lm.lvl]++;                                                       // calculateWarpUpdate(ls), :346
+        lm.incTry = 0;
+        lmSolveAndPropose(lm, sh);
+    } else
+        lmNextLevel(p, lm, sh);
+}
+
+// thread 0 after every evaluation: the decisions of SE3Tracker.cpp:324-446
+__device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMShared& sh)
+{
+    const float* s = sh.sums;
+    const int lvl = lm.lvl;
+    const float warped = s[CH_WARPED];
+    sh.action = ACT_CONTINUE;
+    if (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) {                          // :324-329 / :369-374
+        lm.diverged = 1;
+        sh.action = ACT_DIVERGED;
+        return;
+    }
+    const float error = s[CH_SUMRESW] / warped;                                  // calcWeightsAndResidual, :789
+    lm.nRes[lvl]++;
+    if (lm.phase == PH_INIT) {
+        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);            // :331-335
+        lm.lastErr = error;                                                      // :336
+#pragma unroll
+        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];
+        lm.LM_lambda = p.st.lambdaInitial[lvl];
+        lm.iteration = 0;
+        lmStartIteration(p, lm, sh);
+        return;
+    }
+    if (error < lm.lastErr) {                                                    // :381 accept
+        lm.refToFrame = lm.cand;
+        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);
+        const bool converged = error / lm.lastErr > p.st.convergenceEps[lvl];    // :404
+        lm.last_residual = lm.lastErr = error;                                   // :414
+#pragma unroll
+        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];
+        if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                               // :417-420
+        else lm.LM_lambda *= p.st.lambdaSuccessFac;
+        if (converged) lmNextLevel(p, lm, sh);
+        else { lm.iteration++; lmStartIteration(p, lm, sh); }
+    } else {                                                                     // :424-447 reject
+        float dot = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dot += lm.inc[i] * lm.inc[i];
+        if (!(dot > p.st.stepSizeMin[lvl])) lmNextLevel(p, lm, sh);              // :432-441
+        else {
+            if (lm.LM_lambda == 0) lm.LM_lambda = 0.2;                           // :443-446
+            else lm.LM_lambda *= pow((double)p.st.lambdaFailFac, lm.incTry);
+            lmSolveAndPropose(lm, sh);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out)
+{
+    __shared__ LMShared sh;
+    __shared__ LMState lm;
+    __shared__ float sm[TP_THREADS / 32][EV_NCH];
+    static_assert(EV_NCH == 44, "warpReduceAcc is written for 32 + 8 + 4 channels");
+    unsigned int epoch = 0;
+    long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
+    const long long tStart = clock64();
+
+    // fresh refPixelWasGood mask: all true (Frame.h:433); ordered before the level-1 evaluations by the barriers
+    if (p.maskFresh) {
+        uint32_t* m32 = reinterpret_cast<uint32_t*>(p.goodMask);
+        for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < p.maskBytes / 4; i += gridDim.x * TP_THREADS) m32[i] = 0x01010101u;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = p.initRefToFrame[i];
+        for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
+        for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; }
+        lm.affine_a = 1.f; lm.affine_b = 0.f; lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
+        lm.diverged = 0; lm.incTry = 0; lm.iteration = 0;
+        lm.lvl = SE3TRACKING_MAX_LEVEL - 1; lm.phase = PH_INIT;
+        sh.lvl = lm.lvl; sh.action = ACT_CONTINUE;
+        setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+    }
+    __syncthreads();
+
+    while (true) {
+        const int lvl = sh.lvl;
+        const bool local = p.lvl[lvl].w * p.lvl[lvl].h <= TP_LOCAL_MAX_PIXELS;
+        gridEvaluate(p, lvl, local, sh, sm, epoch, cyc);
+        if (threadIdx.x == 0) lmAdvance(p, lm, sh);
+        __syncthreads();
+        if (sh.action != ACT_CONTINUE) break;
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        lsdgpu_eval_result ev;
+        evalFinish(sh.sums, &ev);        // statistics of the LAST EVALUATED pose
+        for (int i = 0; i < 4; i++) out->refToFrame[i] = lm.refToFrame.q[i];
+        for (int i = 0; i < 3; i++) out->refToFrame[4 + i] = lm.refToFrame.t[i];
+        out->pointUsage = ev.pointUsage; out->goodCount = ev.goodCount; out->badCount = ev.badCount;
+        out->meanRes = ev.meanRes; out->lastResidual = lm.last_residual;
+        out->affine_a = lm.affine_a; out->affine_b = lm.affine_b;
+        out->diverged = lm.diverged;
+        for (int l = 0; l < LSD_LEVELS; l++) { out->numCalcResidualCalls[l] = lm.nRes[l]; out->numCalcWarpUpdateCalls[l] = lm.nUpd[l]; }
+        out->totalEvals = (int)epoch;
+        cyc[5] = clock64() - tStart;
+        cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
+        for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
+    }
+}
+
+static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
+{
+    int coop = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+    if (e != cudaSuccess) return e;
+    if (!coop) return cudaErrorNotSupported;
+    return cudaSuccess;
+}
+
 static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
                            const lsdgpu_track_settings* st, lsdgpu_track_result* out)
 {
-    return trackHostLM(ctx, kf, fr, init_qt, st, out);
+    memset(out, 0, sizeof(*out));
+    TrackParams P;
+    memset(&P, 0, sizeof(P));
+    for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++) {
+        const LevelCam& c = ctx->cam[l];
+        TrackLevelParams& L = P.lvl[l];
+        L.kfIdepth = kf->idepth[l]; L.kfVar = kf->idepthVar[l]; L.kfColor = kf->image[l]; L.frameGrad = fr->grad[l];
+        L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
+        L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+    }
+    P.goodMask = fr->goodMask;
+    P.maskFresh = fr->hasGoodMask ? 0 : 1;
+    P.maskBytes = (ctx->w * ctx->h) / 4;
+    P.W = ctx->w; P.H = ctx->h;
+    lsd::SE3<double> init;
+    for (int i = 0; i < 4; i++) init.q[i] = init_qt[i];
+    for (int i = 0; i < 3; i++) init.t[i] = init_qt[4 + i];
+    lsd::SE3<float> r2f = lsd::se3Cast<float>(lsd::se3Inverse(init));             // SE3Tracker.cpp:306
+    for (int i = 0; i < 4; i++) P.initRefToFrame[i] = r2f.q[i];
+    for (int i = 0; i < 3; i++) P.initRefToFrame[4 + i] = r2f.t[i];
+    P.st = *st;
+    P.C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; P.C.var_weight = st->var_weight; P.C.huber_half = st->huber_d / 2;
+    P.useAffine = ctx->g.useAffineLightningEstimation;
+    P.partials = ctx->evPartials;
+    P.barrier = ctx->evCounter;
+    TrackState* dOut = (TrackState*)ctx->dTrackState;
+    TrackState* hOut = (TrackState*)ctx->hTrackState;
+
+    const int grid = ctx->smCount;            // one CTA per SM
+    void* args[] = { (void*)&P, (void*)&dOut };
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, sizeof(unsigned int), ctx->stream));   // barrier arrivals
+    if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
+    LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, 0, ctx->stream));
+    ctx->launches++;
+    if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
+    LSD_CHECK(ctx, cudaMemcpyAsync(hOut, dOut, sizeof(TrackState), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    fr->hasGoodMask = true;
+
+    if (ctx->profileTrackKernel) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->kBegin, ctx->kEnd);
+        ctx->trackKernelMs += ms;
+        ctx->trackKernelLaunches++;
+        double bytes = 0;
+        for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++)
+            bytes += (double)hOut->numCalcResidualCalls[l] * ((double)ctx->cam[l].w * ctx->cam[l].h * (12.0 + 16.0 + (l == 1 ? 1.0 : 0.0)) + EV_NCH * 4.0);
+        ctx->trackKernelBytes += bytes;
+    }
+
+    if (getenv("LSDGPU_TRACK_DEBUG")) {
+        fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
+                hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
+    }
+    out->pointUsage = hOut->pointUsage; out->lastGoodCount = hOut->goodCount; out->lastBadCount = hOut->badCount;
+    out->lastMeanRes = hOut->meanRes;
+    out->affineEstimation_a = hOut->affine_a; out->affineEstimation_b = hOut->affine_b;
+    for (int l = 0; l < LSD_LEVELS; l++) {
+        out->numCalcResidualCalls[l] = hOut->numCalcResidualCalls[l];
+        out->numCalcWarpUpdateCalls[l] = hOut->numCalcWarpUpdateCalls[l];
+    }
+    if (hOut->diverged) {
+        out->frameToRef_qt[3] = 1;
+        out->diverged = 1; out->trackingWasGood = 0;
+        return 0;
+    }
+    const int W = ctx->w, H = ctx->h;
+    out->lastResidual = hOut->lastResidual;
+    out->trackingWasGood = hOut->goodCount / ((W >> SE3TRACKING_MIN_LEVEL) * (H >> SE3TRACKING_MIN_LEVEL)) > 0.04f
+                           && hOut->goodCount / (hOut->goodCount + hOut->badCount) > 0.5f;
+    out->initialTrackedResidual = out->lastResidual / out->pointUsage;
+    lsd::SE3<float> T;
+    for (int i = 0; i < 4; i++) T.q[i] = hOut->refToFrame[i];
+    for (int i = 0; i < 3; i++) T.t[i] = hOut->refToFrame[4 + i];
+    lsd::SE3<double> f2r = lsd::se3Cast<double>(lsd::se3Inverse(T));
+    for (int i = 0; i < 4; i++) out->frameToRef_qt[i] = f2r.q[i];
+    for (int i = 0; i < 3; i++) out->frameToRef_qt[4 + i] = f2r.t[i];
+    return 0;
 }
