@@ -268,6 +268,12 @@ class Context:
         self._ck(self.L.lsdgpu_frame_get_depth_stats(self.ptr, fid, C.byref(m), C.byref(n), C.byref(f)))
         return m.value, n.value, bool(f.value)
 
+    def depth_updated_flag(self, fid: int) -> bool:
+        """Frame::depthHasBeenUpdatedFlag only (no device sync, unlike depth_stats)."""
+        f = C.c_int()
+        self._ck(self.L.lsdgpu_frame_get_depth_stats(self.ptr, fid, None, None, C.byref(f)))
+        return bool(f.value)
+
     def clear_good_mask(self, fid: int):
         self._ck(self.L.lsdgpu_frame_clear_good_mask(self.ptr, fid))
 

@@ -381,8 +381,9 @@ __device__ __forceinline__ bool makeAndCheckEPL(const DepthCam& cam, const float
 // pixel touches only its own record.
 __global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, DepthGlobals G,
                                                  const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
-                                                 const float* __restrict__ kfMaxGrad, const ObserveParams* __restrict__ OP)
+                                                 const float* __restrict__ kfMaxGrad, const __grid_constant__ ObserveParams OPv)
 {
+    const ObserveParams* OP = &OPv;
     const int x = 3 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = 3 + blockIdx.y;
     if (x >= cam.w - 3 || y >= cam.h - 3) return;
@@ -528,10 +529,29 @@ __global__ void __launch_bounds__(256) k_fill_holes(HypField src, HypField dst, 
 template <bool removeOcclusions>
 __global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G, int validityTH)
 {
-    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= cam.w || y >= cam.h) return;
+    // 32x8 output pixels per CTA; the 36x12 neighbourhood (idepth, var, validity, valid) is staged once in
+    // shared memory, so each hypothesis is fetched from L2 1.7x instead of 25x
+    __shared__ float4 tile[12][36];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x0 = blockIdx.x * 32 - 2, y0 = blockIdx.y * 8 - 2;
     const int width = cam.w;
+    for (int t = threadIdx.x; t < 12 * 36; t += 256) {
+        const int lx = t % 36, ly = t / 36;
+        const int gx = x0 + lx, gy = y0 + ly;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < width && gy >= 0 && gy < cam.h) {
+            const int4 si = src.hi[gx + gy * width];
+            if (si.x) {
+                const float4 s = src.hf[gx + gy * width];
+                e = make_float4(s.x, s.y, __int_as_float(si.z), __int_as_float(1));
+            }
+        }
+        tile[ly][lx] = e;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * 32 + tx;
+    const int y = blockIdx.y * 8 + ty;
+    if (x >= cam.w || y >= cam.h) return;
     const int idx = x + y * width;
     float4 hf = src.hf[idx];
     int4 hi = src.hi[idx];
@@ -541,10 +561,10 @@ __global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, 
         int numOccluding = 0, numNotOccluding = 0;
         for (int dx = -2; dx <= 2; dx++)                 // dx outer, dy inner as in the reference (:782-783)
             for (int dy = -2; dy <= 2; dy++) {
-                int o = idx + dx + dy * width;
-                int4 si = src.hi[o];
-                if (!si.x) continue;
-                float4 s = src.hf[o];
+                const float4 s = tile[ty + 2 + dy][tx + 2 + dx];
+                if (!__float_as_int(s.w)) continue;
+                int4 si;
+                si.z = __float_as_int(s.z);
                 float diff = s.x - hf.x;
                 if (DIFF_FAC_SMOOTHING * diff * diff > s.y + hf.y) {
                     if (removeOcclusions) {
@@ -575,12 +595,54 @@ __global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, 
     dst.hi[idx] = hi;
 }
 
-// Frame::setDepth, Frame.cpp:199-243 (+ per-CTA partial sums of idepth_smoothed / count, combined in order)
-__global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restrict__ idepth, float* __restrict__ idepthVar,
-                                                   int n, double* __restrict__ partials)
+// last-CTA-done combine of per-CTA (sum, count) partials in a fixed order; out[0] = sum, out[1] = count,
+// out[2] = rescaleFactor = count / sum evaluated in float like DepthMap.cpp:1294
+__device__ __forceinline__ void finishSumCount(double s, int c, double* __restrict__ partials, unsigned int* counter,
+                                               double* __restrict__ out)
 {
     __shared__ double ssum[8];
-    __shared__ int scnt[8];
+    __shared__ double scnt[8];
+    __shared__ bool isLast;
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = (double)c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0, tc = 0;
+        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
+        __stcg(partials + 2 * blockIdx.x, t);
+        __stcg(partials + 2 * blockIdx.x + 1, tc);
+        __threadfence();
+        unsigned int tk = atomicAdd(counter, 1u);
+        isLast = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    double a = 0, b = 0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += blockDim.x) { a += __ldcg(partials + 2 * k); b += __ldcg(partials + 2 * k + 1); }
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = a; scnt[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double S = 0, Cn = 0;
+        for (int k = 0; k < 8; k++) { S += ssum[k]; Cn += scnt[k]; }
+        out[0] = S; out[1] = Cn;
+        out[2] = (double)((float)Cn / (float)S);
+        *counter = 0;
+    }
+}
+
+// Frame::setDepth, Frame.cpp:199-243 (+ sum / count of the exported idepth_smoothed)
+__global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restrict__ idepth, float* __restrict__ idepthVar,
+                                                   int n, double* __restrict__ partials, unsigned int* counter, double* __restrict__ out)
+{
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0;
     int c = 0;
@@ -597,56 +659,17 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
             idepthVar[i] = -1;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0; int tc = 0;
-        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
-        partials[2 * blockIdx.x] = t;
-        partials[2 * blockIdx.x + 1] = (double)tc;
-    }
+    finishSumCount(s, c, partials, counter, out);
 }
-// sum of idepth_smoothed over valid hypotheses (createKeyFrame :1286-1293), same partial layout
-__global__ void __launch_bounds__(256) k_sum_idepth(HypField cur, int n, double* __restrict__ partials)
+// sum of idepth_smoothed over valid hypotheses (createKeyFrame :1286-1293)
+__global__ void __launch_bounds__(256) k_sum_idepth(HypField cur, int n, double* __restrict__ partials, unsigned int* counter,
+                                                    double* __restrict__ out)
 {
-    __shared__ double ssum[8];
-    __shared__ int scnt[8];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0.0;
     int c = 0;
     if (i < n && cur.hi[i].x) { s = cur.hf[i].z; c = 1; }
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if ((threadIdx.x & 31) == 0) { ssum[threadIdx.x >> 5] = s; scnt[threadIdx.x >> 5] = c; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0; int tc = 0;
-        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
-        partials[2 * blockIdx.x] = t;
-        partials[2 * blockIdx.x + 1] = (double)tc;
-    }
-}
-// ordered combine of the partials; out[0] = sum, out[1] = count, out[2] = rescaleFactor (float bits in double)
-__global__ void k_combine_partials(const double* __restrict__ partials, int nBlocks, double* __restrict__ out)
-{
-    __shared__ double ss[32], sc[32];
-    double s = 0, c = 0;
-    for (int b = threadIdx.x; b < nBlocks; b += 32) { s += partials[2 * b]; c += partials[2 * b + 1]; }
-    ss[threadIdx.x] = s; sc[threadIdx.x] = c;
-    __syncwarp();
-    if (threadIdx.x == 0) {
-        double S = 0, Cn = 0;
-        for (int k = 0; k < 32; k++) { S += ss[k]; Cn += sc[k]; }
-        out[0] = S; out[1] = Cn;
-        float rescaleFactor = (float)Cn / (float)S;       // :1294 (float division of the float-typed sums)
-        out[2] = (double)rescaleFactor;
-    }
+    finishSumCount(s, c, partials, counter, out);
 }
 // createKeyFrame :1295-1304
 __global__ void __launch_bounds__(256) k_rescale(HypField cur, int n, const double* __restrict__ scal)

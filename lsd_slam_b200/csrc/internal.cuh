@@ -45,6 +45,8 @@ struct FrameSlot {
     bool depthHasBeenUpdatedFlag = false;
     float meanIdepth = 1.f;
     int numPoints = 0;
+    double* dStats = nullptr;            // device: sum(idepth_smoothed), count, rescale (written by setDepth kernels)
+    bool statsPending = false;           // meanIdepth / numPoints still have to be fetched from dStats
     double thisToParent[8];
     int parentId = -1;
     float initialTrackedResidual = 0.f;
@@ -69,19 +71,20 @@ struct RefConst {
     const float* image;           // level 0
     const uint8_t* goodMask;      // refPixelWasGoodNoCreate() or nullptr
 };
-#define LSD_MAX_REFS 64
+#define LSD_MAX_REFS 16
+#define LSD_MAX_ID_SPAN 64
 struct ObserveParams {
     RefConst refs[LSD_MAX_REFS];
     int nRefs;
     int byIdOffset, byIdSize;     // referenceFrameByID_offset / size
-    int byId[256];                // id - offset -> index into refs
+    int byId[LSD_MAX_ID_SPAN];    // id - offset -> index into refs
     int oldestIdx, newestIdx;
     int reactivated;
     int kfNumTracked, kfNumMapped;
 };
 
 // number of reduction channels of one tracker evaluation (see track.cuh)
-#define EV_NCH 44
+#define EV_NCH 40
 
 struct lsdgpu_ctx {
     int device = 0;
@@ -102,8 +105,7 @@ struct lsdgpu_ctx {
     int* integral = nullptr;
     int activeKf = -1;
     bool activeKfReactivated = false;
-    ObserveParams* dObs = nullptr;       // device copy
-    ObserveParams* hObs = nullptr;       // pinned host staging
+    ObserveParams hObs;                  // passed to k_observe by value (__grid_constant__)
     int* propHead = nullptr;             // per-target list heads (propagateDepth)
     int* propNext = nullptr;
     float4* propVal = nullptr;           // per-source (new_idepth, new_var, validity, -)
@@ -119,8 +121,10 @@ struct lsdgpu_ctx {
     void* hTrackState = nullptr;         // pinned mirror
     uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
     int stageEntries = 0;
-    uint8_t* hStage = nullptr;           // pinned staging for the u8 frame upload
-    uint8_t* dStageU8 = nullptr;
+    uint8_t* hStage[2] = { nullptr, nullptr };   // double-buffered pinned staging for the u8 frame upload
+    uint8_t* dStageU8[2] = { nullptr, nullptr };
+    cudaEvent_t stageDone[2];
+    int stageIdx = 0;
     float* hStageF = nullptr;            // pinned float staging (depth / idepth uploads)
     float* dStageF = nullptr;
 

@@ -85,8 +85,8 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     size_t depthBytes = 2 * (alignUp(n0 * 16, 256) * 2) + alignUp(n0 * 4, 256)           // cur/oth hf+hi, integral
                         + 2 * alignUp(n0 * 4, 256) + alignUp(n0 * 16, 256);              // prop head/next/val
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
-    size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
-                     + alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256)
+    size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
+                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + 256 * (size_t)max_frames
                      + alignUp(sizeof(TrackState), 256) + 4096;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
@@ -113,19 +113,23 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     ctx->propHead = (int*)take(n0 * 4);
     ctx->propNext = (int*)take(n0 * 4);
     ctx->propVal = (float4*)take(n0 * 16);
-    ctx->evPartials = (float*)take((size_t)maxBlocks * EV_NCH * 4);
+    ctx->evPartials = (float*)take((size_t)maxBlocks * EV_NCH * 4 + 65536);   // also holds the 2 x 160 x 192 B exchange rows of mode 1
     ctx->evCounter = (unsigned int*)take(256);
     ctx->dEvOut = (float*)take(EV_NCH * 4);
-    ctx->dObs = (ObserveParams*)take(sizeof(ObserveParams));
-    ctx->dStageU8 = (uint8_t*)take(n0);
+    ctx->dStageU8[0] = (uint8_t*)take(n0);
+    ctx->dStageU8[1] = (uint8_t*)take(n0);
+    for (auto& s : ctx->slots) s.dStats = (double*)take(64);
     ctx->dStageF = (float*)take(n0 * 32);
     ctx->dScalars = (double*)take((size_t)maxBlocks * 2 * 8 + 64);
     ctx->dTrackState = take(sizeof(TrackState));
     if ((size_t)(p - ctx->arena) > ctx->arenaBytes) return lsd_fail(ctx, "arena overflow");
 
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hEvOut, EV_NCH * 4, cudaHostAllocDefault));
-    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hObs, sizeof(ObserveParams), cudaHostAllocDefault));
-    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStage, n0, cudaHostAllocDefault));
+    for (int i = 0; i < 2; i++) {
+        LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStage[i], n0, cudaHostAllocDefault));
+        LSD_CHECK(ctx, cudaEventCreateWithFlags(&ctx->stageDone[i], cudaEventDisableTiming));
+        LSD_CHECK(ctx, cudaEventRecord(ctx->stageDone[i], ctx->stream));
+    }
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStageF, n0 * 32, cudaHostAllocDefault));
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hScalars, 64, cudaHostAllocDefault));
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hTrackState, sizeof(TrackState), cudaHostAllocDefault));
@@ -147,7 +151,8 @@ extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->arena);
     if (ctx->stageRing) cudaFree(ctx->stageRing);
-    cudaFreeHost(ctx->hEvOut); cudaFreeHost(ctx->hObs); cudaFreeHost(ctx->hStage); cudaFreeHost(ctx->hStageF);
+    cudaFreeHost(ctx->hEvOut); cudaFreeHost(ctx->hStage[0]); cudaFreeHost(ctx->hStage[1]); cudaFreeHost(ctx->hStageF);
+    cudaEventDestroy(ctx->stageDone[0]); cudaEventDestroy(ctx->stageDone[1]);
     cudaFreeHost(ctx->hScalars); cudaFreeHost(ctx->hTrackState);
     for (int i = 0; i < 8; i++) { if (ctx->tBegin[i]) cudaEventDestroy(ctx->tBegin[i]); if (ctx->tEnd[i]) cudaEventDestroy(ctx->tEnd[i]); }
     if (ctx->kBegin) cudaEventDestroy(ctx->kBegin);
@@ -208,7 +213,7 @@ static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
             fresh.id = id; fresh.used = true;
             fresh.hasDepth = fresh.idepthPyrValid = fresh.hasGoodMask = false;
             fresh.depthHasBeenUpdatedFlag = false;
-            fresh.meanIdepth = 1.f; fresh.numPoints = 0;
+            fresh.meanIdepth = 1.f; fresh.numPoints = 0; fresh.statsPending = false;
             memset(fresh.thisToParent, 0, sizeof(fresh.thisToParent));
             fresh.thisToParent[3] = 1; fresh.thisToParent[7] = 1;
             fresh.parentId = -1; fresh.initialTrackedResidual = 0;
@@ -227,11 +232,15 @@ extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8
     FrameSlot* s = acquireSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
     const size_t n0 = (size_t)ctx->w * ctx->h;
-    // the staging buffer may still be in flight from the previous upload
-    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->hStage, gray, n0);
-    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8, ctx->hStage, n0, cudaMemcpyHostToDevice, ctx->stream));
-    return buildFrameFromDeviceU8(ctx, s, ctx->dStageU8);
+    // double-buffered pinned staging: only wait for the upload issued two frames ago
+    const int b = ctx->stageIdx;
+    ctx->stageIdx ^= 1;
+    LSD_CHECK(ctx, cudaEventSynchronize(ctx->stageDone[b]));
+    memcpy(ctx->hStage[b], gray, n0);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8[b], ctx->hStage[b], n0, cudaMemcpyHostToDevice, ctx->stream));
+    int r = buildFrameFromDeviceU8(ctx, s, ctx->dStageU8[b]);
+    LSD_CHECK(ctx, cudaEventRecord(ctx->stageDone[b], ctx->stream));
+    return r;
 }
 
 extern "C" int lsdgpu_stage_reserve(lsdgpu_ctx* ctx, int n_entries)
@@ -250,8 +259,8 @@ extern "C" int lsdgpu_stage_put(lsdgpu_ctx* ctx, int index, const uint8_t* gray)
     if (index < 0 || index >= ctx->stageEntries) return lsd_fail(ctx, "bad ring index");
     const size_t n0 = (size_t)ctx->w * ctx->h;
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    memcpy(ctx->hStage, gray, n0);
-    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->stageRing + (size_t)index * n0, ctx->hStage, n0, cudaMemcpyHostToDevice, ctx->stream));
+    memcpy(ctx->hStage[0], gray, n0);
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->stageRing + (size_t)index * n0, ctx->hStage[0], n0, cudaMemcpyHostToDevice, ctx->stream));
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
@@ -401,6 +410,14 @@ extern "C" int lsdgpu_frame_get_depth_stats(lsdgpu_ctx* ctx, int frame_id, float
 {
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
+    if ((meanIdepth || numPoints) && s->statsPending) {      // fetched lazily: keeps updateKeyframe free of host syncs
+        LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+        LSD_CHECK(ctx, cudaMemcpyAsync(ctx->hScalars, s->dStats, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        s->numPoints = (int)ctx->hScalars[1];
+        s->meanIdepth = (float)ctx->hScalars[0] / (float)s->numPoints;     // Frame.cpp:234
+        s->statsPending = false;
+    }
     if (meanIdepth) *meanIdepth = s->meanIdepth;
     if (numPoints) *numPoints = s->numPoints;
     if (flag) *flag = s->depthHasBeenUpdatedFlag ? 1 : 0;
@@ -651,15 +668,11 @@ static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf)
 {
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
-    k_set_depth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, kf->idepth[0], kf->idepthVar[0], n, ctx->dScalars + 8);
-    LAUNCH(ctx);
-    k_combine_partials<<<1, 32, 0, ctx->stream>>>(ctx->dScalars + 8, nb, ctx->dScalars);
+    k_set_depth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, kf->idepth[0], kf->idepthVar[0], n, ctx->dScalars + 8,
+                                             ctx->evCounter + 48, kf->dStats);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
-    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->hScalars, ctx->dScalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    kf->numPoints = (int)ctx->hScalars[1];
-    kf->meanIdepth = (float)ctx->hScalars[0] / (float)kf->numPoints;
+    kf->statsPending = true;
     kf->hasDepth = true; kf->idepthPyrValid = false;
     kf->depthHasBeenUpdatedFlag = true;
     return 0;
@@ -786,8 +799,7 @@ static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, Ref
 static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
 {   // DepthMap.cpp:1079-1105
     if (n_refs <= 0 || n_refs > LSD_MAX_REFS) return lsd_fail(ctx, "bad number of reference frames");
-    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // hObs may still be in flight
-    ObserveParams& OP = *ctx->hObs;
+    ObserveParams& OP = ctx->hObs;
     OP.nRefs = n_refs;
     OP.byIdSize = 0;
     for (int k = 0; k < n_refs; k++) {
@@ -803,14 +815,13 @@ static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSl
         rc.goodMask = fr->hasGoodMask ? fr->goodMask : nullptr;
         if (k == 0) OP.byIdOffset = fr->id;
         while (OP.byIdSize + OP.byIdOffset <= fr->id) {
-            if (OP.byIdSize >= 256) return lsd_fail(ctx, "reference id span too large");
+            if (OP.byIdSize >= LSD_MAX_ID_SPAN) return lsd_fail(ctx, "reference id span too large");
             OP.byId[OP.byIdSize++] = k;
         }
     }
     OP.oldestIdx = 0; OP.newestIdx = n_refs - 1;
     OP.reactivated = ctx->activeKfReactivated ? 1 : 0;
     OP.kfNumTracked = kf->numFramesTrackedOnThis; OP.kfNumMapped = kf->numMappedOnThis;
-    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dObs, ctx->hObs, sizeof(ObserveParams), cudaMemcpyHostToDevice, ctx->stream));
     return 0;
 }
 
@@ -823,7 +834,7 @@ static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
     dim3 grid(divUp(cam.w - 6, 128), cam.h - 6);
-    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->dObs);
+    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -926,9 +937,7 @@ extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, doub
     if (r) return r;
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
-    k_sum_idepth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars + 8);                   // :1286-1293
-    LAUNCH(ctx);
-    k_combine_partials<<<1, 32, 0, ctx->stream>>>(ctx->dScalars + 8, nb, ctx->dScalars);
+    k_sum_idepth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars + 8, ctx->evCounter + 48, ctx->dScalars);   // :1286-1293
     LAUNCH(ctx);
     k_rescale<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars);                          // :1295-1304
     LAUNCH(ctx);

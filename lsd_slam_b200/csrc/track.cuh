@@ -21,14 +21,13 @@
 enum {
     CH_A = 0,        // 21 upper-triangle entries of sum J J^T w, row-major (i <= j)
     CH_B = 21,       // 6: sum J r w        (LGS6::b = -this)
-    CH_ERR = 27,     // sum r r w           (LGS6::error)
-    CH_SUMRESW = 28, // sum wh w_p r r      (calcWeightsAndResidual)
-    CH_SUMRESU = 29, // sum r r over good   (sumResUnweighted)
-    CH_SIGNED = 30,  // sum r over good     (sumSignedRes)
-    CH_GOOD = 31, CH_BAD = 32, CH_USAGE = 33,
-    CH_WARPED = 34,  // buf_warped_size
-    CH_REFNUM = 35,  // numData[level]
-    CH_SXX = 36, CH_SYY = 37, CH_SX = 38, CH_SY = 39, CH_SW = 40
+    CH_SUMRESW = 27, // sum wh w_p r r      (calcWeightsAndResidual; LGS6::error is the same sum, LGSX.h:394)
+    CH_SUMRESU = 28, // sum r r over good   (sumResUnweighted)
+    CH_SIGNED = 29,  // sum r over good     (sumSignedRes)
+    CH_GOOD = 30, CH_BAD = 31,              // buf_warped_size == good + bad (exact: integer-valued floats)
+    CH_USAGE = 32,
+    CH_REFNUM = 33,  // numData[level]
+    CH_SXX = 34, CH_SYY = 35, CH_SX = 36, CH_SY = 37, CH_SW = 38      // 39: unused (pads to 32 + 8)
 };
 
 struct EvalLevel {
@@ -99,7 +98,6 @@ __device__ __forceinline__ int evalPoint(float px, float py, float pz, float col
 
     float gx = fx_l * gi0, gy = fy_l * gi1;                                       // :972-973
     float d = 1.0f / pz;                                                          // :976
-    acc.v[CH_WARPED] += 1.f;
     if (isGood) {                                                                 // :981-988
         acc.v[CH_SUMRESU] += residual * residual;
         acc.v[CH_SIGNED] += residual;
@@ -140,7 +138,6 @@ __device__ __forceinline__ int evalPoint(float px, float py, float pz, float col
     float rw = residual * wgt;
 #pragma unroll
     for (int i = 0; i < 6; i++) acc.v[CH_B + i] += J[i] * rw;
-    acc.v[CH_ERR] += residual * residual * wgt;
     return isGood ? 1 : 0;
 }
 
@@ -227,14 +224,14 @@ LSD_HD void evalFinish(const float* s, lsdgpu_eval_result* r)
 {
     static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
                                             {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
-    const float n = s[CH_WARPED];
+    const float n = s[CH_GOOD] + s[CH_BAD];               // buf_warped_size
     for (int k = 0; k < 21; k++) {
         float a = s[CH_A + k] / n;                         // LGS6::finish, LGSX.h:319-325
         r->A[ij[k][0] * 6 + ij[k][1]] = a;
         r->A[ij[k][1] * 6 + ij[k][0]] = a;
     }
     for (int k = 0; k < 6; k++) r->b[k] = -s[CH_B + k] / n;
-    r->lsError = s[CH_ERR] / n;
+    r->lsError = s[CH_SUMRESW] / n;                       // LGS6::error: same sum as calcWeightsAndResidual's
     r->meanWeightedRes = s[CH_SUMRESW] / n;                // SE3Tracker.cpp:789
     r->meanUnweightedRes = s[CH_SUMRESU] / s[CH_GOOD];     // :1028
     r->warpedSize = (int)n;

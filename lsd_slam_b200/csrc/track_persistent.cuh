@@ -18,6 +18,8 @@
 #include <stdlib.h>
 
 #define TP_THREADS 512
+#define TP_MAXGRID_DBG 160
+#define EX_ROW 48                    // floats per exchange row (192 B): EV_NCH data + tag + pad
 #define TP_LOCAL_MAX_PIXELS 1024      // levels up to this many pixels are evaluated redundantly per CTA
 
 struct TrackLevelParams {
@@ -40,7 +42,7 @@ struct TrackParams {
     EvalConsts C;
     int useAffine;
     float* partials;                 // [2][EV_NCH][gridDim]
-    unsigned int* barrier;           // monotonically increasing arrival counter
+    unsigned int* barrier;           // [0] arrival counter (monotonic), [32] released-epoch flag
 };
 
 // what the kernel hands back (block 0 writes it)
@@ -53,19 +55,27 @@ struct TrackState {
     int numCalcWarpUpdateCalls[LSD_LEVELS];
     int totalEvals;
     long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
+    long long cycBlk[TP_MAXGRID_DBG][6];   // the same per CTA (debug)
 };
 
-// grid-wide barrier on a monotonically increasing counter; `target` = arrivals expected so far
-__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int target)
+// Grid-wide barrier.  Arrivals are counted on `counter[0]` (monotonic: epoch e completes at e * gridDim
+// arrivals); the LAST arriver publishes the epoch number in `counter[32]` (a different 128-byte line), which is
+// what everybody else polls -- the pollers never touch the line the atomics serialise on.  Thread 0 carries the
+// release / acquire for its CTA (the fences are cumulative over the preceding / following __syncthreads).
+__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int epoch)
 {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        atomicAdd(counter, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-        } while (v < target);
+        __threadfence();
+        const unsigned int old = atomicAdd(counter, 1u);
+        volatile unsigned int* flag = counter + 32;
+        if (old == epoch * gridDim.x - 1u) {
+            __threadfence();
+            *flag = epoch;
+        } else {
+            while (*flag < epoch) { }
+        }
+        __threadfence();
     }
     __syncthreads();
 }
@@ -118,22 +128,18 @@ template <int K> __device__ __forceinline__ int warpReduceChannel(int lane)
     return c;
 }
 
-// all EV_NCH (= 32 + 8 + 4) channels of a thread's accumulator -> per-warp totals in sm[warp][*]
+// all EV_NCH (= 32 + 8) channels of a thread's accumulator -> per-warp totals in sm[warp][*] (39 shuffles)
 __device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* smRow)
 {
-    float a32[32], a8[8], a4[4];
+    float a32[32], a8[8];
 #pragma unroll
     for (int i = 0; i < 32; i++) a32[i] = acc.v[i];
 #pragma unroll
     for (int i = 0; i < 8; i++) a8[i] = acc.v[32 + i];
-#pragma unroll
-    for (int i = 0; i < 4; i++) a4[i] = acc.v[40 + i];
     warpReduceMulti<32>(a32, lane);
     warpReduceMulti<8>(a8, lane);
-    warpReduceMulti<4>(a4, lane);
     smRow[lane] = a32[0];
     if ((lane & 3) == 0) smRow[32 + warpReduceChannel<8>(lane)] = a8[0];
-    if ((lane & 7) == 0) smRow[40 + warpReduceChannel<4>(lane)] = a4[0];
 }
 
 #define TP_WARPS (TP_THREADS / 32)
@@ -154,7 +160,9 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
     const int w = L.w, h = L.h, n = w * h;
     const float4* fg = L.frameGrad;
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
-    const int first = local ? threadIdx.x : blockIdx.x * TP_THREADS + threadIdx.x;
+    // 32-pixel chunks are dealt round-robin to the CTAs (chunk c -> CTA c % G, warp (c / G) % TP_WARPS): the
+    // semi-dense density varies over the image, a contiguous split would leave CTAs unevenly loaded
+    const int first = local ? threadIdx.x : ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
     const int stride = local ? TP_THREADS : gridDim.x * TP_THREADS;
     for (int i = first; i < n; i += stride) {
         const int x = i % w, y = i / w;
@@ -186,35 +194,38 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
         cyc[0] += t1 - t0; cyc[1] += t2 - t1;
         return;
     }
+    // ---- exchange: one partial row per CTA ([parity][channel][cta], written through to L2), ONE grid barrier,
+    // then every CTA combines all rows in a fixed order (measured alternatives: per-row tag polling without a
+    // barrier is slower -- 148 x 148 polling loads saturate L2)
     const unsigned int parity = epoch & 1u;
     float* part = p.partials + (size_t)parity * EV_NCH * gridDim.x;
     if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
     epoch++;
     long long t2 = clock64();
-    gridBarrier(p.barrier, epoch * gridDim.x);
+    gridBarrier(p.barrier, epoch);
     long long t3 = clock64();
-    // every CTA combines all partial rows in a fixed order: warp wi owns channels wi, wi+TP_WARPS, ... (<= 8 per
-    // warp); all loads are issued first, then one multi-value reduction in double.
+    // warp wi owns channels wi, wi+TP_WARPS, ... (<= 3 per warp); all loads are issued first, then one
+    // multi-value reduction in double
     {
-        double ch[8];
+        double ch[4];
         const int nb = (int)gridDim.x;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 4; k++) {
             const int c = warp + k * TP_WARPS;
             float v[TP_MAXGRID / 32];
 #pragma unroll
             for (int j = 0; j < TP_MAXGRID / 32; j++) {
-                const int b = lane + 32 * j;
-                v[j] = (c < EV_NCH && b < nb) ? __ldcg(part + (size_t)c * nb + b) : 0.f;
+                const int bb = lane + 32 * j;
+                v[j] = (c < EV_NCH && bb < nb) ? __ldcg(part + (size_t)c * nb + bb) : 0.f;
             }
-            double s = 0.0;
+            double sacc = 0.0;
 #pragma unroll
-            for (int j = 0; j < TP_MAXGRID / 32; j++) s += (double)v[j];
-            ch[k] = s;
+            for (int j = 0; j < TP_MAXGRID / 32; j++) sacc += (double)v[j];
+            ch[k] = sacc;
         }
-        warpReduceMulti<8>(ch, lane);
-        if ((lane & 3) == 0) {
-            const int c = warp + warpReduceChannel<8>(lane) * TP_WARPS;
+        warpReduceMulti<4>(ch, lane);
+        if ((lane & 7) == 0) {
+            const int c = warp + warpReduceChannel<4>(lane) * TP_WARPS;
             if (c < EV_NCH) sh.sums[c] = (float)ch[0];
         }
     }
@@ -338,7 +349,7 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
 {
     const float* s = sh.sums;
     const int lvl = lm.lvl;
-    const float warped = s[CH_WARPED];
+    const float warped = s[CH_GOOD] + s[CH_BAD];
     sh.action = ACT_CONTINUE;
     if (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) {                          // :324-329 / :369-374
         lm.diverged = 1;
@@ -386,7 +397,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     __shared__ LMShared sh;
     __shared__ LMState lm;
     __shared__ float sm[TP_THREADS / 32][EV_NCH];
-    static_assert(EV_NCH == 44, "warpReduceAcc is written for 32 + 8 + 4 channels");
+    static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
     unsigned int epoch = 0;
     long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
     const long long tStart = clock64();
@@ -418,6 +429,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         if (sh.action != ACT_CONTINUE) break;
     }
 
+    if (threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
+        long long tot = clock64() - tStart;
+        for (int i = 0; i < 4; i++) out->cycBlk[blockIdx.x][i] = cyc[i];
+        out->cycBlk[blockIdx.x][5] = tot;
+        out->cycBlk[blockIdx.x][4] = tot - cyc[0] - cyc[1] - cyc[2] - cyc[3];
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         lsdgpu_eval_result ev;
         evalFinish(sh.sums, &ev);        // statistics of the LAST EVALUATED pose
@@ -475,9 +492,9 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     TrackState* dOut = (TrackState*)ctx->dTrackState;
     TrackState* hOut = (TrackState*)ctx->hTrackState;
 
-    const int grid = ctx->smCount;            // one CTA per SM
+    const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM
     void* args[] = { (void*)&P, (void*)&dOut };
-    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, sizeof(unsigned int), ctx->stream));   // barrier arrivals
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, 33 * sizeof(unsigned int), ctx->stream));   // arrivals + epoch flag
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
     LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, 0, ctx->stream));
     ctx->launches++;
@@ -500,6 +517,17 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     if (getenv("LSDGPU_TRACK_DEBUG")) {
         fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
                 hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
+        const char* nm[6] = { "points", "ctaReduce", "barrier", "combine", "serial", "total" };
+        for (int k = 0; k < 6; k++) {
+            long long mn = 1LL << 60, mx = 0, sum = 0; int imx = 0, imn = 0;
+            for (int b = 0; b < grid && b < TP_MAXGRID_DBG; b++) {
+                long long v = hOut->cycBlk[b][k];
+                if (v < mn) { mn = v; imn = b; }
+                if (v > mx) { mx = v; imx = b; }
+                sum += v;
+            }
+            fprintf(stderr, "   %-9s min=%lld (cta %d) max=%lld (cta %d) mean=%lld\n", nm[k], mn, imn, mx, imx, sum / grid);
+        }
     }
     out->pointUsage = hOut->pointUsage; out->lastGoodCount = hOut->goodCount; out->lastBadCount = hOut->badCount;
     out->lastMeanRes = hOut->meanRes;

@@ -46,7 +46,7 @@ class GpuStream:
             ctx.frame_from_stage(fid, stage_index)
         else:
             ctx.upload(fid, image_u8)
-        if ctx.depth_stats(self.kf_id)[2]:
+        if ctx.depth_updated_flag(self.kf_id):
             self.tracker.importFrame(self.kf_id)
         pose = self.tracker.trackFrame(self.kf_id, fid, self.last_pose)
         self.n_tracked += 1
