@@ -163,6 +163,17 @@ int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int level, const f
 int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double frameToRef_init_qt[7],
                      const lsdgpu_track_settings* s, int mode, lsdgpu_track_result* out);
 
+/* Point-sharded tracking across GPUs (BASELINE config 5): rank `shard` of `n_shards` evaluates every
+ * n_shards-th 32-pixel chunk of the level; the LSDGPU_EVAL_NSUMS partial sums of every evaluation are handed to
+ * `allreduce` (sum over ranks, in place, HOST buffer) before the LM decision, so all ranks take identical
+ * decisions.  Same host-driven LM loop as mode 0.  The refPixelWasGood mask is only written for the rank's own
+ * chunks (the depth map is not sharded: "replicas only"). */
+#define LSDGPU_EVAL_NSUMS 40
+typedef void (*lsdgpu_allreduce_fn)(void* user, float* sums, int n);
+int lsdgpu_se3_track_sharded(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double frameToRef_init_qt[7],
+                             const lsdgpu_track_settings* s, int shard, int n_shards,
+                             lsdgpu_allreduce_fn allreduce, void* user, lsdgpu_track_result* out);
+
 /* ---- DepthMap: DepthEstimation/DepthMap.cpp ------------------------------------------------------ */
 int lsdgpu_depth_reset(lsdgpu_ctx* ctx);                                  /* DepthMap::reset :102-108 */
 int lsdgpu_depth_is_valid(lsdgpu_ctx* ctx);                               /* DepthMap::isValid, DepthMap.h:71 */

@@ -16,6 +16,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblsdgpu.so")
 LEVELS = 5
 
+EVAL_NSUMS = 40
+ALLREDUCE_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(C.c_float), C.c_int)
+
 BUF_IMAGE, BUF_GRADIENTS, BUF_MAXGRAD, BUF_IDEPTH, BUF_IDEPTH_VAR, BUF_GOODMASK = range(6)
 
 
@@ -96,6 +99,7 @@ SYMBOLS = [
     ("lsdgpu_ref_import", C.c_int, [_vp, C.c_int]),
     ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
     ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
+    ("lsdgpu_se3_track_sharded", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     ("lsdgpu_depth_reset", C.c_int, [_vp]),
     ("lsdgpu_depth_is_valid", C.c_int, [_vp]),
     ("lsdgpu_depth_invalidate", C.c_int, [_vp]),

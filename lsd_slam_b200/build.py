@@ -46,5 +46,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
 
 
+HOST_SRC = os.path.join(HERE, "host", "lsd_host.cpp")
+HOST_OUT = os.path.join(HERE, "liblsdgpu_host.so")
+DEMO_SRC = os.path.join(HERE, "host", "host_demo.cpp")
+DEMO_OUT = os.path.join(HERE, "host_demo")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ host classes (reference call signatures) + the demo driver; plain g++, links liblsdgpu.so."""
+    srcs = [HOST_SRC, DEMO_SRC, os.path.join(HERE, "host", "lsd_host.h"), OUT]
+    if not force and os.path.exists(HOST_OUT) and os.path.exists(DEMO_OUT) and \
+            all(os.path.getmtime(x) <= min(os.path.getmtime(HOST_OUT), os.path.getmtime(DEMO_OUT)) for x in srcs):
+        return HOST_OUT
+    common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wl,-rpath,$ORIGIN", "-L" + HERE]
+    for cmd in (common + ["-fPIC", "-shared", "-o", HOST_OUT, HOST_SRC, "-l:liblsdgpu.so"],
+                common + ["-o", DEMO_OUT, DEMO_SRC, "-l:liblsdgpu_host.so", "-l:liblsdgpu.so"]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return HOST_OUT
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_host(force=True))

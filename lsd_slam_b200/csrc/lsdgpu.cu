@@ -463,6 +463,7 @@ static void fillEvalLevel(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, int lev
     L.w = c.w; L.h = c.h;
     L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
     L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+    L.shard = 0; L.nShards = 1;
 }
 
 // one evaluation launch + readback of the EV_NCH sums into ctx->hEvOut (synchronous)
@@ -522,7 +523,8 @@ extern "C" int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int lev
 
 // SE3Tracker::trackFrame with the LM loop on the host (mode 0): a line-by-line mirror of SE3Tracker.cpp:280-486
 static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
-                       const lsdgpu_track_settings* st, lsdgpu_track_result* out)
+                       const lsdgpu_track_settings* st, lsdgpu_track_result* out,
+                       int shard = 0, int nShards = 1, lsdgpu_allreduce_fn allreduce = nullptr, void* user = nullptr)
 {
     memset(out, 0, sizeof(*out));
     bool diverged = false;
@@ -540,8 +542,10 @@ static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const doub
     for (int lvl = SE3TRACKING_MAX_LEVEL - 1; lvl >= SE3TRACKING_MIN_LEVEL && !diverged; lvl--) {
         EvalLevel L;
         fillEvalLevel(ctx, kf, fr, lvl, lvl == SE3TRACKING_MIN_LEVEL, L);
+        L.shard = shard; L.nShards = nShards;
         int r = runEval(ctx, L, referenceToFrame, affine_a, affine_b, st);
         if (r) return r;
+        if (allreduce) allreduce(user, ctx->hEvOut, EV_NCH);
         evalFinish(ctx->hEvOut, &ev);
         if (ev.warpedSize < 0.01f * (W >> lvl) * (H >> lvl)) { diverged = true; break; }   // :324-329
         if (ctx->g.useAffineLightningEstimation) { affine_a = ev.affine_a_lastIt; affine_b = ev.affine_b_lastIt; }
@@ -565,6 +569,7 @@ static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const doub
                 lsd::SE3<float> new_referenceToFrame = lsd::se3Mul(lsd::se3Exp(inc), referenceToFrame);   // :363
                 r = runEval(ctx, L, new_referenceToFrame, affine_a, affine_b, st);
                 if (r) return r;
+                if (allreduce) allreduce(user, ctx->hEvOut, EV_NCH);
                 evalFinish(ctx->hEvOut, &ev);
                 if (ev.warpedSize < 0.01f * (W >> lvl) * (H >> lvl)) { diverged = true; break; }
                 float error = ev.meanWeightedRes;
@@ -626,6 +631,34 @@ extern "C" int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const 
         for (int i = 0; i < 7; i++) fr->thisToParent[i] = out->frameToRef_qt[i];  // :483 sim3FromSE3(.., 1)
         fr->thisToParent[7] = 1.0;
         fr->parentId = kf->id;                                                    // :484
+    }
+    return 0;
+}
+
+static_assert(LSDGPU_EVAL_NSUMS == EV_NCH, "ABI constant out of sync with the kernel's channel count");
+
+extern "C" int lsdgpu_se3_track_sharded(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double init_qt[7],
+                                        const lsdgpu_track_settings* s, int shard, int n_shards,
+                                        lsdgpu_allreduce_fn allreduce, void* user, lsdgpu_track_result* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    FrameSlot* fr = findSlot(ctx, frame_id);
+    if (!kf || !fr) return lsd_fail(ctx, "unknown frame id");
+    if (n_shards < 1 || shard < 0 || shard >= n_shards) return lsd_fail(ctx, "bad shard");
+    if (n_shards > 1 && !allreduce) return lsd_fail(ctx, "sharded tracking needs an all-reduce callback");
+    int r = ensureIdepthPyramid(ctx, kf);
+    if (r) return r;
+    lsdgpu_track_settings ds;
+    if (!s) { lsdgpu_default_track_settings(&ds); ds.maxItsPerLvl[4] = 0; s = &ds; }
+    r = trackHostLM(ctx, kf, fr, init_qt, s, out, shard, n_shards, allreduce, user);
+    if (r) return r;
+    if (!out->diverged) {
+        if (out->trackingWasGood) kf->numFramesTrackedOnThis++;
+        fr->initialTrackedResidual = out->initialTrackedResidual;
+        for (int i = 0; i < 7; i++) fr->thisToParent[i] = out->frameToRef_qt[i];
+        fr->thisToParent[7] = 1.0;
+        fr->parentId = kf->id;
     }
     return 0;
 }

@@ -38,6 +38,7 @@ struct EvalLevel {
     uint8_t* goodMask;              // level-1 mask or nullptr
     int w, h;
     float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
+    int shard, nShards;             // point sharding across GPUs: this rank owns 32-px chunks c with c % nShards == shard
 };
 struct EvalPose {
     float R[9], t[3];
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_se3_eval(EvalLevel L, EvalPose
     const int w = L.w, h = L.h;
     if (i < w * h) {
         const int x = i % w, y = i / w;
-        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1 && (L.nShards <= 1 || ((i >> 5) % L.nShards) == L.shard)) {
             const float idepth = L.kfIdepth[i], var = L.kfVar[i];
             if (!(var <= 0 || idepth == 0)) {                     // TrackingReference.cpp:133
                 const float sc = 1.0f / idepth;                   // :135

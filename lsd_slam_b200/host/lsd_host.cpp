@@ -1,0 +1,238 @@
+// lsd_host.cpp -- implementation of lsd_host.h over the C ABI.  See the header for the reference citations.
+#include "lsd_host.h"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+namespace lsd_slam {
+
+static void qmul(const double a[4], const double b[4], double o[4])
+{
+    double w = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+    double x = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+    double y = a[3] * b[1] + a[1] * b[3] + a[2] * b[0] - a[0] * b[2];
+    double z = a[3] * b[2] + a[2] * b[3] + a[0] * b[1] - a[1] * b[0];
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w;
+}
+static void qrot(const double q[4], const double v[3], double o[3])
+{
+    double ux = q[1] * v[2] - q[2] * v[1], uy = q[2] * v[0] - q[0] * v[2], uz = q[0] * v[1] - q[1] * v[0];
+    ux += ux; uy += uy; uz += uz;
+    o[0] = v[0] + q[3] * ux + (q[1] * uz - q[2] * uy);
+    o[1] = v[1] + q[3] * uy + (q[2] * ux - q[0] * uz);
+    o[2] = v[2] + q[3] * uz + (q[0] * uy - q[1] * ux);
+}
+static void qnorm(double q[4])
+{
+    double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; i++) q[i] /= n;
+}
+SE3 SE3::inverse() const
+{   // thirdparty/Sophus/sophus/se3.hpp:167-172
+    SE3 r;
+    r.q[0] = -q[0]; r.q[1] = -q[1]; r.q[2] = -q[2]; r.q[3] = q[3];
+    qnorm(r.q);
+    double nt[3] = { -t[0], -t[1], -t[2] };
+    qrot(r.q, nt, r.t);
+    return r;
+}
+SE3 SE3::operator*(const SE3& o) const
+{   // se3.hpp:239-259
+    SE3 r;
+    double rt[3];
+    qrot(q, o.t, rt);
+    qmul(q, o.q, r.q);
+    qnorm(r.q);
+    for (int i = 0; i < 3; i++) r.t[i] = t[i] + rt[i];
+    return r;
+}
+
+DeviceContext::DeviceContext(int device, int w, int h, const Matrix3f& K, int maxFrames) : w_(w), h_(h)
+{
+    int rc = lsdgpu_create(device, w, h, K.m, maxFrames, &ctx_);
+    if (rc != 0) {
+        std::string msg = ctx_ ? lsdgpu_last_error(ctx_) : "lsdgpu_create failed (bad size: width and height must be multiples of 16)";
+        if (ctx_) lsdgpu_destroy(ctx_);
+        ctx_ = nullptr;
+        throw LsdGpuError(msg);
+    }
+}
+DeviceContext::~DeviceContext() { if (ctx_) lsdgpu_destroy(ctx_); }
+void DeviceContext::check(int rc, const char* where) const
+{
+    if (rc != 0) throw LsdGpuError(std::string(where) + ": " + lsdgpu_last_error(ctx_));
+}
+
+Frame::Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f&, double timestamp, const unsigned char* image)
+    : dev_(dev), id_(id), w_(width), h_(height), timestamp_(timestamp)
+{
+    pose = new FramePoseStruct();
+    pose->frameID = id;
+    dev_.check(lsdgpu_frame_upload_u8(dev_.raw(), id, image), "Frame::Frame");
+}
+Frame::~Frame()
+{
+    lsdgpu_frame_release(dev_.raw(), id_);      // may fail for the active keyframe: DepthMap::invalidate() first
+    delete pose;
+}
+void Frame::setDepthFromGroundTruth(const float* depth, float cov_scale)
+{
+    dev_.check(lsdgpu_frame_set_depth_gt(dev_.raw(), id_, depth, cov_scale), "Frame::setDepthFromGroundTruth");
+}
+void Frame::clear_refPixelWasGood() { dev_.check(lsdgpu_frame_clear_good_mask(dev_.raw(), id_), "Frame::clear_refPixelWasGood"); }
+float Frame::meanIdepth()
+{
+    float m = 1; int n = 0, f = 0;
+    dev_.check(lsdgpu_frame_get_depth_stats(dev_.raw(), id_, &m, &n, &f), "Frame::meanIdepth");
+    return m;
+}
+int Frame::numPoints()
+{
+    float m = 1; int n = 0, f = 0;
+    dev_.check(lsdgpu_frame_get_depth_stats(dev_.raw(), id_, &m, &n, &f), "Frame::numPoints");
+    return n;
+}
+bool Frame::depthHasBeenUpdatedFlag() const
+{
+    int f = 0;
+    dev_.check(lsdgpu_frame_get_depth_stats(dev_.raw(), id_, nullptr, nullptr, &f), "Frame::depthHasBeenUpdatedFlag");
+    return f != 0;
+}
+void Frame::downloadIdepth(int level, std::vector<float>& idepth, std::vector<float>& idepthVar)
+{
+    size_t n = (size_t)width(level) * height(level);
+    idepth.resize(n); idepthVar.resize(n);
+    dev_.check(lsdgpu_frame_download(dev_.raw(), id_, LSDGPU_BUF_IDEPTH, level, idepth.data()), "Frame::idepth");
+    dev_.check(lsdgpu_frame_download(dev_.raw(), id_, LSDGPU_BUF_IDEPTH_VAR, level, idepthVar.data()), "Frame::idepthVar");
+}
+void Frame::downloadRefPixelWasGood(std::vector<unsigned char>& mask)
+{
+    mask.resize((size_t)width(1) * height(1));
+    dev_.check(lsdgpu_frame_download(dev_.raw(), id_, LSDGPU_BUF_GOODMASK, 1, mask.data()), "Frame::refPixelWasGood");
+}
+
+void TrackingReference::importFrame(Frame* sourceKF)
+{
+    keyframe = sourceKF;
+    frameID = sourceKF->id();
+    sourceKF->dev().check(lsdgpu_ref_import(sourceKF->dev().raw(), frameID), "TrackingReference::importFrame");
+}
+
+SE3Tracker::SE3Tracker(DeviceContext& dev, int w, int h, const Matrix3f&) : dev_(dev), width_(w), height_(h)
+{
+    if (w != dev.width() || h != dev.height()) throw LsdGpuError("SE3Tracker: size differs from the device context");
+}
+
+SE3 SE3Tracker::trackFrame(TrackingReference* reference, Frame* frame, const SE3& frameToReference_initialEstimate)
+{
+    double init[7];
+    for (int i = 0; i < 4; i++) init[i] = frameToReference_initialEstimate.q[i];
+    for (int i = 0; i < 3; i++) init[4 + i] = frameToReference_initialEstimate.t[i];
+    lsdgpu_track_result r;
+    dev_.check(lsdgpu_se3_track(dev_.raw(), reference->keyframe->id(), frame->id(), init, &settings, mode, &r), "SE3Tracker::trackFrame");
+    pointUsage = r.pointUsage; lastGoodCount = r.lastGoodCount; lastBadCount = r.lastBadCount;
+    lastMeanRes = r.lastMeanRes; lastResidual = r.lastResidual;
+    affineEstimation_a = r.affineEstimation_a; affineEstimation_b = r.affineEstimation_b;
+    diverged = r.diverged != 0; trackingWasGood = r.trackingWasGood != 0;
+    SE3 out;
+    if (diverged) return out;                                         // SE3(), SE3Tracker.cpp:324-329
+    for (int i = 0; i < 4; i++) out.q[i] = r.frameToRef_qt[i];
+    for (int i = 0; i < 3; i++) out.t[i] = r.frameToRef_qt[4 + i];
+    if (trackingWasGood) reference->keyframe->numFramesTrackedOnThis++;   // :479-480
+    frame->initialTrackedResidual = r.initialTrackedResidual;         // :482
+    frame->pose->thisToParent_raw = sim3FromSE3(out, 1);              // :483
+    frame->pose->trackingParent = reference->keyframe->pose;          // :484
+    return out;
+}
+
+DepthMap::DepthMap(DeviceContext& dev, int w, int h, const Matrix3f&) : dev_(dev), width_(w), height_(h)
+{
+    if (w != dev.width() || h != dev.height()) throw LsdGpuError("DepthMap: size differs from the device context");
+    reset();
+}
+void DepthMap::reset() { dev_.check(lsdgpu_depth_reset(dev_.raw()), "DepthMap::reset"); }
+void DepthMap::invalidate()
+{
+    activeKeyFrame = nullptr;
+    dev_.check(lsdgpu_depth_invalidate(dev_.raw()), "DepthMap::invalidate");
+}
+void DepthMap::initializeFromGTDepth(Frame* new_frame)
+{
+    dev_.check(lsdgpu_depth_init_from_gt(dev_.raw(), new_frame->id()), "DepthMap::initializeFromGTDepth");
+    activeKeyFrame = new_frame;
+}
+void DepthMap::initializeRandomly(Frame* new_frame)
+{   // DepthMap.cpp:883-916: the rand() draws stay on the host, the hypotheses are uploaded
+    std::vector<float> maxGrad((size_t)width_ * height_);
+    dev_.check(lsdgpu_frame_download(dev_.raw(), new_frame->id(), LSDGPU_BUF_MAXGRAD, 0, maxGrad.data()), "DepthMap::initializeRandomly");
+    std::vector<lsdgpu_hyp> hyp((size_t)width_ * height_);
+    std::memset(hyp.data(), 0, hyp.size() * sizeof(lsdgpu_hyp));
+    for (int y = 1; y < height_ - 1; y++)
+        for (int x = 1; x < width_ - 1; x++) {
+            lsdgpu_hyp& h = hyp[x + y * width_];
+            if (maxGrad[x + y * width_] > 5.0f /* MIN_ABS_GRAD_CREATE */) {
+                float idepth = 0.5f + 1.0f * ((rand() % 100001) / 100000.0f);
+                h.isValid = 1; h.blacklisted = 0; h.nextStereoFrameMinID = 0; h.validity_counter = 20;
+                h.idepth = idepth; h.idepth_smoothed = idepth;
+                h.idepth_var = 0.5f * 0.5f * 0.5f; h.idepth_var_smoothed = 0.5f * 0.5f * 0.5f;   // VAR_RANDOM_INIT_INITIAL
+            }
+        }
+    dev_.check(lsdgpu_depth_set_hypotheses(dev_.raw(), new_frame->id(), hyp.data(), 0, 1), "DepthMap::initializeRandomly");
+    activeKeyFrame = new_frame;
+}
+void DepthMap::setFromExistingKF(Frame* kf, const float* idepth, const float* idepthVar, const unsigned char* validity)
+{   // DepthMap.cpp:920-962
+    std::vector<lsdgpu_hyp> hyp((size_t)width_ * height_);
+    std::memset(hyp.data(), 0, hyp.size() * sizeof(lsdgpu_hyp));
+    for (size_t i = 0; i < hyp.size(); i++) {
+        lsdgpu_hyp& h = hyp[i];
+        if (idepthVar[i] > 0) {
+            h.isValid = 1; h.blacklisted = 0; h.nextStereoFrameMinID = 0; h.validity_counter = validity[i];
+            h.idepth = idepth[i]; h.idepth_var = idepthVar[i]; h.idepth_smoothed = -1; h.idepth_var_smoothed = -1;
+        } else {
+            h.isValid = 0;
+            h.blacklisted = (idepthVar[i] == -2) ? -2 : 0;
+        }
+    }
+    kf->numMappedOnThis = 0; kf->numFramesTrackedOnThis = 0;
+    dev_.check(lsdgpu_depth_set_hypotheses(dev_.raw(), kf->id(), hyp.data(), 1, 0), "DepthMap::setFromExistingKF");
+    activeKeyFrame = kf;
+}
+void DepthMap::updateKeyframe(std::deque<std::shared_ptr<Frame>> referenceFrames)
+{
+    if (!isValid()) throw LsdGpuError("DepthMap::updateKeyframe: assert(isValid())");
+    std::vector<int> ids;
+    for (auto& f : referenceFrames) ids.push_back(f->id());
+    // the device keeps its own copy of the counters the skip-ahead logic reads (DepthMap.cpp:454)
+    dev_.check(lsdgpu_frame_set_counters(dev_.raw(), activeKeyFrame->id(), activeKeyFrame->numFramesTrackedOnThis, activeKeyFrame->numMappedOnThis),
+               "DepthMap::updateKeyframe");
+    dev_.check(lsdgpu_depth_update_keyframe(dev_.raw(), ids.data(), (int)ids.size()), "DepthMap::updateKeyframe");
+    activeKeyFrame->numMappedOnThis++;
+    activeKeyFrame->numMappedOnThisTotal++;
+}
+void DepthMap::createKeyFrame(Frame* new_keyframe)
+{
+    if (!isValid()) throw LsdGpuError("DepthMap::createKeyFrame: assert(isValid())");
+    if (!new_keyframe || !new_keyframe->hasTrackingParent()) throw LsdGpuError("DepthMap::createKeyFrame: new keyframe has no tracking parent");
+    double qts[8];
+    dev_.check(lsdgpu_depth_create_keyframe(dev_.raw(), new_keyframe->id(), qts), "DepthMap::createKeyFrame");
+    Sim3 s;
+    for (int i = 0; i < 4; i++) s.q[i] = qts[i];
+    for (int i = 0; i < 3; i++) s.t[i] = qts[4 + i];
+    s.s = qts[7];
+    new_keyframe->pose->thisToParent_raw = s;                            // DepthMap.cpp:1305
+    activeKeyFrame = new_keyframe;
+}
+void DepthMap::finalizeKeyFrame()
+{
+    if (!isValid()) throw LsdGpuError("DepthMap::finalizeKeyFrame: assert(isValid())");
+    dev_.check(lsdgpu_depth_finalize_keyframe(dev_.raw()), "DepthMap::finalizeKeyFrame");
+}
+void DepthMap::download(std::vector<lsdgpu_hyp>& out)
+{
+    out.resize((size_t)width_ * height_);
+    dev_.check(lsdgpu_depth_download(dev_.raw(), out.data()), "DepthMap::download");
+}
+
+}  // namespace lsd_slam

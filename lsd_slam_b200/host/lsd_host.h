@@ -1,0 +1,177 @@
+// lsd_host.h -- C++ host side of the B200 hot path: classes that keep the reference's names, call signatures and
+// observable fields for the three seam methods, implemented on top of the C ABI (include/lsdgpu.h).
+//
+//   lsd_slam::SE3Tracker::trackFrame          Tracking/SE3Tracker.h:65-68
+//   lsd_slam::DepthMap::updateKeyframe        DepthEstimation/DepthMap.h:58
+//   lsd_slam::DepthMap::createKeyFrame        DepthEstimation/DepthMap.h:63
+//
+// The reference's headers need Eigen / Sophus / Boost / OpenCV, none of which exist in this image, so this
+// header carries minimal stand-ins (lsd_slam::SE3, Sim3, Matrix3f) with the same semantics; inside
+// lsd_slam_core the adapter in INTEGRATION.md maps them 1:1 onto Sophus::SE3d / Sophus::Sim3d / Eigen::Matrix3f.
+// Host code only: no CUDA headers, no torch.  Everything device-side sits behind lsdgpu_* calls.
+#pragma once
+
+#include <deque>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lsdgpu.h"
+
+namespace lsd_slam {
+
+struct Matrix3f {
+    float m[9];                                      // row-major
+    float operator()(int r, int c) const { return m[r * 3 + c]; }
+};
+
+// Sophus::SE3d stand-in: unit quaternion (x,y,z,w) + translation
+struct SE3 {
+    double q[4] = { 0, 0, 0, 1 };
+    double t[3] = { 0, 0, 0 };
+    SE3 inverse() const;
+    SE3 operator*(const SE3& o) const;
+};
+// Sophus::Sim3d stand-in
+struct Sim3 {
+    double q[4] = { 0, 0, 0, 1 };
+    double t[3] = { 0, 0, 0 };
+    double s = 1.0;
+};
+inline Sim3 sim3FromSE3(const SE3& se3, double scale)     // util/SophusUtil.h:53-58
+{
+    Sim3 r;
+    for (int i = 0; i < 4; i++) r.q[i] = se3.q[i];
+    for (int i = 0; i < 3; i++) r.t[i] = se3.t[i];
+    r.s = scale;
+    return r;
+}
+inline SE3 se3FromSim3(const Sim3& sim3)                  // util/SophusUtil.h:60-63
+{
+    SE3 r;
+    for (int i = 0; i < 4; i++) r.q[i] = sim3.q[i];
+    for (int i = 0; i < 3; i++) r.t[i] = sim3.t[i];
+    return r;
+}
+
+class LsdGpuError : public std::runtime_error {
+public:
+    explicit LsdGpuError(const std::string& what) : std::runtime_error(what) {}
+};
+
+// One device context per SlamSystem (SlamSystem owns one SE3Tracker + one DepthMap, SlamSystem.h:126,131)
+class DeviceContext {
+public:
+    DeviceContext(int device, int w, int h, const Matrix3f& K, int maxFrames = 16);
+    ~DeviceContext();
+    DeviceContext(const DeviceContext&) = delete;
+    DeviceContext& operator=(const DeviceContext&) = delete;
+    lsdgpu_ctx* raw() const { return ctx_; }
+    void check(int rc, const char* where) const;
+    int width() const { return w_; }
+    int height() const { return h_; }
+
+private:
+    lsdgpu_ctx* ctx_ = nullptr;
+    int w_, h_;
+};
+
+// FramePoseStruct, DataStructures/FramePoseStruct.h (the two members the path touches)
+struct FramePoseStruct {
+    Sim3 thisToParent_raw;
+    FramePoseStruct* trackingParent = nullptr;
+    int frameID = -1;
+};
+
+// DataStructures/Frame.h -- device-resident frame; host keeps the bookkeeping the callers read
+class Frame {
+public:
+    Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f& K, double timestamp, const unsigned char* image);
+    ~Frame();
+    Frame(const Frame&) = delete;
+    int id() const { return id_; }
+    int width(int level = 0) const { return w_ >> level; }
+    int height(int level = 0) const { return h_ >> level; }
+    double timestamp() const { return timestamp_; }
+    void setDepthFromGroundTruth(const float* depth, float cov_scale = 1.0f);      // Frame.cpp:245-293
+    bool hasTrackingParent() const { return pose->trackingParent != nullptr; }
+    void clear_refPixelWasGood();                                                   // Frame.h:439
+    float meanIdepth();                                                             // Frame.cpp:234 (lazy D2H)
+    int numPoints();
+    bool depthHasBeenUpdatedFlag() const;
+    // buffers for callers that still need host copies (e.g. Output3DWrapper): explicit downloads
+    void downloadIdepth(int level, std::vector<float>& idepth, std::vector<float>& idepthVar);
+    void downloadRefPixelWasGood(std::vector<unsigned char>& mask);
+
+    FramePoseStruct* pose;
+    float initialTrackedResidual = 0;
+    int numFramesTrackedOnThis = 0, numMappedOnThis = 0, numMappedOnThisTotal = 0;
+
+    DeviceContext& dev() const { return dev_; }
+
+private:
+    DeviceContext& dev_;
+    int id_, w_, h_;
+    double timestamp_;
+};
+
+// Tracking/TrackingReference.h
+class TrackingReference {
+public:
+    Frame* keyframe = nullptr;
+    int frameID = -1;
+    void importFrame(Frame* sourceKF);                                              // TrackingReference.cpp:71-87
+    void invalidate() { keyframe = nullptr; }
+};
+
+// util/settings.h:355-402
+struct DenseDepthTrackerSettings : lsdgpu_track_settings {
+    DenseDepthTrackerSettings() { lsdgpu_default_track_settings(this); }
+};
+
+// Tracking/SE3Tracker.h
+class SE3Tracker {
+public:
+    SE3Tracker(DeviceContext& dev, int w, int h, const Matrix3f& K);
+    SE3Tracker(const SE3Tracker&) = delete;
+
+    SE3 trackFrame(TrackingReference* reference, Frame* frame, const SE3& frameToReference_initialEstimate);
+
+    DenseDepthTrackerSettings settings;
+    float pointUsage = 0, lastGoodCount = 0, lastMeanRes = 0, lastBadCount = 0, lastResidual = 0;
+    float affineEstimation_a = 1, affineEstimation_b = 0;
+    bool diverged = false, trackingWasGood = false;
+    int mode = 1;                 // 1: device-resident LM (one kernel per frame); 0: host-driven LM
+
+private:
+    DeviceContext& dev_;
+    int width_, height_;
+};
+
+// DepthEstimation/DepthMap.h
+class DepthMap {
+public:
+    DepthMap(DeviceContext& dev, int w, int h, const Matrix3f& K);
+    DepthMap(const DepthMap&) = delete;
+
+    void reset();
+    void updateKeyframe(std::deque<std::shared_ptr<Frame>> referenceFrames);
+    void createKeyFrame(Frame* new_keyframe);
+    void finalizeKeyFrame();
+    void invalidate();
+    bool isValid() const { return activeKeyFrame != nullptr; }
+    void initializeFromGTDepth(Frame* new_frame);
+    void initializeRandomly(Frame* new_frame);
+    void setFromExistingKF(Frame* kf, const float* idepth_reAct, const float* idepthVar_reAct, const unsigned char* validity_reAct);
+    // currentDepthMap in the reference's AoS layout (w*h records)
+    void download(std::vector<lsdgpu_hyp>& out);
+
+    Frame* activeKeyFrame = nullptr;
+
+private:
+    DeviceContext& dev_;
+    int width_, height_;
+};
+
+}  // namespace lsd_slam
