@@ -43,6 +43,7 @@ struct TrackParams {
     int useAffine;
     float* partials;                 // [2][EV_NCH][gridDim]
     unsigned int* barrier;           // [0] arrival counter (monotonic), [32] released-epoch flag
+    int barrierMode;
 };
 
 // what the kernel hands back (block 0 writes it)
@@ -62,20 +63,38 @@ struct TrackState {
 // arrivals); the LAST arriver publishes the epoch number in `counter[32]` (a different 128-byte line), which is
 // what everybody else polls -- the pollers never touch the line the atomics serialise on.  Thread 0 carries the
 // release / acquire for its CTA (the fences are cumulative over the preceding / following __syncthreads).
-__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int epoch)
+__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int epoch, int mode)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        const unsigned int old = atomicAdd(counter, 1u);
-        volatile unsigned int* flag = counter + 32;
-        if (old == epoch * gridDim.x - 1u) {
+        const unsigned int target = epoch * gridDim.x;
+        if (mode == 0) {
+            // arrival counter + separate release flag (last arriver publishes the epoch)
             __threadfence();
-            *flag = epoch;
+            const unsigned int old = atomicAdd(counter, 1u);
+            volatile unsigned int* flag = counter + 32;
+            if (old == target - 1u) { __threadfence(); *flag = epoch; }
+            else { while (*flag < epoch) { } }
+            __threadfence();
+        } else if (mode == 1) {
+            // release-add, then acquire-poll the counter itself (one L2 hop less than mode 0)
+            unsigned int v;
+            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+            if (v != target - 1u) {
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+                } while (v < target);
+            } else {
+                asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
         } else {
-            while (*flag < epoch) { }
+            // fire-and-forget release reduction + acquire poll
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+            unsigned int v;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            } while (v < target);
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -202,7 +221,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
     if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
     epoch++;
     long long t2 = clock64();
-    gridBarrier(p.barrier, epoch);
+    gridBarrier(p.barrier, epoch, p.barrierMode);
     long long t3 = clock64();
     // warp wi owns channels wi, wi+TP_WARPS, ... (<= 3 per warp); all loads are issued first, then one
     // multi-value reduction in double
@@ -276,6 +295,53 @@ __device__ __forceinline__ bool ldlt6SolveFast(const float* A, const float* b, f
     return ok;
 }
 
+// exp(inc) * T on the device, latency-trimmed: one sincosf (half angle; sin/cos of the full angle by the
+// double-angle identities), reciprocal-sqrt normalisations.  Same algebra as lsd::se3Exp / se3Mul (hostmath.h,
+// se3.hpp:406-428, 239-259); results agree to ~1e-7 relative.
+__device__ __forceinline__ lsd::SE3<float> se3ExpMulFast(const float* a, const lsd::SE3<float>& T)
+{
+    const float wx = a[3], wy = a[4], wz = a[5];
+    const float theta_sq = wx * wx + wy * wy + wz * wz;
+    float imag, real, c1, c2;
+    if (theta_sq < 1e-10f) {
+        const float theta_po4 = theta_sq * theta_sq;
+        imag = 0.5f - (1.0f / 48.0f) * theta_sq + (1.0f / 3840.0f) * theta_po4;
+        real = 1.0f - 0.5f * theta_sq + (1.0f / 384.0f) * theta_po4;
+        c1 = 0.5f; c2 = 1.0f / 6.0f;                       // V = I + Omega/2 + Omega^2/6 (theta -> 0)
+    } else {
+        const float inv_theta = rsqrtf(theta_sq);
+        const float theta = theta_sq * inv_theta;
+        float sh_, ch_;
+        sincosf(0.5f * theta, &sh_, &ch_);
+        imag = sh_ * inv_theta;
+        real = ch_;
+        const float inv_sq = inv_theta * inv_theta;
+        c1 = 2.0f * sh_ * sh_ * inv_sq;                     // (1 - cos theta) / theta^2
+        c2 = (theta - 2.0f * sh_ * ch_) * inv_sq * inv_theta;   // (theta - sin theta) / theta^3
+    }
+    float q[4] = { imag * wx, imag * wy, imag * wz, real };
+    {
+        const float n = rsqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+    }
+    // V * upsilon with V = I + c1*Omega + c2*Omega^2 :  Omega u = w x u,  Omega^2 u = w x (w x u)
+    const float ux = a[0], uy = a[1], uz = a[2];
+    const float k1x = wy * uz - wz * uy, k1y = wz * ux - wx * uz, k1z = wx * uy - wy * ux;
+    const float k2x = wy * k1z - wz * k1y, k2y = wz * k1x - wx * k1z, k2z = wx * k1y - wy * k1x;
+    const float tx = ux + c1 * k1x + c2 * k2x, ty = uy + c1 * k1y + c2 * k2y, tz = uz + c1 * k1z + c2 * k2z;
+    // (q, t) * T
+    lsd::SE3<float> r;
+    float rt[3];
+    lsd::quatRotate(q, T.t, rt);
+    lsd::quatMul(q, T.q, r.q);
+    {
+        const float n = rsqrtf(r.q[0] * r.q[0] + r.q[1] * r.q[1] + r.q[2] * r.q[2] + r.q[3] * r.q[3]);
+        r.q[0] *= n; r.q[1] *= n; r.q[2] *= n; r.q[3] *= n;
+    }
+    r.t[0] = tx + rt[0]; r.t[1] = ty + rt[1]; r.t[2] = tz + rt[2];
+    return r;
+}
+
 // LM state of SE3Tracker::trackFrame; lives in shared memory, touched by thread 0 only (keeps it out of the
 // register budget of the other threads)
 struct LMState {
@@ -285,6 +351,7 @@ struct LMState {
     float lsq[27];                   // accepted normal equations, RAW sums: 21 upper-triangle A + 6 (sum J r w)
     int nRes[LSD_LEVELS], nUpd[LSD_LEVELS];
     int lvl, iteration, phase, incTry, diverged;
+    long long dbg[4];                // thread-0 cycles: decision, solve, pose update, (spare)
 };
 enum { PH_INIT = 0, PH_TRY = 1 };
 
@@ -304,6 +371,7 @@ __device__ __forceinline__ void lmSolveAndPropose(LMState& lm, LMShared& sh)
     static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
                                             {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
     float A[36], b[6], inc[6];
+    const long long ta = clock64();
 #pragma unroll
     for (int k = 0; k < 21; k++) {
         const float v = lm.lsq[k];
@@ -318,10 +386,13 @@ __device__ __forceinline__ void lmSolveAndPropose(LMState& lm, LMShared& sh)
     if (!ldlt6SolveFast(A, b, inc)) lsd::ldlt6Solve(A, b, inc);
 #pragma unroll
     for (int i = 0; i < 6; i++) lm.inc[i] = inc[i];
+    const long long tb = clock64();
     lm.incTry++;
-    lm.cand = lsd::se3Mul(lsd::se3Exp(inc), lm.refToFrame);
+    lm.cand = se3ExpMulFast(inc, lm.refToFrame);
     setEvalPose(sh.pose, lm.cand, lm.affine_a, lm.affine_b);
     lm.phase = PH_TRY;
+    const long long tc = clock64();
+    lm.dbg[1] += tb - ta; lm.dbg[2] += tc - tb;
 }
 
 __device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, LMShared& sh)
@@ -413,7 +484,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
         for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; }
         lm.affine_a = 1.f; lm.affine_b = 0.f; lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
-        lm.diverged = 0; lm.incTry = 0; lm.iteration = 0;
+        lm.diverged = 0; lm.incTry = 0; lm.iteration = 0; lm.dbg[0] = lm.dbg[1] = lm.dbg[2] = lm.dbg[3] = 0;
         lm.lvl = SE3TRACKING_MAX_LEVEL - 1; lm.phase = PH_INIT;
         sh.lvl = lm.lvl; sh.action = ACT_CONTINUE;
         setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
@@ -424,7 +495,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         const int lvl = sh.lvl;
         const bool local = p.lvl[lvl].w * p.lvl[lvl].h <= TP_LOCAL_MAX_PIXELS;
         gridEvaluate(p, lvl, local, sh, sm, epoch, cyc);
-        if (threadIdx.x == 0) lmAdvance(p, lm, sh);
+        if (threadIdx.x == 0) { const long long t0 = clock64(); lmAdvance(p, lm, sh); lm.dbg[0] += clock64() - t0; }
         __syncthreads();
         if (sh.action != ACT_CONTINUE) break;
     }
@@ -449,6 +520,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
+        for (int i = 0; i < 3; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
     }
 }
 
@@ -489,6 +561,7 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     P.useAffine = ctx->g.useAffineLightningEstimation;
     P.partials = ctx->evPartials;
     P.barrier = ctx->evCounter;
+    { const char* bm = getenv("LSDGPU_BARRIER_MODE"); P.barrierMode = bm ? atoi(bm) : 1; }
     TrackState* dOut = (TrackState*)ctx->dTrackState;
     TrackState* hOut = (TrackState*)ctx->hTrackState;
 
@@ -517,6 +590,7 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     if (getenv("LSDGPU_TRACK_DEBUG")) {
         fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
                 hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
+        fprintf(stderr, "   thread0: lmAdvance=%lld (solve=%lld pose=%lld)\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2]);
         const char* nm[6] = { "points", "ctaReduce", "barrier", "combine", "serial", "total" };
         for (int k = 0; k < 6; k++) {
             long long mn = 1LL << 60, mx = 0, sum = 0; int imx = 0, imn = 0;
