@@ -11,6 +11,7 @@
 //     plus the int32 validity integral image.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -41,6 +42,7 @@ struct FrameSlot {
     float* idepth[LSD_LEVELS];
     float* idepthVar[LSD_LEVELS];
     uint8_t* goodMask;
+    CUtensorMap gradMap[LSD_LEVELS];     // TMA descriptors of grad[l] (float4 texels as 4 x f32), box = tracker window
     bool hasDepth = false, idepthPyrValid = false, hasGoodMask = false;
     bool depthHasBeenUpdatedFlag = false;
     float meanIdepth = 1.f;
@@ -82,6 +84,11 @@ struct ObserveParams {
     int reactivated;
     int kfNumTracked, kfNumMapped;
 };
+
+// per-warp shared-memory window of the new frame's gradient level used by the persistent tracker: WIN_W x WIN_H
+// float4 texels, loaded by one TMA box copy per warp and level (track_persistent.cuh)
+#define TRK_WIN_W 48
+#define TRK_WIN_H 17
 
 // number of reduction channels of one tracker evaluation (see track.cuh)
 #define EV_NCH 40
@@ -135,6 +142,7 @@ struct lsdgpu_ctx {
     long long trackKernelLaunches = 0;
     double trackKernelBytes = 0;
     bool profileTrackKernel = false;
+    void* encodeTiled = nullptr;         // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
 };
 
 #define LSD_CHECK(ctx, expr)                                                                              \

@@ -107,6 +107,27 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
         memset(s.thisToParent, 0, sizeof(s.thisToParent));
         s.thisToParent[3] = 1; s.thisToParent[7] = 1;
     }
+    // TMA descriptors for the tracker's shared-memory windows (one per slot and level)
+    {
+        cudaDriverEntryPointQueryResult qres;
+        LSD_CHECK(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ctx->encodeTiled, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ctx->encodeTiled) return lsd_fail(ctx, "cuTensorMapEncodeTiled not available in this driver");
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        EncodeFn enc = (EncodeFn)ctx->encodeTiled;
+        for (auto& s : ctx->slots)
+            for (int l = 0; l < LSD_LEVELS; l++) {
+                const cuuint64_t gdim[2] = { (cuuint64_t)4 * (width >> l), (cuuint64_t)(height >> l) };
+                const cuuint64_t gstr[1] = { (cuuint64_t)16 * (width >> l) };
+                const cuuint32_t box[2] = { 4 * TRK_WIN_W, TRK_WIN_H };
+                const cuuint32_t estr[2] = { 1, 1 };
+                CUresult cr = enc(&s.gradMap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)s.grad[l], gdim, gstr, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (cr != CUDA_SUCCESS) return lsd_fail(ctx, "cuTensorMapEncodeTiled failed");
+            }
+    }
     ctx->cur.hf = (float4*)take(n0 * 16); ctx->cur.hi = (int4*)take(n0 * 16);
     ctx->oth.hf = (float4*)take(n0 * 16); ctx->oth.hi = (int4*)take(n0 * 16);
     ctx->integral = (int*)take(n0 * 4);

@@ -19,6 +19,7 @@
 
 #define TP_THREADS 512
 #define TP_MAXGRID_DBG 160
+#define TP_WIN_SMEM ((TP_THREADS / 32) * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
 #define EX_ROW 48                    // floats per exchange row (192 B): EV_NCH data + tag + pad
 #define TP_LOCAL_MAX_PIXELS 1024      // levels up to this many pixels are evaluated redundantly per CTA
 
@@ -31,7 +32,8 @@ struct TrackLevelParams {
     float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
 };
 
-struct TrackParams {
+struct alignas(64) TrackParams {
+    CUtensorMap gradMap[LSD_LEVELS]; // TMA descriptors of the tracked frame's gradient levels (64-byte aligned)
     TrackLevelParams lvl[LSD_LEVELS];
     uint8_t* goodMask;               // level-1 mask of the tracked frame
     int maskFresh;                   // 1: initialise the mask to true first (Frame.h:433)
@@ -44,6 +46,7 @@ struct TrackParams {
     float* partials;                 // [2][EV_NCH][gridDim]
     unsigned int* barrier;           // [0] arrival counter (monotonic), [32] released-epoch flag
     int barrierMode;
+    int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
 };
 
 // what the kernel hands back (block 0 writes it)
@@ -58,6 +61,38 @@ struct TrackState {
     long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
     long long cycBlk[TP_MAXGRID_DBG][6];   // the same per CTA (debug)
 };
+
+// ---- TMA / mbarrier PTX (sm_90+; SASS: UTMALDG / SYNCS) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smemU32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemU32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemU32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: returns false if the phase did not complete within ~maxPolls probes (never observed; keeps a
+// mis-programmed copy from hanging the whole cooperative grid)
+__device__ __forceinline__ bool mbarWait(uint64_t* bar, unsigned int parity, int maxPolls = 1 << 16)
+{
+    for (int it = 0; it < maxPolls; it++) {
+        unsigned int done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smemU32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smemU32(dst)), "l"(map), "r"(x), "r"(y), "r"(smemU32(bar)) : "memory");
+}
 
 // Grid-wide barrier.  Arrivals are counted on `counter[0]` (monotonic: epoch e completes at e * gridDim
 // arrivals); the LAST arriver publishes the epoch number in `counter[32]` (a different 128-byte line), which is
@@ -167,8 +202,18 @@ __device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* sm
 // One evaluation.  Levels with few pixels (local == true) are evaluated REDUNDANTLY by every CTA over the whole
 // level -- no grid barrier, no exchange; big levels are split over the grid with one barrier.  On return
 // sh.sums holds the EV_NCH totals, bit-identical in every CTA.
+struct WarpWindow {
+    const float4* win;               // this warp's TRK_WIN_H x TRK_WIN_W window in shared memory
+    uint64_t* bar;
+    unsigned int parity;             // phase of the next completion to wait for
+    int lvl;                         // level the window currently holds (-1: none)
+    int ox, oy;                      // window origin in level pixels
+    bool valid;
+    unsigned int hits;               // low 16 bits: taps served from the window, high 16: taps through L1/L2
+};
+
 __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool local, LMShared& sh, float (*sm)[EV_NCH],
-                                             unsigned int& epoch, long long* cyc)
+                                             unsigned int& epoch, long long* cyc, WarpWindow& W)
 {
     long long t0 = clock64();
     const TrackLevelParams& L = p.lvl[lvl];
@@ -183,17 +228,84 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
     // semi-dense density varies over the image, a contiguous split would leave CTAs unevenly loaded
     const int first = local ? threadIdx.x : ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
     const int stride = local ? TP_THREADS : gridDim.x * TP_THREADS;
-    for (int i = first; i < n; i += stride) {
+    // the loop bound is evaluated on the chunk base so that whole warps stay in the loop (the window set-up below
+    // uses full-warp ballots / shuffles); w*h need not be a multiple of 32 (e.g. 40x30 on level 4)
+    const int laneId = threadIdx.x & 31;
+    for (int base = first - laneId; base < n; base += stride) {
+        const int i = base + laneId;
         const int x = i % w, y = i / w;
-        if (x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-            const float idepth = __ldg(L.kfIdepth + i), var = __ldg(L.kfVar + i);
+        bool isPoint = false;
+        float px = 0.f, py = 0.f, pz = 0.f, var = 0.f;
+        if (i < n && x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+            const float idepth = __ldg(L.kfIdepth + i);
+            var = __ldg(L.kfVar + i);
             if (!(var <= 0 || idepth == 0)) {
                 const float sc = 1.0f / idepth;
-                const float px = sc * (L.fxi * x + L.cxi), py = sc * (L.fyi * y + L.cyi), pz = sc * 1;
-                auto tap = [fg, w](float u, float v, float& o0, float& o1, float& o2) { interp43(fg, u, v, w, o0, o1, o2); };
-                int good = evalPoint(px, py, pz, __ldg(L.kfColor + i), var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
-                if (mask) mask[i] = (uint8_t)good;
+                px = sc * (L.fxi * x + L.cxi); py = sc * (L.fyi * y + L.cyi); pz = sc * 1;
+                isPoint = true;
             }
+        }
+        // First chunk of this warp on a new level: stage the part of the frame's gradient level that the chunk
+        // warps into (centred on the chunk under the level's initial pose) in shared memory with ONE TMA box copy.
+        // All later evaluations of the level tap the window; taps that leave it fall back to L1/L2.
+        const bool firstChunk = (base == first - laneId);
+        if (p.useTma && !local && firstChunk && W.lvl != lvl) {          // warp-uniform condition
+            const int lane = threadIdx.x & 31;
+            float u = 0.f, v = 0.f;
+            bool ok = false;
+            if (isPoint) {
+                const float Wx = ((P.R[0] * px + P.R[1] * py) + P.R[2] * pz) + P.t[0];
+                const float Wy = ((P.R[3] * px + P.R[4] * py) + P.R[5] * pz) + P.t[1];
+                const float Wz = ((P.R[6] * px + P.R[7] * py) + P.R[8] * pz) + P.t[2];
+                u = (Wx / Wz) * L.fx + L.cx; v = (Wy / Wz) * L.fy + L.cy;
+                ok = (u > -1e4f && u < 1e4f && v > -1e4f && v < 1e4f);
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, ok);
+            W.lvl = lvl;
+            W.valid = bal != 0u;
+            if (W.valid) {
+                // reference lane: the valid lane closest to the chunk centre
+                int src = 16;
+                if (!((bal >> 16) & 1u)) src = (bal >> 16) ? (__ffs(bal >> 16) - 1 + 16) : (31 - __clz(bal));
+                const float uc = __shfl_sync(0xffffffffu, u, src), vc = __shfl_sync(0xffffffffu, v, src);
+                W.ox = (int)floorf(uc) - (src - 16) - (TRK_WIN_W - 32) / 2 - 16;
+                W.oy = (int)floorf(vc) - TRK_WIN_H / 2;
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the old window are done
+                    mbarExpectTx(W.bar, TRK_WIN_W * TRK_WIN_H * 16);
+                    tmaLoad2D((void*)W.win, &p.gradMap[lvl], 4 * W.ox, W.oy, W.bar);
+                }
+                if (mbarWait(W.bar, W.parity)) W.parity ^= 1u;
+                else { W.valid = false; W.lvl = -2; if (lane == 0) atomicAdd(p.barrier + 40, 1u); }   // counted, reported by the host
+            }
+        }
+        if (isPoint) {
+            const bool useWin = p.useTma && !local && firstChunk && W.valid && W.lvl == lvl;
+            const float4* win = W.win;
+            const int ox = W.ox, oy = W.oy;
+            unsigned int* hitCtr = &W.hits;
+            auto tap = [fg, w, win, ox, oy, useWin, hitCtr](float u, float v, float& o0, float& o1, float& o2) {
+                const int ix = (int)u, iy = (int)v;
+                const int lx = ix - ox, ly = iy - oy;
+                if (useWin && lx >= 0 && lx < TRK_WIN_W - 1 && ly >= 0 && ly < TRK_WIN_H - 1) {
+                    (*hitCtr)++;
+                    // same weights and summation order as interp43 (globalFuncs.h:63-77), texels from shared memory
+                    const float dx = u - ix, dy = v - iy;
+                    const float dxdy = dx * dy;
+                    const float4* bp = win + ly * TRK_WIN_W + lx;
+                    const float4 br = bp[1 + TRK_WIN_W], bl = bp[TRK_WIN_W], tr = bp[1], tl = bp[0];
+                    const float w0 = dxdy, w1 = (dy - dxdy), w2 = (dx - dxdy), w3 = (1 - dx - dy + dxdy);
+                    o0 = w0 * br.x + w1 * bl.x + w2 * tr.x + w3 * tl.x;
+                    o1 = w0 * br.y + w1 * bl.y + w2 * tr.y + w3 * tl.y;
+                    o2 = w0 * br.z + w1 * bl.z + w2 * tr.z + w3 * tl.z;
+                } else {
+                    (*hitCtr) += 0x10000u;
+                    interp43(fg, u, v, w, o0, o1, o2);
+                }
+            };
+            int good = evalPoint(px, py, pz, __ldg(L.kfColor + i), var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
+            if (mask) mask[i] = (uint8_t)good;
         }
     }
     __syncthreads();
@@ -469,9 +581,19 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     __shared__ LMState lm;
     __shared__ float sm[TP_THREADS / 32][EV_NCH];
     static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
+    extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
+    __shared__ __align__(8) uint64_t winBar[TP_WARPS];
     unsigned int epoch = 0;
     long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
     const long long tStart = clock64();
+    WarpWindow W;
+    W.win = reinterpret_cast<const float4*>(winSmem) + (size_t)(threadIdx.x >> 5) * (TRK_WIN_W * TRK_WIN_H);
+    W.bar = &winBar[threadIdx.x >> 5];
+    W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u;
+    if (p.useTma && (threadIdx.x & 31) == 0) {
+        mbarInit(W.bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     // fresh refPixelWasGood mask: all true (Frame.h:433); ordered before the level-1 evaluations by the barriers
     if (p.maskFresh) {
@@ -494,12 +616,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     while (true) {
         const int lvl = sh.lvl;
         const bool local = p.lvl[lvl].w * p.lvl[lvl].h <= TP_LOCAL_MAX_PIXELS;
-        gridEvaluate(p, lvl, local, sh, sm, epoch, cyc);
+        gridEvaluate(p, lvl, local, sh, sm, epoch, cyc, W);
         if (threadIdx.x == 0) { const long long t0 = clock64(); lmAdvance(p, lm, sh); lm.dbg[0] += clock64() - t0; }
         __syncthreads();
         if (sh.action != ACT_CONTINUE) break;
     }
 
+    atomicAdd(p.barrier + 41, W.hits & 0xffffu);
+    atomicAdd(p.barrier + 42, W.hits >> 16);
     if (threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
         long long tot = clock64() - tStart;
         for (int i = 0; i < 4; i++) out->cycBlk[blockIdx.x][i] = cyc[i];
@@ -530,7 +654,7 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
     cudaError_t e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     if (e != cudaSuccess) return e;
     if (!coop) return cudaErrorNotSupported;
-    return cudaSuccess;
+    return cudaFuncSetAttribute((const void*)k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_WIN_SMEM);
 }
 
 static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
@@ -546,6 +670,8 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
         L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
         L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
     }
+    for (int l = 0; l < LSD_LEVELS; l++) P.gradMap[l] = fr->gradMap[l];
+    { const char* tm = getenv("LSDGPU_TRACK_TMA"); P.useTma = tm ? atoi(tm) : 1; }
     P.goodMask = fr->goodMask;
     P.maskFresh = fr->hasGoodMask ? 0 : 1;
     P.maskBytes = (ctx->w * ctx->h) / 4;
@@ -567,9 +693,9 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
 
     const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM
     void* args[] = { (void*)&P, (void*)&dOut };
-    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, 33 * sizeof(unsigned int), ctx->stream));   // arrivals + epoch flag
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, 44 * sizeof(unsigned int), ctx->stream));   // arrivals + epoch flag
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
-    LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, 0, ctx->stream));
+    LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, TP_WIN_SMEM, ctx->stream));
     ctx->launches++;
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
     LSD_CHECK(ctx, cudaMemcpyAsync(hOut, dOut, sizeof(TrackState), cudaMemcpyDeviceToHost, ctx->stream));
@@ -588,6 +714,9 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     }
 
     if (getenv("LSDGPU_TRACK_DEBUG")) {
+        unsigned int dbgc[3] = { 0, 0, 0 };
+        cudaMemcpy(dbgc, ctx->evCounter + 40, 12, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[track] useTma=%d tmaTimeouts=%u taps: %u from the smem window, %u through L1/L2\n", P.useTma, dbgc[0], dbgc[1], dbgc[2]);
         fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
                 hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
         fprintf(stderr, "   thread0: lmAdvance=%lld (solve=%lld pose=%lld)\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2]);
