@@ -163,6 +163,17 @@ int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int level, const f
 int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double frameToRef_init_qt[7],
                      const lsdgpu_track_settings* s, int mode, lsdgpu_track_result* out);
 
+/* One frame of the sequential (dataset_slam _hz:=0) loop in a single call -- the order of SlamSystem::trackFrame
+ * (SlamSystem.cpp:890-1040) followed by SlamSystem::doMappingIteration (:739-828):
+ *   Frame construction (from HOST `gray`, or from prefetch-ring entry `stage_index` when gray == NULL),
+ *   lsdgpu_ref_import if the keyframe's depth changed, lsdgpu_se3_track, then
+ *   keyframe_change == 0: lsdgpu_depth_update_keyframe({frame_id}) + clear_good_mask        (:571-573)
+ *   keyframe_change != 0: lsdgpu_depth_finalize_keyframe + lsdgpu_depth_create_keyframe     (:400, :473)
+ * Exactly equivalent to issuing those calls one by one; exists so that a host loop pays one FFI crossing per frame. */
+int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t* gray, int stage_index,
+                         const double frameToRef_init_qt[7], const lsdgpu_track_settings* s, int mode,
+                         int keyframe_change, lsdgpu_track_result* out, double new_kf_thisToParent_qts[8]);
+
 /* Point-sharded tracking across GPUs (BASELINE config 5): rank `shard` of `n_shards` evaluates every
  * n_shards-th 32-pixel chunk of the level; the LSDGPU_EVAL_NSUMS partial sums of every evaluation are handed to
  * `allreduce` (sum over ranks, in place, HOST buffer) before the LM decision, so all ranks take identical

@@ -99,6 +99,7 @@ SYMBOLS = [
     ("lsdgpu_ref_import", C.c_int, [_vp, C.c_int]),
     ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
     ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
+    ("lsdgpu_track_and_map", C.c_int, [_vp, C.c_int, C.c_int, _u8p, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.POINTER(TrackResult), _dp]),
     ("lsdgpu_se3_track_sharded", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     ("lsdgpu_depth_reset", C.c_int, [_vp]),
     ("lsdgpu_depth_is_valid", C.c_int, [_vp]),

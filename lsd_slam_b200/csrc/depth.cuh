@@ -661,6 +661,59 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
     }
     finishSumCount(s, c, partials, counter, out);
 }
+// Frame::setDepth fused with Frame::buildIDepthAndIDepthVar for levels 1..4 (Frame.cpp:199-243 + :775-877): one CTA =
+// one 16x16 level-0 tile; the tracker imports the new depth right after every update, so the pyramid is always
+// needed and building it here saves a pass over the level-0 planes and a launch.
+__global__ void __launch_bounds__(256) k_set_depth_pyr(HypField cur, PyrPtrs id, PyrPtrs var, int w, int h,
+                                                       double* __restrict__ partials, unsigned int* counter, double* __restrict__ out)
+{
+    __shared__ float2 s0[16][17], s1[8][9], s2[4][5], s3[2][3];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int tilesX = w >> 4;
+    const int bx = blockIdx.x % tilesX, by = blockIdx.x / tilesX;
+    const int x = bx * 16 + tx, y = by * 16 + ty;
+    const int i = x + y * w;
+    double s = 0.0;
+    int c = 0;
+    float2 v;
+    {
+        const float4 hf = cur.hf[i];
+        const int4 hi = cur.hi[i];
+        if (hi.x && hf.z >= -0.05) { v = make_float2(hf.z, hf.w); s = hf.z; c = 1; }
+        else v = make_float2(-1.f, -1.f);
+    }
+    id.l[0][i] = v.x; var.l[0][i] = v.y;
+    s0[ty][tx] = v;
+    __syncthreads();
+    if (tx < 8 && ty < 8) {
+        float2 r = mergeIdepth4(s0[2 * ty][2 * tx], s0[2 * ty][2 * tx + 1], s0[2 * ty + 1][2 * tx], s0[2 * ty + 1][2 * tx + 1]);
+        s1[ty][tx] = r;
+        int o = (by * 8 + ty) * (w >> 1) + bx * 8 + tx;
+        id.l[1][o] = r.x; var.l[1][o] = r.y;
+    }
+    __syncthreads();
+    if (tx < 4 && ty < 4) {
+        float2 r = mergeIdepth4(s1[2 * ty][2 * tx], s1[2 * ty][2 * tx + 1], s1[2 * ty + 1][2 * tx], s1[2 * ty + 1][2 * tx + 1]);
+        s2[ty][tx] = r;
+        int o = (by * 4 + ty) * (w >> 2) + bx * 4 + tx;
+        id.l[2][o] = r.x; var.l[2][o] = r.y;
+    }
+    __syncthreads();
+    if (tx < 2 && ty < 2) {
+        float2 r = mergeIdepth4(s2[2 * ty][2 * tx], s2[2 * ty][2 * tx + 1], s2[2 * ty + 1][2 * tx], s2[2 * ty + 1][2 * tx + 1]);
+        s3[ty][tx] = r;
+        int o = (by * 2 + ty) * (w >> 3) + bx * 2 + tx;
+        id.l[3][o] = r.x; var.l[3][o] = r.y;
+    }
+    __syncthreads();
+    if (tx == 0 && ty == 0) {
+        float2 r = mergeIdepth4(s3[0][0], s3[0][1], s3[1][0], s3[1][1]);
+        int o = by * (w >> 4) + bx;
+        id.l[4][o] = r.x; var.l[4][o] = r.y;
+    }
+    finishSumCount(s, c, partials, counter, out);
+}
+
 // sum of idepth_smoothed over valid hypotheses (createKeyFrame :1286-1293)
 __global__ void __launch_bounds__(256) k_sum_idepth(HypField cur, int n, double* __restrict__ partials, unsigned int* counter,
                                                     double* __restrict__ out)

@@ -722,12 +722,14 @@ static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf)
 {
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
-    k_set_depth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, kf->idepth[0], kf->idepthVar[0], n, ctx->dScalars + 8,
-                                             ctx->evCounter + 48, kf->dStats);
+    PyrPtrs id, var;
+    for (int l = 0; l < LSD_LEVELS; l++) { id.l[l] = kf->idepth[l]; var.l[l] = kf->idepthVar[l]; }
+    k_set_depth_pyr<<<(ctx->w / 16) * (ctx->h / 16), 256, 0, ctx->stream>>>(ctx->cur, id, var, ctx->w, ctx->h, ctx->dScalars + 8,
+                                                                           ctx->evCounter + 48, kf->dStats);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     kf->statsPending = true;
-    kf->hasDepth = true; kf->idepthPyrValid = false;
+    kf->hasDepth = true; kf->idepthPyrValid = true;          // levels 1..4 were built by the same kernel
     kf->depthHasBeenUpdatedFlag = true;
     return 0;
 }
@@ -1017,4 +1019,26 @@ extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
     r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);
     if (r) return r;
     return setDepthOnKeyframe(ctx, kf);
+}
+
+extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t* gray, int stage_index,
+                                    const double init_qt[7], const lsdgpu_track_settings* s, int mode,
+                                    int keyframe_change, lsdgpu_track_result* out, double new_qts[8])
+{
+    int r = gray ? lsdgpu_frame_upload_u8(ctx, frame_id, gray) : lsdgpu_frame_from_stage(ctx, frame_id, stage_index);
+    if (r) return r;
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (kf->depthHasBeenUpdatedFlag) { r = lsdgpu_ref_import(ctx, kf_id); if (r) return r; }     // SlamSystem.cpp:907-912
+    r = lsdgpu_se3_track(ctx, kf_id, frame_id, init_qt, s, mode, out);
+    if (r) return r;
+    if (out->diverged) return 0;                 // the caller decides (relocalisation is out of scope)
+    if (keyframe_change) {
+        r = lsdgpu_depth_finalize_keyframe(ctx);
+        if (r) return r;
+        return lsdgpu_depth_create_keyframe(ctx, frame_id, new_qts);
+    }
+    r = lsdgpu_depth_update_keyframe(ctx, &frame_id, 1);
+    if (r) return r;
+    return lsdgpu_frame_clear_good_mask(ctx, frame_id);
 }

@@ -236,3 +236,20 @@ def test_full_loop_parity(gpu_ctx_small, oracle, seq_small, frames_small):
     both = va & vb
     rel = np.abs(a["idepth_smoothed"][both] - b["idepth_smoothed"][both]) / np.abs(b["idepth_smoothed"][both])
     assert (rel <= 1e-3).mean() >= 0.999, float((rel <= 1e-3).mean())
+
+
+def test_fused_call_equals_individual_calls(seq_small, frames_small):
+    """lsdgpu_track_and_map (one ABI call per frame) == the individual calls, bit for bit"""
+    from lsd_slam_b200.stream import GpuStream
+    outs = []
+    for fused in (True, False):
+        ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, max_frames=8)
+        gs = GpuStream(ctx, mode=1, kf_every=4, fused_call=fused)
+        gs.init_gt(0, frames_small[0][0], frames_small[0][1])
+        for k in range(1, 8):
+            gs.step(k, frames_small[k][0])
+        outs.append((np.array(gs.poses), gs.map.current().copy(), ctx.download(gs.kf_id, abi.BUF_IDEPTH, 2)))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1].tobytes() == outs[1][1].tobytes()
+    assert np.array_equal(outs[0][2], outs[1][2])
