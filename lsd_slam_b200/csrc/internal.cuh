@@ -125,7 +125,9 @@ struct lsdgpu_ctx {
     float* dEvOut = nullptr;             // EV_NCH floats (device)
     float* hEvOut = nullptr;             // pinned host mirror
     void* dTrackState = nullptr;         // persistent-kernel state block (device)
-    void* hTrackState = nullptr;         // pinned mirror
+    void* hTrackState = nullptr;         // mapped pinned result block (host view)
+    void* dTrackStateMapped = nullptr;   // device view of the same block
+    unsigned int barrierBase = 0;        // arrivals already counted on evCounter[0] by earlier launches
     uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
     int stageEntries = 0;
     uint8_t* hStage[2] = { nullptr, nullptr };   // double-buffered pinned staging for the u8 frame upload

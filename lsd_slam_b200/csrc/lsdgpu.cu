@@ -153,7 +153,9 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     }
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hStageF, n0 * 32, cudaHostAllocDefault));
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hScalars, 64, cudaHostAllocDefault));
-    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hTrackState, sizeof(TrackState), cudaHostAllocDefault));
+    // the tracker writes its result block straight into mapped pinned memory (no D2H copy on the path)
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hTrackState, sizeof(TrackState), cudaHostAllocMapped));
+    LSD_CHECK(ctx, cudaHostGetDevicePointer(&ctx->dTrackStateMapped, ctx->hTrackState, 0));
     for (int i = 0; i < 8; i++) {
         LSD_CHECK(ctx, cudaEventCreate(&ctx->tBegin[i]));
         LSD_CHECK(ctx, cudaEventCreate(&ctx->tEnd[i]));
@@ -253,12 +255,16 @@ extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8
     FrameSlot* s = acquireSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
     const size_t n0 = (size_t)ctx->w * ctx->h;
-    // double-buffered pinned staging: only wait for the upload issued two frames ago
+    // double-buffered staging: only wait for the upload issued two frames ago.  A caller buffer that is already
+    // page-locked (cudaHostAlloc / cudaHostRegister, e.g. a camera DMA buffer) is copied from directly -- it must then
+    // stay untouched until the frame has been consumed; pageable memory goes through the pinned staging copy.
     const int b = ctx->stageIdx;
     ctx->stageIdx ^= 1;
     LSD_CHECK(ctx, cudaEventSynchronize(ctx->stageDone[b]));
-    memcpy(ctx->hStage[b], gray, n0);
-    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8[b], ctx->hStage[b], n0, cudaMemcpyHostToDevice, ctx->stream));
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, gray) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) { cudaGetLastError(); memcpy(ctx->hStage[b], gray, n0); }
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dStageU8[b], pinned ? gray : ctx->hStage[b], n0, cudaMemcpyHostToDevice, ctx->stream));
     int r = buildFrameFromDeviceU8(ctx, s, ctx->dStageU8[b]);
     LSD_CHECK(ctx, cudaEventRecord(ctx->stageDone[b], ctx->stream));
     return r;

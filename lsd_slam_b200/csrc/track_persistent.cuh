@@ -46,6 +46,8 @@ struct alignas(64) TrackParams {
     float* partials;                 // [2][EV_NCH][gridDim]
     unsigned int* barrier;           // [0] arrival counter (monotonic), [32] released-epoch flag
     int barrierMode;
+    unsigned int barrierBase;        // arrivals counted by earlier launches (the counter is never reset)
+    int debug;                       // 1: also write the per-CTA cycle table
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
 };
 
@@ -98,18 +100,18 @@ __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int
 // arrivals); the LAST arriver publishes the epoch number in `counter[32]` (a different 128-byte line), which is
 // what everybody else polls -- the pollers never touch the line the atomics serialise on.  Thread 0 carries the
 // release / acquire for its CTA (the fences are cumulative over the preceding / following __syncthreads).
-__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int epoch, int mode)
+__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int base, unsigned int epoch, int mode)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int target = epoch * gridDim.x;
+        const unsigned int target = base + epoch * gridDim.x;     // wraps consistently (unsigned arithmetic)
         if (mode == 0) {
             // arrival counter + separate release flag (last arriver publishes the epoch)
             __threadfence();
             const unsigned int old = atomicAdd(counter, 1u);
             volatile unsigned int* flag = counter + 32;
-            if (old == target - 1u) { __threadfence(); *flag = epoch; }
-            else { while (*flag < epoch) { } }
+            if (old == target - 1u) { __threadfence(); *flag = target; }
+            else { while ((int)(*flag - target) < 0) { } }
             __threadfence();
         } else if (mode == 1) {
             // release-add, then acquire-poll the counter itself (one L2 hop less than mode 0)
@@ -118,7 +120,7 @@ __device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int 
             if (v != target - 1u) {
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-                } while (v < target);
+                } while ((int)(v - target) < 0);
             } else {
                 asm volatile("fence.acq_rel.gpu;" ::: "memory");
             }
@@ -128,7 +130,7 @@ __device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int 
             unsigned int v;
             do {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            } while (v < target);
+            } while ((int)(v - target) < 0);
         }
     }
     __syncthreads();
@@ -333,7 +335,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
     if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
     epoch++;
     long long t2 = clock64();
-    gridBarrier(p.barrier, epoch, p.barrierMode);
+    gridBarrier(p.barrier, p.barrierBase, epoch, p.barrierMode);
     long long t3 = clock64();
     // warp wi owns channels wi, wi+TP_WARPS, ... (<= 3 per warp); all loads are issued first, then one
     // multi-value reduction in double
@@ -622,9 +624,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         if (sh.action != ACT_CONTINUE) break;
     }
 
-    atomicAdd(p.barrier + 41, W.hits & 0xffffu);
-    atomicAdd(p.barrier + 42, W.hits >> 16);
-    if (threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
+    if (p.debug) {
+        atomicAdd(p.barrier + 41, W.hits & 0xffffu);
+        atomicAdd(p.barrier + 42, W.hits >> 16);
+    }
+    if (p.debug && threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
         long long tot = clock64() - tStart;
         for (int i = 0; i < 4; i++) out->cycBlk[blockIdx.x][i] = cyc[i];
         out->cycBlk[blockIdx.x][5] = tot;
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
-        for (int i = 0; i < 3; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
+        if (p.debug) for (int i = 0; i < 3; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
     }
 }
 
@@ -688,18 +692,21 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     P.partials = ctx->evPartials;
     P.barrier = ctx->evCounter;
     { const char* bm = getenv("LSDGPU_BARRIER_MODE"); P.barrierMode = bm ? atoi(bm) : 1; }
-    TrackState* dOut = (TrackState*)ctx->dTrackState;
+    TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* hOut = (TrackState*)ctx->hTrackState;
 
     const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM
     void* args[] = { (void*)&P, (void*)&dOut };
-    LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter, 0, 44 * sizeof(unsigned int), ctx->stream));   // arrivals + epoch flag
+    const bool dbg = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
+    P.debug = dbg ? 1 : 0;
+    P.barrierBase = ctx->barrierBase;
+    if (dbg) LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter + 40, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
     LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, TP_WIN_SMEM, ctx->stream));
     ctx->launches++;
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
-    LSD_CHECK(ctx, cudaMemcpyAsync(hOut, dOut, sizeof(TrackState), cudaMemcpyDeviceToHost, ctx->stream));
-    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the result block is mapped host memory
+    ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
     fr->hasGoodMask = true;
 
     if (ctx->profileTrackKernel) {
