@@ -156,6 +156,7 @@ def gpu_run(args, rank, world, local_rank):
         raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -255,6 +256,11 @@ def main():
         return
 
     seq, frames, res = gpu_run(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
     if rank != 0:
         return
     import torch  # noqa: F401
