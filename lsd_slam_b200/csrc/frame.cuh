@@ -16,12 +16,6 @@
 struct PyrPtrs {
     float* l[LSD_LEVELS];
 };
-struct GradPtrs {
-    const float* img[LSD_LEVELS];
-    float4* grad[LSD_LEVELS];
-    int w[LSD_LEVELS], h[LSD_LEVELS];
-};
-
 // One CTA = one 16x16 level-0 tile -> 8x8, 4x4, 2x2, 1x1 on levels 1..4 (w, h are multiples of 16,
 // SlamSystem.cpp:55).  The 2x2 box sum is exact in fp32 for u8-origin data and is
 // associated like the scalar loop (Frame.cpp:621-624).
@@ -59,8 +53,33 @@ __global__ void __launch_bounds__(256) k_image_pyramid(const uint8_t* __restrict
     }
 }
 
-// Gradients of all levels in one launch (blockIdx.y = level).  The reference sweeps the LINEAR index range
-// [w, w*(h-1)) so x = 0 and x = w-1 wrap across rows (Frame.cpp:658-677); rows 0 and h-1 are defined as zero.
+// Gradients of all levels in one launch (blockIdx.y = level) + maxGradients of level 0 in the same pass.
+// The reference sweeps the LINEAR index range [w, w*(h-1)) so x = 0 and x = w-1 wrap across rows
+// (Frame.cpp:658-677); rows 0 and h-1 are defined as zero.
+// maxGradients (Frame.cpp:708-759): |grad|, then a 3x1 vertical and a 1x3 horizontal max, all over LINEAR index
+// ranges, never-written cells defined as zero.  |grad| is recomputed from the image for the 9
+// neighbours (same fp32 operations as reading the stored gradients), which saves a launch and a pass over the
+// 4.9 MB gradient level.
+struct GradPtrs {
+    const float* img[LSD_LEVELS];
+    float4* grad[LSD_LEVELS];
+    int w[LSD_LEVELS], h[LSD_LEVELS];
+    float* maxgrad0;
+};
+__device__ __forceinline__ float absGradImg(const float* __restrict__ img, int j, int w, int h)
+{
+    if (j < w || j >= w * (h - 1)) return 0.f;
+    const float gx = 0.5f * (__ldg(img + j + 1) - __ldg(img + j - 1));
+    const float gy = 0.5f * (__ldg(img + j + w) - __ldg(img + j - w));
+    return sqrtf(gx * gx + gy * gy);
+}
+__device__ __forceinline__ float vmax3Img(const float* __restrict__ img, int t, int w, int h)
+{
+    if (t < w + 1 || t >= w * (h - 1) - 1) return 0.f;
+    float g1 = absGradImg(img, t - w, w, h), g2 = absGradImg(img, t, w, h), g3 = absGradImg(img, t + w, w, h);
+    if (g1 < g2) g1 = g2;
+    return (g1 < g3) ? g3 : g1;
+}
 __global__ void __launch_bounds__(256) k_gradients(const __grid_constant__ GradPtrs p)
 {
     const int lvl = blockIdx.y;
@@ -75,36 +94,17 @@ __global__ void __launch_bounds__(256) k_gradients(const __grid_constant__ GradP
         g.z = img[i];
     }
     p.grad[lvl][i] = g;
-}
-
-// maxGradients at level 0: |grad| then a 3x1 vertical and a 1x3 horizontal max, all over LINEAR index ranges
-// (Frame.cpp:708-759) with never-written cells defined as zero.
-__device__ __forceinline__ float absGradAt(const float4* __restrict__ grad, int j, int w, int h)
-{
-    if (j < w || j >= w * (h - 1)) return 0.f;
-    float4 g = __ldg(grad + j);
-    return sqrtf(g.x * g.x + g.y * g.y);
-}
-__device__ __forceinline__ float vmax3At(const float4* __restrict__ grad, int t, int w, int h)
-{
-    if (t < w + 1 || t >= w * (h - 1) - 1) return 0.f;
-    float g1 = absGradAt(grad, t - w, w, h), g2 = absGradAt(grad, t, w, h), g3 = absGradAt(grad, t + w, w, h);
-    if (g1 < g2) g1 = g2;
-    return (g1 < g3) ? g3 : g1;
-}
-__global__ void __launch_bounds__(256) k_maxgrad(const float4* __restrict__ grad, float* __restrict__ out, int w, int h)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
-    float r;
-    if (i >= w + 1 && i < w * (h - 1) - 1) {
-        float g1 = vmax3At(grad, i - 1, w, h), g2 = vmax3At(grad, i, w, h), g3 = vmax3At(grad, i + 1, w, h);
-        if (g1 < g2) g1 = g2;
-        r = (g1 < g3) ? g3 : g1;
-    } else {
-        r = absGradAt(grad, i, w, h);    // cells w and w*(h-1)-1 keep the raw |grad| of pass 1
+    if (lvl == 0) {
+        float r;
+        if (i >= w + 1 && i < w * (h - 1) - 1) {
+            float g1 = vmax3Img(img, i - 1, w, h), g2 = vmax3Img(img, i, w, h), g3 = vmax3Img(img, i + 1, w, h);
+            if (g1 < g2) g1 = g2;
+            r = (g1 < g3) ? g3 : g1;
+        } else {
+            r = (i >= w && i < w * (h - 1)) ? sqrtf(g.x * g.x + g.y * g.y) : 0.f;   // cells w and w*(h-1)-1 keep the raw |grad|
+        }
+        p.maxgrad0[i] = r;
     }
-    out[i] = r;
 }
 
 // Frame::setDepthFromGroundTruth, Frame.cpp:264-285

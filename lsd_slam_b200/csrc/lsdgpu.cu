@@ -310,9 +310,8 @@ static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* 
     LAUNCH(ctx);
     GradPtrs gp;
     for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }
-    k_gradients<<<dim3(divUp((int)n0, 256), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);
-    LAUNCH(ctx);
-    k_maxgrad<<<divUp((int)n0, 256), 256, 0, ctx->stream>>>(s->grad[0], s->maxgrad, w, h);
+    gp.maxgrad0 = s->maxgrad;
+    k_gradients<<<dim3(divUp((int)n0, 256), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);      // + maxGradients of level 0
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     s->hasDepth = false; s->idepthPyrValid = false; s->hasGoodMask = false;

@@ -518,18 +518,9 @@ __device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, L
     sh.lvl = lm.lvl;
 }
 
-// start iteration lm.iteration of the current level, or leave the level when the budget is used up (:343)
-__device__ __forceinline__ void lmStartIteration(const TrackParams& p, LMState& lm, LMShared& sh)
-{
-    if (lm.iteration < p.st.maxItsPerLvl[lm.lvl]) {
-        lm.nUpd[lm.lvl]++;                                                       // calculateWarpUpdate(ls), :346
-        lm.incTry = 0;
-        lmSolveAndPropose(lm, sh);
-    } else
-        lmNextLevel(p, lm, sh);
-}
-
-// thread 0 after every evaluation: the decisions of SE3Tracker.cpp:324-446
+// thread 0 after every evaluation: the decisions of SE3Tracker.cpp:324-446.  Written as one straight line with a
+// single solve/propose site (the three call sites of the reference's loop structure -- first iteration of a level,
+// next iteration after an accept, retry after a reject -- only differ in which normal equations and lambda they use).
 __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMShared& sh)
 {
     const float* s = sh.sums;
@@ -543,38 +534,37 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
     }
     const float error = s[CH_SUMRESW] / warped;                                  // calcWeightsAndResidual, :789
     lm.nRes[lvl]++;
-    if (lm.phase == PH_INIT) {
-        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);            // :331-335
-        lm.lastErr = error;                                                      // :336
+    const bool init = lm.phase == PH_INIT;
+    const bool accept = init || error < lm.lastErr;                              // :381
+    bool leave;
+    if (accept) {
+        if (!init) lm.refToFrame = lm.cand;
+        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);            // :331-335 / :385-389
+        const bool converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);   // :404
+        if (!init) lm.last_residual = error;                                     // :414
+        lm.lastErr = error;                                                      // :336 / :414
 #pragma unroll
-        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];
-        lm.LM_lambda = p.st.lambdaInitial[lvl];
-        lm.iteration = 0;
-        lmStartIteration(p, lm, sh);
-        return;
-    }
-    if (error < lm.lastErr) {                                                    // :381 accept
-        lm.refToFrame = lm.cand;
-        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);
-        const bool converged = error / lm.lastErr > p.st.convergenceEps[lvl];    // :404
-        lm.last_residual = lm.lastErr = error;                                   // :414
-#pragma unroll
-        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];
-        if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                               // :417-420
-        else lm.LM_lambda *= p.st.lambdaSuccessFac;
-        if (converged) lmNextLevel(p, lm, sh);
-        else { lm.iteration++; lmStartIteration(p, lm, sh); }
+        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                           // buffers now belong to this pose
+        if (init) { lm.LM_lambda = p.st.lambdaInitial[lvl]; lm.iteration = 0; }  // :341
+        else {
+            if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                           // :417-420
+            else lm.LM_lambda *= p.st.lambdaSuccessFac;
+            if (!converged) lm.iteration++;
+        }
+        leave = converged || !(lm.iteration < p.st.maxItsPerLvl[lvl]);           // :343, :411
+        if (!leave) { lm.nUpd[lvl]++; lm.incTry = 0; }                           // calculateWarpUpdate(ls), :346
     } else {                                                                     // :424-447 reject
         float dot = 0;
 #pragma unroll
         for (int i = 0; i < 6; i++) dot += lm.inc[i] * lm.inc[i];
-        if (!(dot > p.st.stepSizeMin[lvl])) lmNextLevel(p, lm, sh);              // :432-441
-        else {
+        leave = !(dot > p.st.stepSizeMin[lvl]);                                  // :432-441
+        if (!leave) {
             if (lm.LM_lambda == 0) lm.LM_lambda = 0.2;                           // :443-446
             else lm.LM_lambda *= pow((double)p.st.lambdaFailFac, lm.incTry);
-            lmSolveAndPropose(lm, sh);
         }
     }
+    if (leave) lmNextLevel(p, lm, sh);
+    else lmSolveAndPropose(lm, sh);
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out)
