@@ -381,9 +381,11 @@ __device__ __forceinline__ bool makeAndCheckEPL(const DepthCam& cam, const float
 // pixel touches only its own record.
 __global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, DepthGlobals G,
                                                  const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
-                                                 const float* __restrict__ kfMaxGrad, const __grid_constant__ ObserveParams OPv)
+                                                 const float* __restrict__ kfMaxGrad, const __grid_constant__ ObserveParams OPv,
+                                                 const ObserveParams* __restrict__ OPdev, const int* __restrict__ skip)
 {
-    const ObserveParams* OP = &OPv;
+    if (skip && *skip) return;                       // this frame's tracking diverged: no mapping (SlamSystem.cpp:948-967)
+    const ObserveParams* OP = OPdev ? OPdev : &OPv;
     const int x = 3 + blockIdx.x * blockDim.x + threadIdx.x;
     const int y = 3 + blockIdx.y;
     if (x >= cam.w - 3 || y >= cam.h - 3) return;
@@ -488,8 +490,9 @@ __global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, Dep
 
 // regularizeDepthMapFillHoles, DepthMap.cpp:656-718.  dst = src + created hypotheses.
 __global__ void __launch_bounds__(256) k_fill_holes(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
-                                                    const float* __restrict__ kfMaxGrad)
+                                                    const float* __restrict__ kfMaxGrad, const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (x >= cam.w || y >= cam.h) return;
@@ -527,8 +530,10 @@ __global__ void __launch_bounds__(256) k_fill_holes(HypField src, HypField dst, 
 
 // regularizeDepthMapRow<removeOcclusions>, DepthMap.cpp:758-848.  dst = src with smoothed values / removals.
 template <bool removeOcclusions>
-__global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G, int validityTH)
+__global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G, int validityTH,
+                                                    const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     // 32x8 output pixels per CTA; the 36x12 neighbourhood (idepth, var, validity, valid) is staged once in
     // shared memory, so each hypothesis is fetched from L2 1.7x instead of 25x
     __shared__ float4 tile[12][36];
@@ -665,9 +670,11 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
 // one 16x16 level-0 tile; the tracker imports the new depth right after every update, so the pyramid is always
 // needed and building it here saves a pass over the level-0 planes and a launch.
 __global__ void __launch_bounds__(256) k_set_depth_pyr(HypField cur, PyrPtrs id, PyrPtrs var, int w, int h,
-                                                       double* __restrict__ partials, unsigned int* counter, double* __restrict__ out)
+                                                       double* __restrict__ partials, unsigned int* counter, double* __restrict__ out,
+                                                       const int* __restrict__ skip)
 {
     __shared__ float2 s0[16][17], s1[8][9], s2[4][5], s3[2][3];
+    if (skip && *skip) return;
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int tilesX = w >> 4;
     const int bx = blockIdx.x % tilesX, by = blockIdx.x / tilesX;

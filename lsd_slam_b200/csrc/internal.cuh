@@ -127,6 +127,9 @@ struct lsdgpu_ctx {
     void* dTrackState = nullptr;         // persistent-kernel state block (device)
     void* hTrackState = nullptr;         // mapped pinned result block (host view)
     void* dTrackStateMapped = nullptr;   // device view of the same block
+    int trackUseTma = 1;
+    int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
+    ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
     unsigned int barrierBase = 0;        // arrivals already counted on evCounter[0] by earlier launches
     uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
     int stageEntries = 0;

@@ -87,7 +87,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
                      + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + 256 * (size_t)max_frames
-                     + alignUp(sizeof(TrackState), 256) + 4096;
+                     + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
     LSD_CHECK(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arenaBytes, ctx->stream));
@@ -143,6 +143,8 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     ctx->dStageF = (float*)take(n0 * 32);
     ctx->dScalars = (double*)take((size_t)maxBlocks * 2 * 8 + 64);
     ctx->dTrackState = take(sizeof(TrackState));
+    ctx->dObs = (ObserveParams*)take(sizeof(ObserveParams));
+    ctx->dSkipFlag = (int*)take(256);
     if ((size_t)(p - ctx->arena) > ctx->arenaBytes) return lsd_fail(ctx, "arena overflow");
 
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hEvOut, EV_NCH * 4, cudaHostAllocDefault));
@@ -723,14 +725,14 @@ extern "C" int lsdgpu_depth_invalidate(lsdgpu_ctx* ctx) { ctx->activeKf = -1; re
 extern "C" int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx) { return ctx->activeKf; }
 
 // Frame::setDepth(currentDepthMap) of the active keyframe
-static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf)
+static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf, const int* skip = nullptr)
 {
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
     PyrPtrs id, var;
     for (int l = 0; l < LSD_LEVELS; l++) { id.l[l] = kf->idepth[l]; var.l[l] = kf->idepthVar[l]; }
     k_set_depth_pyr<<<(ctx->w / 16) * (ctx->h / 16), 256, 0, ctx->stream>>>(ctx->cur, id, var, ctx->w, ctx->h, ctx->dScalars + 8,
-                                                                           ctx->evCounter + 48, kf->dStats);
+                                                                           ctx->evCounter + 48, kf->dStats, skip);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     kf->statsPending = true;
@@ -753,19 +755,19 @@ extern "C" int lsdgpu_depth_init_from_gt(lsdgpu_ctx* ctx, int kf_id)
     return setDepthOnKeyframe(ctx, kf);
 }
 
-static int runRegularize(lsdgpu_ctx* ctx, bool removeOcclusions, int validityTH)
+static int runRegularize(lsdgpu_ctx* ctx, bool removeOcclusions, int validityTH, const int* skip = nullptr)
 {
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
     dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
     std::swap(ctx->cur, ctx->oth);         // oth = previous current (the memcpy of :862), cur = output
-    if (removeOcclusions) k_regularize<true><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH);
-    else k_regularize<false><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH);
+    if (removeOcclusions) k_regularize<true><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH, skip);
+    else k_regularize<false><<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, validityTH, skip);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
 }
-static int runFillHoles(lsdgpu_ctx* ctx)
+static int runFillHoles(lsdgpu_ctx* ctx, const int* skip = nullptr)
 {
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "no active keyframe");
@@ -773,7 +775,7 @@ static int runFillHoles(lsdgpu_ctx* ctx)
     DepthGlobals G = depthGlobals(ctx);
     dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
     std::swap(ctx->cur, ctx->oth);
-    k_fill_holes<<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad);
+    k_fill_holes<<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, skip);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -826,13 +828,10 @@ extern "C" int lsdgpu_depth_download_integral(lsdgpu_ctx* ctx, int32_t* out)
     return 0;
 }
 
-// Frame::prepareForStereoWith, DataStructures/Frame.cpp:295-317 (host, double -> float like the reference)
-static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, RefConst& rc)
+// Frame::prepareForStereoWith, DataStructures/Frame.cpp:295-317 (double -> float like the reference).  Host and
+// device: the same IEEE operations, so k_prepare_observe produces bit-identical constants on the GPU.
+LSD_HD void prepareStereoConsts(const float K[9], const double q[4], const double t[3], const double s, RefConst& rc)
 {
-    const double* q = fr->thisToParent;
-    const double* t = fr->thisToParent + 4;
-    const double s = fr->thisToParent[7];
-    const float* K = ctx->cam[0].K;
     double qi[4] = { -q[0], -q[1], -q[2], q[3] };
     const double si = 1.0 / s;
     double nt[3] = { t[0] * -1.0, t[1] * -1.0, t[2] * -1.0 }, rt[3];
@@ -855,6 +854,45 @@ static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, Ref
     float tR[9];
     for (int i = 0; i < 9; i++) tR[i] = (float)R[i] * (float)s;       // thisToOther_R
     for (int i = 0; i < 3; i++) { rc.row0[i] = tR[i * 3 + 0]; rc.row1[i] = tR[i * 3 + 1]; rc.row2[i] = tR[i * 3 + 2]; }
+}
+static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, RefConst& rc)
+{
+    prepareStereoConsts(ctx->cam[0].K, fr->thisToParent, fr->thisToParent + 4, fr->thisToParent[7], rc);
+}
+
+// Device-side tail of SE3Tracker::trackFrame (SE3Tracker.cpp:473-485) + head of DepthMap::updateKeyframe
+// (DepthMap.cpp:1079-1105) for the frame that was just tracked on the active keyframe: turns the tracker's
+// device-resident result into the observe parameters, so that the mapping kernels can be enqueued behind the
+// tracking kernel without a host round trip.  One thread.
+struct PrepareConsts {
+    float K[9];
+    int frameId, reactivated, kfNumTracked, kfNumMapped, W1, H1;
+    const float* image;
+    const uint8_t* goodMask;
+};
+__global__ void k_prepare_observe(const TrackState* __restrict__ ts, PrepareConsts c, ObserveParams* __restrict__ OP, int* __restrict__ skip)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    *skip = ts->diverged;
+    if (ts->diverged) return;
+    lsd::SE3<float> T;
+    for (int i = 0; i < 4; i++) T.q[i] = ts->refToFrame[i];
+    for (int i = 0; i < 3; i++) T.t[i] = ts->refToFrame[4 + i];
+    const lsd::SE3<double> f2r = lsd::se3Cast<double>(lsd::se3Inverse(T));        // SE3Tracker.cpp:483-485
+    RefConst& rc = OP->refs[0];
+    prepareStereoConsts(c.K, f2r.q, f2r.t, 1.0, rc);
+    rc.initialTrackedResidual = ts->lastResidual / ts->pointUsage;               // :482
+    rc.id = c.frameId;
+    rc.trackedOnActive = 1;
+    rc.image = c.image;
+    rc.goodMask = c.goodMask;
+    const bool trackingWasGood = ts->goodCount / (c.W1 * c.H1) > 0.04f && ts->goodCount / (ts->goodCount + ts->badCount) > 0.5f;   // :475-477
+    OP->nRefs = 1;
+    OP->byIdOffset = c.frameId; OP->byIdSize = 1; OP->byId[0] = 0;
+    OP->oldestIdx = 0; OP->newestIdx = 0;
+    OP->reactivated = c.reactivated;
+    OP->kfNumTracked = c.kfNumTracked + (trackingWasGood ? 1 : 0);               // :479-480
+    OP->kfNumMapped = c.kfNumMapped;
 }
 
 static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
@@ -886,16 +924,18 @@ static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSl
     return 0;
 }
 
-static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
+static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devParams = false, const int* skip = nullptr)
 {
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "no active keyframe");
-    int r = setupObserve(ctx, ref_ids, n_refs, kf);
-    if (r) return r;
+    if (!devParams) {
+        int r = setupObserve(ctx, ref_ids, n_refs, kf);
+        if (r) return r;
+    }
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
     dim3 grid(divUp(cam.w - 6, 128), cam.h - 6);
-    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs);
+    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs, devParams ? ctx->dObs : nullptr, skip);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -1035,6 +1075,48 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
     if (kf->depthHasBeenUpdatedFlag) { r = lsdgpu_ref_import(ctx, kf_id); if (r) return r; }     // SlamSystem.cpp:907-912
+    FrameSlot* fr = findSlot(ctx, frame_id);
+    if (mode == 1 && !keyframe_change && ctx->activeKf == kf_id && fr) {
+        // Whole frame enqueued back to back: tracking kernel, device-side prepareForStereoWith, observe, fill holes,
+        // regularise, setDepth -- ONE host synchronisation at the end (the mapping kernels read the pose from the
+        // tracker's device-resident result and do nothing if tracking diverged).
+        lsdgpu_track_settings ds;
+        if (!s) { lsdgpu_default_track_settings(&ds); ds.maxItsPerLvl[4] = 0; s = &ds; }
+        r = ensureIdepthPyramid(ctx, kf);
+        if (r) return r;
+        r = trackPersistentEnqueue(ctx, kf, fr, init_qt, s);
+        if (r) return r;
+        PrepareConsts pc;
+        memcpy(pc.K, ctx->cam[0].K, 36);
+        pc.frameId = frame_id; pc.reactivated = ctx->activeKfReactivated ? 1 : 0;
+        pc.kfNumTracked = kf->numFramesTrackedOnThis; pc.kfNumMapped = kf->numMappedOnThis;
+        pc.W1 = ctx->w >> SE3TRACKING_MIN_LEVEL; pc.H1 = ctx->h >> SE3TRACKING_MIN_LEVEL;
+        pc.image = fr->image[0]; pc.goodMask = fr->goodMask;
+        k_prepare_observe<<<1, 32, 0, ctx->stream>>>((const TrackState*)ctx->dTrackState, pc, ctx->dObs, ctx->dSkipFlag);
+        LAUNCH(ctx);
+        r = runObserve(ctx, &frame_id, 1, true, ctx->dSkipFlag);          // DepthMap.cpp:1127
+        if (r) return r;
+        r = runFillHoles(ctx, ctx->dSkipFlag);                            // :1135
+        if (r) return r;
+        r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP, ctx->dSkipFlag);   // :1143
+        if (r) return r;
+        const bool didSetDepth = !kf->depthHasBeenUpdatedFlag;            // :1150-1157
+        const bool prevPending = kf->statsPending, prevPyr = kf->idepthPyrValid;
+        if (didSetDepth) { r = setDepthOnKeyframe(ctx, kf, ctx->dSkipFlag); if (r) return r; }
+        r = trackPersistentFinish(ctx, fr, out);                          // the one synchronisation of the frame
+        if (r) return r;
+        if (out->diverged) {                 // nothing ran on the device: undo the host-side bookkeeping of setDepth
+            if (didSetDepth) { kf->depthHasBeenUpdatedFlag = false; kf->statsPending = prevPending; kf->idepthPyrValid = prevPyr; }
+            return 0;
+        }
+        if (out->trackingWasGood) kf->numFramesTrackedOnThis++;           // SE3Tracker.cpp:479-480
+        fr->initialTrackedResidual = out->initialTrackedResidual;
+        for (int i = 0; i < 7; i++) fr->thisToParent[i] = out->frameToRef_qt[i];
+        fr->thisToParent[7] = 1.0;
+        fr->parentId = kf->id;
+        kf->numMappedOnThis++;                                            // DepthMap.cpp:1165
+        return lsdgpu_frame_clear_good_mask(ctx, frame_id);               // SlamSystem.cpp:573
+    }
     r = lsdgpu_se3_track(ctx, kf_id, frame_id, init_qt, s, mode, out);
     if (r) return r;
     if (out->diverged) return 0;                 // the caller decides (relocalisation is out of scope)

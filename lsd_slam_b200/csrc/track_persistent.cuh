@@ -567,7 +567,7 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
     else lmSolveAndPropose(lm, sh);
 }
 
-__global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out)
+__global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out, TrackState* __restrict__ outDev)
 {
     __shared__ LMShared sh;
     __shared__ LMState lm;
@@ -635,6 +635,10 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         out->diverged = lm.diverged;
         for (int l = 0; l < LSD_LEVELS; l++) { out->numCalcResidualCalls[l] = lm.nRes[l]; out->numCalcWarpUpdateCalls[l] = lm.nUpd[l]; }
         out->totalEvals = (int)epoch;
+        // device-resident copy of what the mapping kernels of the same frame need (no host round trip in between)
+        for (int i = 0; i < 7; i++) outDev->refToFrame[i] = out->refToFrame[i];
+        outDev->pointUsage = ev.pointUsage; outDev->goodCount = ev.goodCount; outDev->badCount = ev.badCount;
+        outDev->lastResidual = lm.last_residual; outDev->diverged = lm.diverged;
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
@@ -651,10 +655,12 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
     return cudaFuncSetAttribute((const void*)k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_WIN_SMEM);
 }
 
-static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
-                           const lsdgpu_track_settings* st, lsdgpu_track_result* out)
+static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_result* out);
+
+// enqueue the tracking kernel of one frame on the context's stream (no host synchronisation)
+static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
+                                  const lsdgpu_track_settings* st)
 {
-    memset(out, 0, sizeof(*out));
     TrackParams P;
     memset(&P, 0, sizeof(P));
     for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++) {
@@ -683,10 +689,10 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     P.barrier = ctx->evCounter;
     { const char* bm = getenv("LSDGPU_BARRIER_MODE"); P.barrierMode = bm ? atoi(bm) : 1; }
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
-    TrackState* hOut = (TrackState*)ctx->hTrackState;
+    TrackState* dOutDev = (TrackState*)ctx->dTrackState;
 
     const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM
-    void* args[] = { (void*)&P, (void*)&dOut };
+    void* args[] = { (void*)&P, (void*)&dOut, (void*)&dOutDev };
     const bool dbg = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
     P.debug = dbg ? 1 : 0;
     P.barrierBase = ctx->barrierBase;
@@ -695,9 +701,27 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, TP_WIN_SMEM, ctx->stream));
     ctx->launches++;
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
+    fr->hasGoodMask = true;
+    ctx->trackUseTma = P.useTma;
+    return 0;
+}
+
+static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
+                           const lsdgpu_track_settings* st, lsdgpu_track_result* out)
+{
+    int r = trackPersistentEnqueue(ctx, kf, fr, init_qt, st);
+    if (r) return r;
+    return trackPersistentFinish(ctx, fr, out);
+}
+
+// wait for the frame's work and translate the mapped result block (SE3Tracker.cpp:453-485)
+static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_result* out)
+{
+    memset(out, 0, sizeof(*out));
+    TrackState* hOut = (TrackState*)ctx->hTrackState;
+    const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the result block is mapped host memory
     ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
-    fr->hasGoodMask = true;
 
     if (ctx->profileTrackKernel) {
         float ms = 0;
@@ -713,7 +737,7 @@ static int trackPersistent(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const 
     if (getenv("LSDGPU_TRACK_DEBUG")) {
         unsigned int dbgc[3] = { 0, 0, 0 };
         cudaMemcpy(dbgc, ctx->evCounter + 40, 12, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[track] useTma=%d tmaTimeouts=%u taps: %u from the smem window, %u through L1/L2\n", P.useTma, dbgc[0], dbgc[1], dbgc[2]);
+        fprintf(stderr, "[track] useTma=%d tmaTimeouts=%u taps: %u from the smem window, %u through L1/L2\n", ctx->trackUseTma, dbgc[0], dbgc[1], dbgc[2]);
         fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
                 hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
         fprintf(stderr, "   thread0: lmAdvance=%lld (solve=%lld pose=%lld)\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2]);

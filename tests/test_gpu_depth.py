@@ -253,3 +253,28 @@ def test_fused_call_equals_individual_calls(seq_small, frames_small):
     assert np.array_equal(outs[0][0], outs[1][0])
     assert outs[0][1].tobytes() == outs[1][1].tobytes()
     assert np.array_equal(outs[0][2], outs[1][2])
+
+
+def test_fused_call_divergence_leaves_map_untouched(seq_small, frames_small):
+    """single-sync frame path: when tracking diverges the already-enqueued mapping kernels must do nothing"""
+    import ctypes as C
+    ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, max_frames=8)
+    from lsd_slam_b200.stream import GpuStream
+    gs = GpuStream(ctx, mode=1, kf_every=0, fused_call=True)
+    gs.init_gt(0, frames_small[0][0], frames_small[0][1])
+    gs.step(1, frames_small[1][0])
+    before = gs.map.current().copy()
+    idepth_before = ctx.download(0, abi.BUF_IDEPTH, 1).copy()
+    gs.last_pose = np.array([0, 0.7071067811865476, 0, 0.7071067811865476, 0, 0, 0], np.float64)   # looks away
+    with pytest.raises(RuntimeError):
+        gs.step(2, frames_small[2][0])
+    assert gs.tracker.diverged
+    assert gs.map.current().tobytes() == before.tobytes()
+    assert np.array_equal(ctx.download(0, abi.BUF_IDEPTH, 1), idepth_before)
+    # and the stream continues normally afterwards
+    gs.last_pose = np.array(gs.poses[-1])
+    gs.n_tracked -= 1
+    ctx.release(2)
+    p = gs.step(3, frames_small[3][0])
+    assert not gs.tracker.diverged and np.isfinite(p).all()
+    ctx.close()
