@@ -8,6 +8,7 @@
 #include "track_persistent.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 #include <new>
 
 #define LAUNCH(ctx) ((ctx)->launches++)
@@ -1076,7 +1077,11 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
     if (kf->depthHasBeenUpdatedFlag) { r = lsdgpu_ref_import(ctx, kf_id); if (r) return r; }     // SlamSystem.cpp:907-912
     FrameSlot* fr = findSlot(ctx, frame_id);
-    if (mode == 1 && !keyframe_change && ctx->activeKf == kf_id && fr) {
+    // Measured on B200 (A/B on one box, 640x480): the single-sync path is ~5 us per frame SLOWER than syncing after
+    // the tracking kernel and preparing the stereo constants on the host (the one-thread double-precision
+    // k_prepare_observe costs more than the host round trip it removes), so it is opt-in.
+    const bool singleSync = getenv("LSDGPU_SINGLE_SYNC") && atoi(getenv("LSDGPU_SINGLE_SYNC")) == 1;
+    if (singleSync && mode == 1 && !keyframe_change && ctx->activeKf == kf_id && fr) {
         // Whole frame enqueued back to back: tracking kernel, device-side prepareForStereoWith, observe, fill holes,
         // regularise, setDepth -- ONE host synchronisation at the end (the mapping kernels read the pose from the
         // tracker's device-resident result and do nothing if tracking diverged).

@@ -255,9 +255,11 @@ def test_fused_call_equals_individual_calls(seq_small, frames_small):
     assert np.array_equal(outs[0][2], outs[1][2])
 
 
-def test_fused_call_divergence_leaves_map_untouched(seq_small, frames_small):
-    """single-sync frame path: when tracking diverges the already-enqueued mapping kernels must do nothing"""
-    import ctypes as C
+@pytest.mark.parametrize("single_sync", ["0", "1"])
+def test_fused_call_divergence_leaves_map_untouched(seq_small, frames_small, single_sync, monkeypatch):
+    """frame path (also the opt-in single-sync variant, where the mapping kernels are already enqueued behind the
+    tracking kernel): when tracking diverges nothing of the map may change"""
+    monkeypatch.setenv("LSDGPU_SINGLE_SYNC", single_sync)
     ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, max_frames=8)
     from lsd_slam_b200.stream import GpuStream
     gs = GpuStream(ctx, mode=1, kf_every=0, fused_call=True)
@@ -278,3 +280,46 @@ def test_fused_call_divergence_leaves_map_untouched(seq_small, frames_small):
     p = gs.step(3, frames_small[3][0])
     assert not gs.tracker.diverged and np.isfinite(p).all()
     ctx.close()
+
+
+def test_single_sync_variant_is_bit_identical(seq_small, frames_small, monkeypatch):
+    """LSDGPU_SINGLE_SYNC=1 (device-side prepareForStereoWith) == default path, bit for bit"""
+    from lsd_slam_b200.stream import GpuStream
+    outs = []
+    for v in ("0", "1"):
+        monkeypatch.setenv("LSDGPU_SINGLE_SYNC", v)
+        ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, max_frames=8)
+        gs = GpuStream(ctx, mode=1, kf_every=0, fused_call=True)
+        gs.init_gt(0, frames_small[0][0], frames_small[0][1])
+        for k in range(1, 6):
+            gs.step(k, frames_small[k][0])
+        outs.append((np.array(gs.poses), gs.map.current().copy()))
+        ctx.close()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1].tobytes() == outs[1][1].tobytes()
+
+
+def test_reactivated_keyframe_and_multiple_reference_frames(gpu_ctx_small, oracle, seq_small, frames_small):
+    """setFromExistingKF semantics (activeKeyFrameIsReactivated: newest reference frame is used, DepthMap.cpp:241,317)
+    and a 3-frame reference deque with id gaps (referenceFrameByID, DepthMap.cpp:1103-1104)"""
+    p = Pair(gpu_ctx_small, oracle, seq_small, frames_small, "random")
+    refs = []
+    for k in (3, 5, 8):                      # ids with gaps: byId table has repeated entries
+        of = p.add_frame(k)
+        gpu_ctx_small.set_pose(k, of.thisToParent(), 0, 0.0)
+        refs.append(of)
+    # non-reactivated, three references at once
+    oracle.lib().lsdo_frame_set_depthHasBeenUpdatedFlag(p.okf.ptr, 0)
+    gpu_ctx_small.L.lsdgpu_ref_import(gpu_ctx_small.ptr, 0)
+    p.odm.updateKeyframe(refs)
+    p.gdm.updateKeyframe([3, 5, 8])
+    p.compare(exact=True)
+    # make some hypotheses point at later frames, then update again
+    cur = p.odm.current().copy()
+    rng = np.random.default_rng(9)
+    cur["nextStereoFrameMinID"] = rng.integers(0, 12, cur.shape).astype(np.float32)
+    p.odm.set_current(cur)
+    p.gdm.setHypotheses(0, cur, do_set_depth=False)
+    p.odm.observeDepth(refs)
+    p.gdm.observeDepth([3, 5, 8])
+    p.compare(exact=True)
