@@ -128,6 +128,7 @@ struct lsdgpu_ctx {
     void* hTrackState = nullptr;         // mapped pinned result block (host view)
     void* dTrackStateMapped = nullptr;   // device view of the same block
     int trackUseTma = 1;
+    int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
     unsigned int barrierBase = 0;        // arrivals already counted on evCounter[0] by earlier launches

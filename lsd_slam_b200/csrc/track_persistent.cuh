@@ -16,12 +16,15 @@
 #include "internal.cuh"
 #include "track.cuh"
 #include <stdlib.h>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #define TP_THREADS 512
 #define TP_MAXGRID_DBG 160
 #define TP_WIN_SMEM ((TP_THREADS / 32) * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
 #define EX_ROW 48                    // floats per exchange row (192 B): EV_NCH data + tag + pad
 #define TP_LOCAL_MAX_PIXELS 1024      // levels up to this many pixels are evaluated redundantly per CTA
+#define TP_CLUSTER_MAX_PIXELS 8192    // ... and up to this many redundantly per thread-block cluster (DSMEM exchange)
 
 struct TrackLevelParams {
     const float* kfIdepth;
@@ -48,6 +51,7 @@ struct alignas(64) TrackParams {
     int barrierMode;
     unsigned int barrierBase;        // arrivals counted by earlier launches (the counter is never reset)
     int debug;                       // 1: also write the per-CTA cycle table
+    int clusterLocalMaxPixels;       // levels up to this size are evaluated per cluster (0: never; needs a cluster launch)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
 };
 
@@ -214,9 +218,18 @@ struct WarpWindow {
     unsigned int hits;               // low 16 bits: taps served from the window, high 16: taps through L1/L2
 };
 
-__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool local, LMShared& sh, float (*sm)[EV_NCH],
+enum { EVAL_GRID = 0, EVAL_CTA = 1, EVAL_CLUSTER = 2 };
+
+// evalMode: EVAL_GRID    the level is split over the whole grid (one grid barrier + L2 exchange),
+//           EVAL_CLUSTER every thread-block cluster evaluates the whole level redundantly (small levels: the CTAs of a
+//                        cluster exchange their 40 sums through distributed shared memory behind one hardware
+//                        cluster barrier, ~10x cheaper than the grid barrier and no L2 round trip),
+//           EVAL_CTA     every CTA evaluates the whole level redundantly (tiny levels, no exchange at all).
+__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int evalMode, LMShared& sh, float (*sm)[EV_NCH],
+                                             float (*xrow)[EV_NCH], unsigned int& xphase,
                                              unsigned int& epoch, long long* cyc, WarpWindow& W)
 {
+    const bool local = evalMode != EVAL_GRID;
     long long t0 = clock64();
     const TrackLevelParams& L = p.lvl[lvl];
     const EvalPose P = sh.pose;
@@ -228,8 +241,12 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
     // 32-pixel chunks are dealt round-robin to the CTAs (chunk c -> CTA c % G, warp (c / G) % TP_WARPS): the
     // semi-dense density varies over the image, a contiguous split would leave CTAs unevenly loaded
-    const int first = local ? threadIdx.x : ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31);
-    const int stride = local ? TP_THREADS : gridDim.x * TP_THREADS;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
+    int first, stride;
+    if (evalMode == EVAL_GRID) { first = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31); stride = gridDim.x * TP_THREADS; }
+    else if (evalMode == EVAL_CLUSTER) { first = ((threadIdx.x >> 5) * csize + crank) * 32 + (threadIdx.x & 31); stride = csize * TP_THREADS; }
+    else { first = threadIdx.x; stride = TP_THREADS; }
     // the loop bound is evaluated on the chunk base so that whole warps stay in the loop (the window set-up below
     // uses full-warp ballots / shuffles); w*h need not be a multiple of 32 (e.g. 40x30 on level 4)
     const int laneId = threadIdx.x & 31;
@@ -320,8 +337,25 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, bool
 #pragma unroll
         for (int wi = 0; wi < TP_WARPS; wi++) ctaSum += sm[wi][threadIdx.x];
     }
-    if (local) {
+    if (evalMode == EVAL_CTA) {
         if (threadIdx.x < EV_NCH) sh.sums[threadIdx.x] = ctaSum;
+        __syncthreads();
+        long long t2 = clock64();
+        cyc[0] += t1 - t0; cyc[1] += t2 - t1;
+        return;
+    }
+    if (evalMode == EVAL_CLUSTER) {
+        // DSMEM exchange: publish this CTA's row (double-buffered by phase), one cluster barrier, then every CTA sums
+        // the rows of all ranks in rank order -> identical totals in every CTA of every cluster
+        float* mine = xrow[xphase & 1u];
+        if (threadIdx.x < EV_NCH) mine[threadIdx.x] = ctaSum;
+        cluster.sync();
+        if (threadIdx.x < EV_NCH) {
+            float tot = 0.f;
+            for (int r = 0; r < csize; r++) tot += cluster.map_shared_rank(mine, r)[threadIdx.x];
+            sh.sums[threadIdx.x] = tot;
+        }
+        xphase++;
         __syncthreads();
         long long t2 = clock64();
         cyc[0] += t1 - t0; cyc[1] += t2 - t1;
@@ -575,6 +609,9 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
     extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
     __shared__ __align__(8) uint64_t winBar[TP_WARPS];
+    __shared__ float xrow[2][EV_NCH];                              // this CTA's row for the cluster-local exchange
+    unsigned int xphase = 0;
+    const int clusterSize = (int)cg::this_cluster().num_blocks();
     unsigned int epoch = 0;
     long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
     const long long tStart = clock64();
@@ -607,13 +644,16 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
 
     while (true) {
         const int lvl = sh.lvl;
-        const bool local = p.lvl[lvl].w * p.lvl[lvl].h <= TP_LOCAL_MAX_PIXELS;
-        gridEvaluate(p, lvl, local, sh, sm, epoch, cyc, W);
+        const int npx = p.lvl[lvl].w * p.lvl[lvl].h;
+        const int evalMode = npx <= TP_LOCAL_MAX_PIXELS ? EVAL_CTA
+                           : (clusterSize > 1 && npx <= p.clusterLocalMaxPixels) ? EVAL_CLUSTER : EVAL_GRID;
+        gridEvaluate(p, lvl, evalMode, sh, sm, xrow, xphase, epoch, cyc, W);
         if (threadIdx.x == 0) { const long long t0 = clock64(); lmAdvance(p, lm, sh); lm.dbg[0] += clock64() - t0; }
         __syncthreads();
         if (sh.action != ACT_CONTINUE) break;
     }
 
+    if (clusterSize > 1) cg::this_cluster().sync();             // nobody may exit while a peer can still read its xrow
     if (p.debug) {
         atomicAdd(p.barrier + 41, W.hits & 0xffffu);
         atomicAdd(p.barrier + 42, W.hits >> 16);
@@ -652,7 +692,48 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
     cudaError_t e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
     if (e != cudaSuccess) return e;
     if (!coop) return cudaErrorNotSupported;
-    return cudaFuncSetAttribute((const void*)k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_WIN_SMEM);
+    e = cudaFuncSetAttribute((const void*)k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_WIN_SMEM);
+    if (e != cudaSuccess) return e;
+    // Optional (LSDGPU_TRACK_CLUSTER=2|4|8): launch as thread-block clusters and evaluate levels of <= 8192 pixels (L3, L4
+    // at 640x480) redundantly per cluster with a DSMEM exchange instead of the grid barrier.  Measured on B200: SLOWER
+    // (cluster 4: 228k vs 211k cycles per frame; cluster 2: 275k) -- a warp then walks 2-3 chunks sequentially and the
+    // per-chunk dependency chain (~2 700 cycles) dominates; the grid has enough warps to give every chunk its own.
+    // Default: no clusters.  The grid is the largest whole number of co-resident clusters (B200: 33 x 4 = 132 CTAs).
+    {
+        const char* ce = getenv("LSDGPU_TRACK_CLUSTER");
+        int cs = ce ? atoi(ce) : 1;
+        if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 1;
+        ctx->trackCluster = 1;
+        ctx->trackGrid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;
+        if (cs > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctx->smCount / cs * cs); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, (const void*)k_track_persistent, &cfg) == cudaSuccess && nc * cs >= 64) {
+                ctx->trackCluster = cs;
+                ctx->trackGrid = nc * cs < TP_MAXGRID ? nc * cs : (TP_MAXGRID / cs) * cs;
+            } else
+                cudaGetLastError();
+        }
+    }
+    if (getenv("LSDGPU_TRACK_DEBUG")) {
+        fprintf(stderr, "[track] cluster %d, grid %d\n", ctx->trackCluster, ctx->trackGrid);
+        for (int cs = 1; cs <= 8; cs *= 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctx->smCount / cs * cs); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nc = -1;
+            cudaError_t ce = cudaOccupancyMaxActiveClusters(&nc, (const void*)k_track_persistent, &cfg);
+            fprintf(stderr, "[track] cluster size %d: max active clusters %d (%s) -> %d CTAs\n", cs, nc, cudaGetErrorString(ce), nc * cs);
+        }
+        cudaGetLastError();
+    }
+    return cudaSuccess;
 }
 
 static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_result* out);
@@ -691,14 +772,24 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* dOutDev = (TrackState*)ctx->dTrackState;
 
-    const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM
+    const int grid = ctx->trackGrid;                                               // one CTA per SM (whole clusters)
+    P.clusterLocalMaxPixels = ctx->trackCluster > 1 ? TP_CLUSTER_MAX_PIXELS : 0;
     void* args[] = { (void*)&P, (void*)&dOut, (void*)&dOutDev };
     const bool dbg = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
     P.debug = dbg ? 1 : 0;
     P.barrierBase = ctx->barrierBase;
     if (dbg) LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter + 40, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
-    LSD_CHECK(ctx, cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(grid), dim3(TP_THREADS), args, TP_WIN_SMEM, ctx->stream));
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM; cfg.stream = ctx->stream;
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        at[1].id = cudaLaunchAttributeClusterDimension;
+        at[1].val.clusterDim.x = ctx->trackCluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = ctx->trackCluster > 1 ? 2 : 1;
+        LSD_CHECK(ctx, cudaLaunchKernelExC(&cfg, (const void*)k_track_persistent, args));
+    }
     ctx->launches++;
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
     fr->hasGoodMask = true;
@@ -719,7 +810,7 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
 {
     memset(out, 0, sizeof(*out));
     TrackState* hOut = (TrackState*)ctx->hTrackState;
-    const int grid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;
+    const int grid = ctx->trackGrid;
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the result block is mapped host memory
     ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
 

@@ -164,6 +164,7 @@ void lsdo_depthmap_destroy(lsdo_depthmap* d);
 void lsdo_depthmap_reset(lsdo_depthmap* d);
 void lsdo_depthmap_initializeFromGTDepth(lsdo_depthmap* d, lsdo_frame* f);
 void lsdo_depthmap_initializeRandomly(lsdo_depthmap* d, lsdo_frame* f);
+void lsdo_depthmap_setFromExistingKF(lsdo_depthmap* d, lsdo_frame* kf, const float* idepth_reAct, const float* idepthVar_reAct, const unsigned char* validity_reAct);
 void lsdo_depthmap_updateKeyframe(lsdo_depthmap* d, lsdo_frame** refs, int n_refs);
 void lsdo_depthmap_createKeyFrame(lsdo_depthmap* d, lsdo_frame* new_kf);
 void lsdo_depthmap_finalizeKeyFrame(lsdo_depthmap* d);

@@ -128,6 +128,7 @@ def lib(fast: bool = False):
     sig("lsdo_depthmap_reset", None, vp)
     sig("lsdo_depthmap_initializeFromGTDepth", None, vp, vp)
     sig("lsdo_depthmap_initializeRandomly", None, vp, vp)
+    sig("lsdo_depthmap_setFromExistingKF", None, vp, vp, fp, fp, u8p)
     sig("lsdo_depthmap_updateKeyframe", None, vp, C.POINTER(vp), C.c_int)
     sig("lsdo_depthmap_createKeyFrame", None, vp, vp)
     sig("lsdo_depthmap_finalizeKeyFrame", None, vp)
@@ -286,6 +287,12 @@ class DepthMap:
     def initializeRandomly(self, f: Frame):
         self._keep.append(f)
         self.L.lsdo_depthmap_initializeRandomly(self.ptr, f.ptr)
+
+    def setFromExistingKF(self, kf: Frame, idepth, idepthVar, validity):
+        self._keep.append(kf)
+        a, b = np.ascontiguousarray(idepth, np.float32), np.ascontiguousarray(idepthVar, np.float32)
+        c = np.ascontiguousarray(validity, np.uint8)
+        self.L.lsdo_depthmap_setFromExistingKF(self.ptr, kf.ptr, _fp(a), _fp(b), c.ctypes.data_as(C.POINTER(C.c_uint8)))
 
     def _refs(self, refs):
         arr = (C.c_void_p * len(refs))(*[r.ptr for r in refs])

@@ -323,3 +323,46 @@ def test_reactivated_keyframe_and_multiple_reference_frames(gpu_ctx_small, oracl
     p.odm.observeDepth(refs)
     p.gdm.observeDepth([3, 5, 8])
     p.compare(exact=True)
+
+
+def test_set_from_existing_keyframe_reactivated(gpu_ctx_small, oracle, seq_small, frames_small):
+    """DepthMap::setFromExistingKF (DepthMap.cpp:920-962): re-activation data -> hypotheses, regularizeDepthMap(false),
+    activeKeyFrameIsReactivated => observeDepth uses the NEWEST reference frame (:241, :317)"""
+    img0, d0 = frames_small[0]
+    rng = np.random.default_rng(11)
+    okf = oracle.Frame(0, img0, seq_small.K)
+    mg = okf.maxGradients(0)
+    idepth = np.where(mg >= 5, 1.0 / d0 + rng.normal(0, 0.02, d0.shape), 0).astype(np.float32)
+    var = np.where(mg >= 5, 0.01, -1.0).astype(np.float32)
+    var[rng.random(var.shape) < 0.02] = -2.0                       # blacklisted cells (Frame.cpp:134-137)
+    validity = rng.integers(0, 60, d0.shape).astype(np.uint8)
+    odm = oracle.DepthMap(seq_small.w, seq_small.h, seq_small.K)
+    odm.setFromExistingKF(okf, idepth, var, validity)
+    # GPU: the host builds the AoS exactly as DepthMap.cpp:937-959 and asks for the reactivation semantics
+    hyp = np.zeros(d0.shape, abi.HYP_DTYPE)
+    ok = var > 0
+    hyp["isValid"] = ok
+    hyp["idepth"] = np.where(ok, idepth, 0); hyp["idepth_var"] = np.where(ok, var, 0)
+    hyp["idepth_smoothed"] = np.where(ok, -1, 0); hyp["idepth_var_smoothed"] = np.where(ok, -1, 0)
+    hyp["validity_counter"] = np.where(ok, validity, 0)
+    hyp["blacklisted"] = np.where(~ok & (var == -2), -2, 0)
+    gpu_ctx_small.upload(0, img0)
+    gdm = abi.DepthMap(gpu_ctx_small)
+    gdm.setHypotheses(0, hyp, reactivated=True, do_set_depth=False)
+    a, b = gdm.current(), odm.current()
+    rep = hyp_equal_report(a, b)
+    assert rep["valid_mismatch"] == 0 and rep["blacklist_mismatch"] == 0 and rep["idepth_smoothed_bitdiff"] == 0, rep
+    # two reference frames: the reactivated map must take the newest one for every pixel
+    ofs = []
+    for k in (4, 7):
+        of = oracle.Frame(k, frames_small[k][0], seq_small.K)
+        qts = np.concatenate([seq_small.frame_to_ref_qt(k), [1.0]])
+        of.set_thisToParent(qts, okf)
+        gpu_ctx_small.upload(k, frames_small[k][0])
+        gpu_ctx_small.set_pose(k, qts, 0, 0.0)
+        ofs.append(of)
+    odm.observeDepth(ofs)
+    gdm.observeDepth([4, 7])
+    rep = hyp_equal_report(gdm.current(), odm.current())
+    assert rep["valid_mismatch"] == 0 and rep["idepth_bitdiff"] == 0 and rep["idepth_var_bitdiff"] == 0, rep
+    assert rep["nextStereoFrameMinID_bitdiff"] == 0 and rep["validity_mismatch"] == 0, rep
