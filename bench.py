@@ -274,6 +274,13 @@ def main():
     r, e = res["resident"], res["e2e"]
     fps = world * args.steps / (r["total_ms"] * 1e-3)
     fps_e2e = world * args.steps / (e["total_ms"] * 1e-3)
+    traffic = None
+    try:        # DRAM bytes per launch of the tracking kernel from the committed ncu --set full capture (640x480 only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_track_persistent"]
+        if (args.width, args.height) == (640, 480):
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     ach = (r["kbytes"] / max(r["klaunch"], 1)) / (r["kms"] * 1e-3 / max(r["klaunch"], 1)) / 1e9 if r["kms"] > 0 else 0.0
     line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -284,7 +291,8 @@ def main():
             "gpu_launches": int(r["launches"]),
             "step_ms": {"p50": r["p50"], "p95": r["p95"], "wall_ms_per_step_incl_flush": 1e3 * r["wall"] / args.steps},
             "roofline": {"kernel": "warp/residual/JtJ (SE3 tracking) kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "share_of_step": r["kms"] / max(r["total_ms"], 1e-9),
                          "launches": int(r["klaunch"]), "avg_launch_us": 1e3 * r["kms"] / max(r["klaunch"], 1),
                          "algorithmic_bytes_per_launch": r["kbytes"] / max(r["klaunch"], 1),
                          "note": "working set (<= 2.2 MB per level) is L2/SMEM resident: the kernel is latency-bound, not HBM-bound"},
