@@ -174,6 +174,18 @@ int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t
                          const double frameToRef_init_qt[7], const lsdgpu_track_settings* s, int mode,
                          int keyframe_change, lsdgpu_track_result* out, double new_kf_thisToParent_qts[8]);
 
+/* ---- permaRef tracking, batched ------------------------------------------------------------
+ * Frame::setPermaRef Frame.cpp:149-174: freeze the keyframe's CURRENT level-4 point cloud (positions, colour, variance). */
+int lsdgpu_frame_set_perma_ref(lsdgpu_ctx* ctx, int kf_id, int* num_points_out);
+/* SE3Tracker::checkPermaRefOverlap SE3Tracker.cpp:121-157 for n candidates in one launch:
+ * usage_out[i] = pointUsage of keyframe kf_ids[i] under referenceToFrame refToFrame_qt[7*i..] */
+int lsdgpu_perma_overlap_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, const double* refToFrame_qt, float* usage_out);
+/* SE3Tracker::trackFrameOnPermaref SE3Tracker.cpp:162-272 for n candidate keyframes against ONE frame in one launch
+ * (one CTA per candidate; TestTrack settings util/settings.h:379-382: 5 iterations, eps 0.98, step-min 1e-3).
+ * results[i].frameToRef_qt holds referenceToFrame (the reference returns it un-inverted, :271). */
+int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, int frame_id, const double* refToFrame_init_qt,
+                             lsdgpu_track_result* results);
+
 /* Point-sharded tracking across GPUs (BASELINE config 5): rank `shard` of `n_shards` evaluates every
  * n_shards-th 32-pixel chunk of the level; the LSDGPU_EVAL_NSUMS partial sums of every evaluation are handed to
  * `allreduce` (sum over ranks, in place, HOST buffer) before the LM decision, so all ranks take identical

@@ -100,6 +100,9 @@ SYMBOLS = [
     ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
     ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
     ("lsdgpu_track_and_map", C.c_int, [_vp, C.c_int, C.c_int, _u8p, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.POINTER(TrackResult), _dp]),
+    ("lsdgpu_frame_set_perma_ref", C.c_int, [_vp, C.c_int, _ip]),
+    ("lsdgpu_perma_overlap_batch", C.c_int, [_vp, C.c_int, _ip, _dp, _fp]),
+    ("lsdgpu_perma_track_batch", C.c_int, [_vp, C.c_int, _ip, C.c_int, _dp, C.POINTER(TrackResult)]),
     ("lsdgpu_se3_track_sharded", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(TrackResult)]),
     ("lsdgpu_depth_reset", C.c_int, [_vp]),
     ("lsdgpu_depth_is_valid", C.c_int, [_vp]),
@@ -313,6 +316,26 @@ class SE3Tracker:
         self.affineEstimation_a, self.affineEstimation_b = r.affineEstimation_a, r.affineEstimation_b
         self.diverged, self.trackingWasGood = bool(r.diverged), bool(r.trackingWasGood)
         return np.array(r.frameToRef_qt, np.float64)
+
+    # ---- permaRef tracking, batched over candidate keyframes ----
+    def setPermaRef(self, kf_id: int) -> int:
+        n = C.c_int()
+        self.ctx._ck(self.ctx.L.lsdgpu_frame_set_perma_ref(self.ctx.ptr, kf_id, C.byref(n)))
+        return n.value
+
+    def checkPermaRefOverlap(self, kf_ids, refToFrame_qts) -> np.ndarray:
+        ids = np.ascontiguousarray(kf_ids, np.int32)
+        q = np.ascontiguousarray(refToFrame_qts, np.float64).reshape(len(ids), 7)
+        out = np.zeros(len(ids), np.float32)
+        self.ctx._ck(self.ctx.L.lsdgpu_perma_overlap_batch(self.ctx.ptr, len(ids), ids.ctypes.data_as(_ip), q.ctypes.data_as(_dp), out.ctypes.data_as(_fp)))
+        return out
+
+    def trackFrameOnPermaref(self, kf_ids, frame_id: int, refToFrame_qts):
+        ids = np.ascontiguousarray(kf_ids, np.int32)
+        q = np.ascontiguousarray(refToFrame_qts, np.float64).reshape(len(ids), 7)
+        res = (TrackResult * len(ids))()
+        self.ctx._ck(self.ctx.L.lsdgpu_perma_track_batch(self.ctx.ptr, len(ids), ids.ctypes.data_as(_ip), frame_id, q.ctypes.data_as(_dp), res))
+        return list(res)
 
     def eval(self, kf_id: int, frame_id: int, level: int, refToFrame_qt, a=1.0, b=0.0, write_mask=False) -> EvalResult:
         q = np.ascontiguousarray(refToFrame_qt, np.float32)

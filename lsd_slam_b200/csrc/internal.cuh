@@ -42,6 +42,9 @@ struct FrameSlot {
     float* idepth[LSD_LEVELS];
     float* idepthVar[LSD_LEVELS];
     uint8_t* goodMask;
+    float4* permaPC = nullptr;           // permaRef: (x, y, z, colour) per level-4 point (Frame::setPermaRef)
+    float* permaVar = nullptr;
+    int permaNumPts = 0;
     CUtensorMap gradMap[LSD_LEVELS];     // TMA descriptors of grad[l] (float4 texels as 4 x f32), box = tracker window
     bool hasDepth = false, idepthPyrValid = false, hasGoodMask = false;
     bool depthHasBeenUpdatedFlag = false;
@@ -73,6 +76,7 @@ struct RefConst {
     const float* image;           // level 0
     const uint8_t* goodMask;      // refPixelWasGoodNoCreate() or nullptr
 };
+#define LSD_MAX_PERMA_BATCH 4096
 #define LSD_MAX_REFS 16
 #define LSD_MAX_ID_SPAN 64
 struct ObserveParams {
@@ -128,6 +132,8 @@ struct lsdgpu_ctx {
     void* hTrackState = nullptr;         // mapped pinned result block (host view)
     void* dTrackStateMapped = nullptr;   // device view of the same block
     int trackUseTma = 1;
+    void* dPermaItems = nullptr;         // batched permaRef tracking: candidate descriptors / results (device)
+    void* dPermaResults = nullptr;
     int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe

@@ -6,6 +6,7 @@
 #include "track.cuh"
 #include "depth.cuh"
 #include "track_persistent.cuh"
+#include "perma.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -87,7 +88,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
                         + 2 * alignUp(n0 * 4, 256) + alignUp(n0 * 16, 256);              // prop head/next/val
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
-                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + 256 * (size_t)max_frames
+                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256)) * (size_t)max_frames + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024
                      + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
@@ -140,7 +141,13 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     ctx->dEvOut = (float*)take(EV_NCH * 4);
     ctx->dStageU8[0] = (uint8_t*)take(n0);
     ctx->dStageU8[1] = (uint8_t*)take(n0);
-    for (auto& s : ctx->slots) s.dStats = (double*)take(64);
+    for (auto& s : ctx->slots) {
+        s.dStats = (double*)take(64);
+        s.permaPC = (float4*)take((n0 >> 8) * 16);
+        s.permaVar = (float*)take((n0 >> 8) * 4);
+    }
+    ctx->dPermaItems = take(LSD_MAX_PERMA_BATCH * sizeof(PermaItem));
+    ctx->dPermaResults = take(LSD_MAX_PERMA_BATCH * sizeof(PermaResult));
     ctx->dStageF = (float*)take(n0 * 32);
     ctx->dScalars = (double*)take((size_t)maxBlocks * 2 * 8 + 64);
     ctx->dTrackState = take(sizeof(TrackState));
@@ -244,6 +251,7 @@ static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
             fresh.thisToParent[3] = 1; fresh.thisToParent[7] = 1;
             fresh.parentId = -1; fresh.initialTrackedResidual = 0;
             fresh.numFramesTrackedOnThis = fresh.numMappedOnThis = 0;
+            fresh.permaNumPts = 0;
             c = fresh;
             return &c;
         }
@@ -1133,4 +1141,130 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
     r = lsdgpu_depth_update_keyframe(ctx, &frame_id, 1);
     if (r) return r;
     return lsdgpu_frame_clear_good_mask(ctx, frame_id);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// permaRef tracking
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lsdgpu_frame_set_perma_ref(lsdgpu_ctx* ctx, int kf_id, int* num_points_out)
+{   // Frame::setPermaRef -> reference->makePointCloud(QUICK_KF_CHECK_LVL) + copy (Frame.cpp:149-174, TrackingReference.cpp:96-147)
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    int r = ensureIdepthPyramid(ctx, kf);
+    if (r) return r;
+    const LevelCam& c = ctx->cam[QUICK_KF_CHECK_LVL];
+    const int w = c.w, h = c.h, n = w * h;
+    std::vector<float> id(n), var(n), col(n);
+    LSD_CHECK(ctx, cudaMemcpyAsync(id.data(), kf->idepth[QUICK_KF_CHECK_LVL], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaMemcpyAsync(var.data(), kf->idepthVar[QUICK_KF_CHECK_LVL], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaMemcpyAsync(col.data(), kf->image[QUICK_KF_CHECK_LVL], n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<float4> pc;
+    std::vector<float> pv;
+    for (int x = 1; x < w - 1; x++)                    // x outer, y inner: the reference's point order (:128-129)
+        for (int y = 1; y < h - 1; y++) {
+            const int idx = x + y * w;
+            if (var[idx] <= 0 || id[idx] == 0) continue;
+            const float sc = 1.0f / id[idx];
+            pc.push_back(make_float4(sc * (c.fxi * x + c.cxi), sc * (c.fyi * y + c.cyi), sc * 1, col[idx]));
+            pv.push_back(var[idx]);
+        }
+    kf->permaNumPts = (int)pc.size();
+    if (kf->permaNumPts) {
+        LSD_CHECK(ctx, cudaMemcpyAsync(kf->permaPC, pc.data(), pc.size() * 16, cudaMemcpyHostToDevice, ctx->stream));
+        LSD_CHECK(ctx, cudaMemcpyAsync(kf->permaVar, pv.data(), pv.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if (num_points_out) *num_points_out = kf->permaNumPts;
+    return 0;
+}
+
+static int fillPermaItems(lsdgpu_ctx* ctx, int n, const int* kf_ids, const double* qt, std::vector<PermaItem>& items)
+{
+    if (n <= 0 || n > LSD_MAX_PERMA_BATCH) return lsd_fail(ctx, "bad candidate count");
+    items.resize(n);
+    for (int i = 0; i < n; i++) {
+        FrameSlot* kf = findSlot(ctx, kf_ids[i]);
+        if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+        if (kf->permaNumPts <= 0) return lsd_fail(ctx, "keyframe has no permaRef (call lsdgpu_frame_set_perma_ref)");
+        lsd::SE3<double> T;
+        for (int k = 0; k < 4; k++) T.q[k] = qt[7 * i + k];
+        for (int k = 0; k < 3; k++) T.t[k] = qt[7 * i + 4 + k];
+        const lsd::SE3<float> Tf = lsd::se3Cast<float>(T);                 // referenceToFrameOrg.cast<float>(), :125,168
+        items[i].pc = kf->permaPC; items[i].var = kf->permaVar; items[i].n = kf->permaNumPts;
+        for (int k = 0; k < 4; k++) items[i].refToFrame[k] = Tf.q[k];
+        for (int k = 0; k < 3; k++) items[i].refToFrame[4 + k] = Tf.t[k];
+    }
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dPermaItems, items.data(), n * sizeof(PermaItem), cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_perma_overlap_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, const double* refToFrame_qt, float* usage_out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    std::vector<PermaItem> items;
+    int r = fillPermaItems(ctx, n, kf_ids, refToFrame_qt, items);
+    if (r) return r;
+    const LevelCam& c = ctx->cam[QUICK_KF_CHECK_LVL];
+    float* dUsage = (float*)ctx->dPermaResults;
+    k_perma_overlap<<<n, 128, 0, ctx->stream>>>((const PermaItem*)ctx->dPermaItems, c.fx, c.fy, c.cx, c.cy, c.w - 1, c.h - 1, dUsage);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(usage_out, dUsage, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, int frame_id, const double* refToFrame_init_qt,
+                                        lsdgpu_track_result* results)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* fr = findSlot(ctx, frame_id);
+    if (!fr) return lsd_fail(ctx, "unknown frame id");
+    std::vector<PermaItem> items;
+    int r = fillPermaItems(ctx, n, kf_ids, refToFrame_init_qt, items);
+    if (r) return r;
+    TrackParams P;
+    memset(&P, 0, sizeof(P));
+    const LevelCam& c = ctx->cam[QUICK_KF_CHECK_LVL];
+    TrackLevelParams& L = P.lvl[QUICK_KF_CHECK_LVL];
+    L.frameGrad = fr->grad[QUICK_KF_CHECK_LVL];
+    L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
+    L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+    P.W = ctx->w; P.H = ctx->h;
+    lsdgpu_track_settings st;
+    lsdgpu_default_track_settings(&st);
+    // TestTrack settings (util/settings.h:379-382) mapped onto level 4
+    st.lambdaInitial[QUICK_KF_CHECK_LVL] = 0; st.stepSizeMin[QUICK_KF_CHECK_LVL] = 1e-3f;
+    st.convergenceEps[QUICK_KF_CHECK_LVL] = 0.98f; st.maxItsPerLvl[QUICK_KF_CHECK_LVL] = 5;
+    P.st = st;
+    P.C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; P.C.var_weight = st.var_weight; P.C.huber_half = st.huber_d / 2;
+    P.useAffine = ctx->g.useAffineLightningEstimation;
+    P.minLevel = QUICK_KF_CHECK_LVL;
+    PermaResult* dRes = (PermaResult*)ctx->dPermaResults;
+    k_perma_track<<<n, PERMA_THREADS, 0, ctx->stream>>>(P, (const PermaItem*)ctx->dPermaItems, dRes);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    std::vector<PermaResult> hres(n);
+    LSD_CHECK(ctx, cudaMemcpyAsync(hres.data(), dRes, n * sizeof(PermaResult), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < n; i++) {
+        lsdgpu_track_result& o = results[i];
+        memset(&o, 0, sizeof(o));
+        const PermaResult& h = hres[i];
+        o.pointUsage = h.pointUsage; o.lastGoodCount = h.goodCount; o.lastBadCount = h.badCount; o.lastMeanRes = h.meanRes;
+        o.affineEstimation_a = h.affine_a; o.affineEstimation_b = h.affine_b;
+        o.numCalcResidualCalls[QUICK_KF_CHECK_LVL] = h.nRes; o.numCalcWarpUpdateCalls[QUICK_KF_CHECK_LVL] = h.nUpd;
+        if (h.diverged) { o.frameToRef_qt[3] = 1; o.diverged = 1; continue; }             // return SE3(), :180-185
+        o.lastResidual = h.lastResidual;                                                // :265
+        o.trackingWasGood = h.goodCount / (c.w * c.h) > 0.04f && h.goodCount / (h.goodCount + h.badCount) > 0.5f;   // :267-269
+        lsd::SE3<float> T;
+        for (int k = 0; k < 4; k++) T.q[k] = h.refToFrame[k];
+        for (int k = 0; k < 3; k++) T.t[k] = h.refToFrame[4 + k];
+        const lsd::SE3<double> Td = lsd::se3Cast<double>(T);                            // toSophus(referenceToFrame), :271
+        for (int k = 0; k < 4; k++) o.frameToRef_qt[k] = Td.q[k];
+        for (int k = 0; k < 3; k++) o.frameToRef_qt[4 + k] = Td.t[k];
+    }
+    return 0;
 }

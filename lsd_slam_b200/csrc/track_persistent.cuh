@@ -51,6 +51,7 @@ struct alignas(64) TrackParams {
     int barrierMode;
     unsigned int barrierBase;        // arrivals counted by earlier launches (the counter is never reset)
     int debug;                       // 1: also write the per-CTA cycle table
+    int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
     int clusterLocalMaxPixels;       // levels up to this size are evaluated per cluster (0: never; needs a cluster launch)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
 };
@@ -546,7 +547,7 @@ __device__ __forceinline__ void lmSolveAndPropose(LMState& lm, LMShared& sh)
 __device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, LMShared& sh)
 {
     lm.lvl--;
-    if (lm.lvl < SE3TRACKING_MIN_LEVEL) { sh.action = ACT_LEVEL_DONE; return; }     // all levels done
+    if (lm.lvl < p.minLevel) { sh.action = ACT_LEVEL_DONE; return; }                // all levels done
     lm.phase = PH_INIT;
     setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
     sh.lvl = lm.lvl;
@@ -753,6 +754,7 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     }
     for (int l = 0; l < LSD_LEVELS; l++) P.gradMap[l] = fr->gradMap[l];
     { const char* tm = getenv("LSDGPU_TRACK_TMA"); P.useTma = tm ? atoi(tm) : 1; }
+    P.minLevel = SE3TRACKING_MIN_LEVEL;
     P.goodMask = fr->goodMask;
     P.maskFresh = fr->hasGoodMask ? 0 : 1;
     P.maskBytes = (ctx->w * ctx->h) / 4;

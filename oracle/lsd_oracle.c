@@ -1081,4 +1081,104 @@ int lsdo_se3_track(lsdo_frame* kf, lsdo_frame* frame, const double frameToRef_in
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * permaRef tracking: Frame::setPermaRef DataStructures/Frame.cpp:149-174,
+ * SE3Tracker::checkPermaRefOverlap Tracking/SE3Tracker.cpp:121-157,
+ * SE3Tracker::trackFrameOnPermaref Tracking/SE3Tracker.cpp:162-272  (QUICK_KF_CHECK_LVL = 4, util/settings.h:104)
+ * ---------------------------------------------------------------------------------------- */
+#define QUICK_KF_CHECK_LVL 4
+int lsdo_frame_setPermaRef(lsdo_frame* kf, float* posData /*3/pt, >= w4*h4*/, float* colorAndVarData /*2/pt*/)
+{
+    return lsdo_make_point_cloud(kf, QUICK_KF_CHECK_LVL, posData, 0, colorAndVarData, 0);
+}
+
+float lsdo_checkPermaRefOverlap(int w0, int h0, const float K4[9], const float* permaPos, int numPts, const double refToFrame_qt[7])
+{
+    float q[7]; se3_d2f(refToFrame_qt, q);
+    int w2 = (w0 >> QUICK_KF_CHECK_LVL)-1, h2 = (h0 >> QUICK_KF_CHECK_LVL)-1;
+    float fx_l = K4[0], fy_l = K4[4], cx_l = K4[2], cy_l = K4[5];
+    float rotMat[9], transVec[3];
+    lsdo_se3f_matrix(q, rotMat, transVec);
+    float usageCount = 0;
+    for (int k = 0; k < numPts; k++) {
+        const float* p = permaPos + 3*k;
+        float Wxp[3];
+        for (int i = 0; i < 3; i++) Wxp[i] = ((rotMat[i*3+0]*p[0] + rotMat[i*3+1]*p[1]) + rotMat[i*3+2]*p[2]) + transVec[i];
+        float u_new = (Wxp[0]/Wxp[2])*fx_l + cx_l;
+        float v_new = (Wxp[1]/Wxp[2])*fy_l + cy_l;
+        if ((u_new > 0 && v_new > 0 && u_new < w2 && v_new < h2)) {
+            float depthChange = p[2] / Wxp[2];
+            usageCount += depthChange < 1 ? depthChange : 1;
+        }
+    }
+    return usageCount / (float)numPts;
+}
+
+/* returns referenceToFrame (NOT inverted, SE3Tracker.cpp:271) in out->frameToRef_qt */
+int lsdo_trackFrameOnPermaref(int w0, int h0, const float* permaPos, const float* permaColVar, int numPts,
+                              lsdo_frame* frame, const double refToFrame_qt[7], lsdo_track_result* out)
+{
+    lsdo_track_settings s; lsdo_default_track_settings(&s);
+    Tracker T; Tracker* t = &T; tracker_init(t, w0, h0, &s);
+    memset(out, 0, sizeof(*out));
+    const float lambdaInitialTestTrack = 0, stepSizeMinTestTrack = 1e-3, convergenceEpsTestTrack = 0.98, maxItsTestTrack = 5;   /* settings.h:379-382 */
+    float referenceToFrame[7]; se3_d2f(refToFrame_qt, referenceToFrame);
+    t->affineEstimation_a = 1; t->affineEstimation_b = 0;
+    LGS6 ls;
+    t->diverged = 0; t->trackingWasGood = 1;
+    const float divTh = MIN_GOODPERALL_PIXEL_ABSMIN * (w0>>QUICK_KF_CHECK_LVL)*(h0>>QUICK_KF_CHECK_LVL);
+    int diverged = 0;
+    calcResidualAndBuffers(t, permaPos, permaColVar, 0, numPts, frame, referenceToFrame, QUICK_KF_CHECK_LVL);
+    float lastErr = 0;
+    if (t->buf_warped_size < divTh) diverged = 1;
+    else {
+        if (G.useAffineLightningEstimation) { t->affineEstimation_a = t->affineEstimation_a_lastIt; t->affineEstimation_b = t->affineEstimation_b_lastIt; }
+        lastErr = calcWeightsAndResidual(t, referenceToFrame);
+        out->numCalcResidualCalls[QUICK_KF_CHECK_LVL]++;
+        float LM_lambda = lambdaInitialTestTrack;
+        for (int iteration = 0; iteration < maxItsTestTrack && !diverged; iteration++) {
+            calculateWarpUpdate(t, &ls);
+            out->numCalcWarpUpdateCalls[QUICK_KF_CHECK_LVL]++;
+            int incTry = 0;
+            while (1) {
+                float b[6], A[36], inc[6];
+                for (int i = 0; i < 6; i++) b[i] = -ls.b[i];
+                memcpy(A, ls.A, sizeof(A));
+                for (int i = 0; i < 6; i++) A[i*6+i] *= 1+LM_lambda;
+                lsdo_ldlt6_solve(A, b, inc);
+                incTry++;
+                float expInc[7], newT[7];
+                lsdo_se3f_exp(inc, expInc);
+                lsdo_se3f_mul(expInc, referenceToFrame, newT);
+                calcResidualAndBuffers(t, permaPos, permaColVar, 0, numPts, frame, newT, QUICK_KF_CHECK_LVL);
+                if (t->buf_warped_size < divTh) { diverged = 1; break; }
+                float error = calcWeightsAndResidual(t, newT);
+                out->numCalcResidualCalls[QUICK_KF_CHECK_LVL]++;
+                if (error < lastErr) {
+                    memcpy(referenceToFrame, newT, sizeof(newT));
+                    if (G.useAffineLightningEstimation) { t->affineEstimation_a = t->affineEstimation_a_lastIt; t->affineEstimation_b = t->affineEstimation_b_lastIt; }
+                    if (error / lastErr > convergenceEpsTestTrack) iteration = maxItsTestTrack;
+                    lastErr = error;
+                    if (LM_lambda <= 0.2) LM_lambda = 0; else LM_lambda *= s.lambdaSuccessFac;
+                    break;
+                } else {
+                    float dot = 0; for (int i = 0; i < 6; i++) dot += inc[i]*inc[i];
+                    if (!(dot > stepSizeMinTestTrack)) { iteration = maxItsTestTrack; break; }
+                    if (LM_lambda == 0) LM_lambda = 0.2; else LM_lambda *= pow(s.lambdaFailFac, incTry);
+                }
+            }
+        }
+    }
+    out->pointUsage = t->pointUsage; out->lastGoodCount = t->lastGoodCount; out->lastBadCount = t->lastBadCount; out->lastMeanRes = t->lastMeanRes;
+    out->affineEstimation_a = t->affineEstimation_a; out->affineEstimation_b = t->affineEstimation_b;
+    if (diverged) { out->frameToRef_qt[3] = 1; out->diverged = 1; out->trackingWasGood = 0; tracker_free(t); return 0; }
+    out->lastResidual = lastErr;
+    out->trackingWasGood = t->lastGoodCount / (frame->width[QUICK_KF_CHECK_LVL]*frame->height[QUICK_KF_CHECK_LVL]) > MIN_GOODPERALL_PIXEL
+        && t->lastGoodCount / (t->lastGoodCount + t->lastBadCount) > MIN_GOODPERGOODBAD_PIXEL;
+    double d[7]; se3_f2d(referenceToFrame, d);
+    memcpy(out->frameToRef_qt, d, sizeof(d));
+    tracker_free(t);
+    return 0;
+}
+
 #include "lsd_oracle_depth.inc"

@@ -158,6 +158,12 @@ int lsdo_se3_eval(lsdo_frame* kf, lsdo_frame* frame, int level, const float refT
 int lsdo_se3_track(lsdo_frame* kf, lsdo_frame* frame, const double frameToRef_init_qt[7],
                    const lsdo_track_settings* s, lsdo_track_result* out);
 
+/* ---- permaRef tracking, SURVEY 8f row 2 (Frame.cpp:149-174, SE3Tracker.cpp:121-272) ---- */
+int   lsdo_frame_setPermaRef(lsdo_frame* kf, float* posData, float* colorAndVarData);      /* returns permaRefNumPts */
+float lsdo_checkPermaRefOverlap(int w0, int h0, const float K4[9], const float* permaPos, int numPts, const double refToFrame_qt[7]);
+int   lsdo_trackFrameOnPermaref(int w0, int h0, const float* permaPos, const float* permaColVar, int numPts,
+                                lsdo_frame* frame, const double refToFrame_qt[7], lsdo_track_result* out /* frameToRef_qt holds referenceToFrame */);
+
 /* ---- DepthMap (DepthEstimation/DepthMap.cpp) ---- */
 lsdo_depthmap* lsdo_depthmap_create(int w, int h, const float K[9]);
 void lsdo_depthmap_destroy(lsdo_depthmap* d);

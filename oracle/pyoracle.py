@@ -123,6 +123,9 @@ def lib(fast: bool = False):
     sig("lsdo_make_point_cloud", C.c_int, vp, C.c_int, fp, fp, fp, ip)
     sig("lsdo_se3_eval", C.c_int, vp, vp, C.c_int, fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult))
     sig("lsdo_se3_track", C.c_int, vp, vp, dp, C.POINTER(TrackSettings), C.POINTER(TrackResult))
+    sig("lsdo_frame_setPermaRef", C.c_int, vp, fp, fp)
+    sig("lsdo_checkPermaRefOverlap", C.c_float, C.c_int, C.c_int, fp, fp, C.c_int, dp)
+    sig("lsdo_trackFrameOnPermaref", C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, vp, dp, C.POINTER(TrackResult))
     sig("lsdo_depthmap_create", vp, C.c_int, C.c_int, fp)
     sig("lsdo_depthmap_destroy", None, vp)
     sig("lsdo_depthmap_reset", None, vp)
@@ -247,6 +250,30 @@ class Frame:
         idx = np.zeros(n, np.int32)
         m = self.L.lsdo_make_point_cloud(self.ptr, level, _fp(pos), _fp(grad), _fp(cv), idx.ctypes.data_as(C.POINTER(C.c_int)))
         return pos[:m], grad[:m], cv[:m], idx[:m]
+
+
+class PermaRef:
+    """Frame::setPermaRef snapshot of a keyframe's level-4 point cloud (Frame.cpp:149-174)"""
+
+    def __init__(self, kf: Frame):
+        w, h = kf.size(4)
+        self.w0, self.h0 = kf.w, kf.h
+        self.pos = np.zeros((w * h, 3), np.float32)
+        self.colvar = np.zeros((w * h, 2), np.float32)
+        self.n = kf.L.lsdo_frame_setPermaRef(kf.ptr, _fp(self.pos), _fp(self.colvar))
+        self.K4 = kf.K(4)[0].copy()
+        self.L = kf.L
+
+    def overlap(self, refToFrame_qt) -> float:
+        q = np.ascontiguousarray(refToFrame_qt, np.float64)
+        K4 = np.ascontiguousarray(self.K4, np.float32).reshape(9)
+        return float(self.L.lsdo_checkPermaRefOverlap(self.w0, self.h0, _fp(K4), _fp(self.pos), self.n, _dp(q)))
+
+    def track(self, frame: Frame, refToFrame_qt) -> TrackResult:
+        q = np.ascontiguousarray(refToFrame_qt, np.float64)
+        r = TrackResult()
+        self.L.lsdo_trackFrameOnPermaref(self.w0, self.h0, _fp(self.pos), _fp(self.colvar), self.n, frame.ptr, _dp(q), C.byref(r))
+        return r
 
 
 def se3_track(kf: Frame, frame: Frame, init_frameToRef_qt, settings: TrackSettings | None = None) -> TrackResult:
