@@ -666,6 +666,117 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
     }
     finishSumCount(s, c, partials, counter, out);
 }
+// regularizeDepthMapFillHoles (DepthMap.cpp:656-718) immediately followed by regularizeDepthMap(false, TH)
+// (:758-880) -- the pair that updateKeyframe (:1135-1143), createKeyFrame (:1270-1277) and finalizeKeyFrame
+// (:1373-1379) always run back to back -- as ONE kernel.  A CTA produces a 32x8 tile: stage 1 stages the 40x16 source
+// neighbourhood in shared memory, stage 2 evaluates fill-holes on the 36x12 region the regulariser will look at,
+// stage 3 regularises the tile.  Per-pixel arithmetic and its order are those of the two separate kernels, so the
+// result is bit-identical to running them one after the other; it saves a launch and one round trip of the
+// 9.8 MB hypothesis planes.
+__global__ void __launch_bounds__(256) k_fill_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
+                                                         const float* __restrict__ kfMaxGrad, int validityTH,
+                                                         const int* __restrict__ skip)
+{
+    __shared__ float4 sA[16][40];        // source:      (idepth, idepth_var, validity_counter, isValid)
+    __shared__ float4 sB[12][36];        // after fill:  same fields
+    __shared__ unsigned char sCreated[12][36];
+    if (skip && *skip) return;
+    const int width = cam.w, height = cam.h;
+    const int ax0 = blockIdx.x * 32 - 4, ay0 = blockIdx.y * 8 - 4;
+    for (int t = threadIdx.x; t < 16 * 40; t += 256) {
+        const int lx = t % 40, ly = t / 40;
+        const int gx = ax0 + lx, gy = ay0 + ly;
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
+            const int4 si = src.hi[gx + gy * width];
+            if (si.x) {
+                const float4 sf = src.hf[gx + gy * width];
+                e = make_float4(sf.x, sf.y, __int_as_float(si.z), __int_as_float(1));
+            }
+        }
+        sA[ly][lx] = e;
+    }
+    __syncthreads();
+    // stage 2: fill holes on the 36x12 region (tile + 2)
+    for (int t = threadIdx.x; t < 12 * 36; t += 256) {
+        const int lx = t % 36, ly = t / 36;
+        const int gx = ax0 + 2 + lx, gy = ay0 + 2 + ly;
+        float4 e = sA[ly + 2][lx + 2];
+        unsigned char created = 0;
+        if (gx >= 3 && gx < width - 2 && gy >= 3 && gy < height - 2 && !__float_as_int(e.w)) {
+            const int idx = gx + gy * width;
+            if (!(kfMaxGrad[idx] < G.minUseGrad)) {
+                int val = 0;
+                for (int dy = -2; dy <= 2; dy++)
+                    for (int dx = -2; dx <= 2; dx++) {
+                        const float4 q = sA[ly + 2 + dy][lx + 2 + dx];
+                        if (__float_as_int(q.w)) val += __float_as_int(q.z);
+                    }
+                const int blacklisted = src.hi[idx].y;
+                if ((blacklisted >= MIN_BLACKLIST && val > VAL_SUM_MIN_FOR_CREATE) || val > VAL_SUM_MIN_FOR_UNBLACKLIST) {
+                    float sumIdepthObs = 0, sumIVarObs = 0;
+                    for (int dy = -2; dy <= 2; dy++)         // row-major source order, :679-688
+                        for (int dx = -2; dx <= 2; dx++) {
+                            const float4 q = sA[ly + 2 + dy][lx + 2 + dx];
+                            if (!__float_as_int(q.w)) continue;
+                            sumIdepthObs += q.x / q.y;
+                            sumIVarObs += 1.0f / q.y;
+                        }
+                    float idepthObs = sumIdepthObs / sumIVarObs;
+                    idepthObs = unzero_f(idepthObs);
+                    e = make_float4(idepthObs, VAR_RANDOM_INIT_INITIAL, __int_as_float(0), __int_as_float(1));
+                    created = 1;
+                }
+            }
+        }
+        sB[ly][lx] = e;
+        sCreated[ly][lx] = created;
+    }
+    __syncthreads();
+    // stage 3: regularizeDepthMapRow<false> on the tile
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
+    if (x >= width || y >= height) return;
+    const int idx = x + y * width;
+    float4 hf;
+    int4 hi;
+    if (sCreated[ty + 2][tx + 2]) {      // fresh DepthMapPixelHypothesis(idepth, var, 0): blacklisted = 0, smoothed = -1
+        const float4 c = sB[ty + 2][tx + 2];
+        hf = make_float4(c.x, c.y, -1.f, -1.f);
+        hi = make_int4(1, 0, 0, __float_as_int(0.f));
+    } else {
+        hf = src.hf[idx];
+        hi = src.hi[idx];
+    }
+    if (x >= 2 && x < width - 2 && y >= 2 && y < height - 2 && hi.x) {
+        const float regDistVar = G.regDistVar;
+        float sum = 0, val_sum = 0, sumIvar = 0;
+        for (int dx = -2; dx <= 2; dx++)                 // dx outer, dy inner as in the reference (:782-783)
+            for (int dy = -2; dy <= 2; dy++) {
+                const float4 q = sB[ty + 2 + dy][tx + 2 + dx];
+                if (!__float_as_int(q.w)) continue;
+                const float diff = q.x - hf.x;
+                if (DIFF_FAC_SMOOTHING * diff * diff > q.y + hf.y) continue;
+                val_sum += __float_as_int(q.z);
+                const float distFac = (float)(dx * dx + dy * dy) * regDistVar;
+                const float ivar = 1.0f / (q.y + distFac);
+                sum += q.x * ivar;
+                sumIvar += ivar;
+            }
+        if (val_sum < validityTH) {
+            hi.x = 0;
+            hi.y--;
+        } else {
+            sum = sum / sumIvar;
+            sum = unzero_f(sum);
+            hf.z = sum;
+            hf.w = 1.0f / sumIvar;
+        }
+    }
+    dst.hf[idx] = hf;
+    dst.hi[idx] = hi;
+}
+
 // Frame::setDepth fused with Frame::buildIDepthAndIDepthVar for levels 1..4 (Frame.cpp:199-243 + :775-877): one CTA =
 // one 16x16 level-0 tile; the tracker imports the new depth right after every update, so the pyramid is always
 // needed and building it here saves a pass over the level-0 planes and a launch.

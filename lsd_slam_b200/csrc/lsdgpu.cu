@@ -776,6 +776,21 @@ static int runRegularize(lsdgpu_ctx* ctx, bool removeOcclusions, int validityTH,
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
 }
+// regularizeDepthMapFillHoles() + regularizeDepthMap(false, TH) as one kernel (see k_fill_regularize)
+static int runFillRegularize(lsdgpu_ctx* ctx, int validityTH, const int* skip = nullptr)
+{
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "no active keyframe");
+    DepthCam cam = depthCam(ctx);
+    DepthGlobals G = depthGlobals(ctx);
+    dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
+    std::swap(ctx->cur, ctx->oth);
+    k_fill_regularize<<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
 static int runFillHoles(lsdgpu_ctx* ctx, const int* skip = nullptr)
 {
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
@@ -973,9 +988,7 @@ extern "C" int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids,
     if (!kf) return lsd_fail(ctx, "updateKeyframe: depth map is not valid (no active keyframe)");
     int r = runObserve(ctx, ref_ids, n_refs);                      // :1127
     if (r) return r;
-    r = runFillHoles(ctx);                                         // :1135
-    if (r) return r;
-    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);           // :1143
+    r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP);              // :1135 + :1143
     if (r) return r;
     if (!kf->depthHasBeenUpdatedFlag) {                            // :1150-1157
         r = setDepthOnKeyframe(ctx, kf);
@@ -1041,9 +1054,7 @@ extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, doub
     ctx->activeKf = new_kf_id; ctx->activeKfReactivated = false;   // :1255-1258
     r = runRegularize(ctx, true, VAL_SUM_MIN_FOR_KEEP);            // :1263
     if (r) return r;
-    r = runFillHoles(ctx);                                         // :1270
-    if (r) return r;
-    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);           // :1277
+    r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP);              // :1270 + :1277
     if (r) return r;
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
@@ -1068,9 +1079,7 @@ extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "finalizeKeyFrame: depth map is not valid");
-    int r = runFillHoles(ctx);
-    if (r) return r;
-    r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);
+    int r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP);          // :1373 + :1379
     if (r) return r;
     return setDepthOnKeyframe(ctx, kf);
 }
@@ -1109,16 +1118,15 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
         LAUNCH(ctx);
         r = runObserve(ctx, &frame_id, 1, true, ctx->dSkipFlag);          // DepthMap.cpp:1127
         if (r) return r;
-        r = runFillHoles(ctx, ctx->dSkipFlag);                            // :1135
-        if (r) return r;
-        r = runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP, ctx->dSkipFlag);   // :1143
+        r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, ctx->dSkipFlag);    // :1135 + :1143
         if (r) return r;
         const bool didSetDepth = !kf->depthHasBeenUpdatedFlag;            // :1150-1157
         const bool prevPending = kf->statsPending, prevPyr = kf->idepthPyrValid;
         if (didSetDepth) { r = setDepthOnKeyframe(ctx, kf, ctx->dSkipFlag); if (r) return r; }
         r = trackPersistentFinish(ctx, fr, out);                          // the one synchronisation of the frame
         if (r) return r;
-        if (out->diverged) {                 // nothing ran on the device: undo the host-side bookkeeping of setDepth
+        if (out->diverged) {                 // nothing ran on the device: undo the host-side bookkeeping
+            std::swap(ctx->cur, ctx->oth);   // the (skipped) fill+regularise kernel had swapped the ping-pong buffers once
             if (didSetDepth) { kf->depthHasBeenUpdatedFlag = false; kf->statsPending = prevPending; kf->idepthPyrValid = prevPyr; }
             return 0;
         }
