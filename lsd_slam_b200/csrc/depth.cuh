@@ -377,59 +377,67 @@ __device__ __forceinline__ bool makeAndCheckEPL(const DepthCam& cam, const float
     return true;
 }
 
-// observeDepthRow + Create + Update, DepthMap.cpp:111-146, 237-292, 294-473.  In place on `cur`: every
-// pixel touches only its own record.
-__global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, DepthGlobals G,
-                                                 const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
-                                                 const float* __restrict__ kfMaxGrad, const __grid_constant__ ObserveParams OPv,
-                                                 const ObserveParams* __restrict__ OPdev, const int* __restrict__ skip)
-{
-    if (skip && *skip) return;                       // this frame's tracking diverged: no mapping (SlamSystem.cpp:948-967)
-    const ObserveParams* OP = OPdev ? OPdev : &OPv;
-    const int x = 3 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = 3 + blockIdx.y;
-    if (x >= cam.w - 3 || y >= cam.h - 3) return;
-    const int idx = x + y * cam.w;
+// observeDepthRow + Create + Update, DepthMap.cpp:111-146, 237-292, 294-473.  In place on `cur`: every pixel touches
+// only its own record.
+//
+// The work is sparse and very uneven (about 40 % of the pixels pass the gates, and the line search runs 5-40 steps), so a
+// CTA first runs the cheap gates for its 2048 pixels (4 per thread, coalesced), collects the survivors in a shared-memory
+// list, and then walks that list densely: warps stay full during the expensive doLineStereo part.  The per-pixel
+// arithmetic is untouched (the list order does not matter: pixels are independent).
+#define OBS_THREADS 512
+#define OBS_PIX_PER_CTA 2048          // 640x480: 147 CTAs = one wave of 1 CTA per SM on 148 SMs
 
+// gates of observeDepthRow (:124-132) and of observeDepthCreate / Update up to and including makeAndCheckEPL
+// (:241-256, :300-333).  Returns the reference index (>= 0) if the pixel must run the line search, -1 otherwise.
+__device__ __forceinline__ int observeGate(const HypField& cur, const DepthCam& cam, const DepthGlobals& G,
+                                           const float* __restrict__ kfImage, const float* __restrict__ kfMaxGrad,
+                                           const ObserveParams* __restrict__ OP, int x, int y, int idx, float& epx, float& epy)
+{
     int4 hiv = cur.hi[idx];
     const bool hasHypothesis = hiv.x != 0;
     const float mg = kfMaxGrad[idx];
     if (hasHypothesis && mg < G.minUseGrad) {              // :125-129
         hiv.x = 0;
         cur.hi[idx] = hiv;
-        return;
+        return -1;
     }
-    if (mg < G.minUseGrad || hiv.y < MIN_BLACKLIST) return;   // :131-132
-
-    Hyp t = loadHyp(cur, idx);
+    if (mg < G.minUseGrad || hiv.y < MIN_BLACKLIST) return -1;   // :131-132
     int refIdx;
     if (!hasHypothesis) {
         refIdx = OP->reactivated ? OP->newestIdx : OP->oldestIdx;                 // :241
     } else {
         if (!OP->reactivated) {                                                   // :300-317
-            int rel = (int)t.nextStereoFrameMinID - OP->byIdOffset;
-            if (rel >= OP->byIdSize) return;
+            const int rel = (int)__int_as_float(hiv.w) - OP->byIdOffset;
+            if (rel >= OP->byIdSize) return -1;
             refIdx = rel < 0 ? OP->oldestIdx : OP->byId[rel];
         } else
             refIdx = OP->newestIdx;
     }
     const RefConst& ref = OP->refs[refIdx];
-
     if (ref.trackedOnActive && ref.goodMask != nullptr &&
         !ref.goodMask[(x >> SE3TRACKING_MIN_LEVEL) + (cam.w >> SE3TRACKING_MIN_LEVEL) * (y >> SE3TRACKING_MIN_LEVEL)])
-        return;                                                                    // :243-252 / :320-329
+        return -1;                                                                 // :243-252 / :320-329
+    if (!makeAndCheckEPL(cam, kfImage, x, y, ref, epx, epy)) return -1;
+    return refIdx;
+}
 
-    float epx, epy;
-    if (!makeAndCheckEPL(cam, kfImage, x, y, ref, epx, epy)) return;
-
+// line search + hypothesis create / EKF update for one surviving pixel (:254-291, :335-472)
+__device__ __forceinline__ void observeStereo(const HypField& cur, const DepthCam& cam, const DepthGlobals& G,
+                                              const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
+                                              const float* __restrict__ kfMaxGrad, const ObserveParams* __restrict__ OP,
+                                              int x, int y, int idx, int refIdx, float epx, float epy)
+{
+    const RefConst& ref = OP->refs[refIdx];
+    Hyp t = loadHyp(cur, idx);
+    const bool hasHypothesis = t.isValid != 0;
     float result_idepth = 0, result_var = 0, result_eplLength = 0;
     if (!hasHypothesis) {
         // observeDepthCreate :254-291
         float error = doLineStereo(cam, G, kfImage, kfGrad, (float)x, (float)y, epx, epy, 0.0f, 1.0f, 1.0f / MIN_DEPTH,
                                    ref, result_idepth, result_var, result_eplLength);
         if (error == -3 || error == -2) {
-            t.blacklisted--;
-            hiv.y = t.blacklisted;
+            int4 hiv = cur.hi[idx];
+            hiv.y = t.blacklisted - 1;
             cur.hi[idx] = hiv;
         }
         if (error < 0 || result_var > MAX_VAR) return;
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, Dep
         id_var = id_var * w;
         if (id_var < t.idepth_var) t.idepth_var = id_var;
         t.validity_counter += VALIDITY_COUNTER_INC;
-        float absGrad = mg;
+        float absGrad = kfMaxGrad[idx];
         if (t.validity_counter > VALIDITY_COUNTER_MAX + absGrad * (VALIDITY_COUNTER_MAX_VARIABLE) / 255.0f)
             t.validity_counter = VALIDITY_COUNTER_MAX + absGrad * (VALIDITY_COUNTER_MAX_VARIABLE) / 255.0f;
         if (result_eplLength < MIN_EPL_LENGTH_CROP) {
@@ -485,6 +493,43 @@ __global__ void __launch_bounds__(128) k_observe(HypField cur, DepthCam cam, Dep
             t.nextStereoFrameMinID = ref.id + inc;
         }
         storeHyp(cur, idx, t);
+    }
+}
+
+__global__ void __launch_bounds__(OBS_THREADS) k_observe(HypField cur, DepthCam cam, DepthGlobals G,
+                                                 const float* __restrict__ kfImage, const float4* __restrict__ kfGrad,
+                                                 const float* __restrict__ kfMaxGrad, const __grid_constant__ ObserveParams OPv,
+                                                 const ObserveParams* __restrict__ OPdev, const int* __restrict__ skip)
+{
+    __shared__ int sList[OBS_PIX_PER_CTA];
+    __shared__ int sCount;
+    if (skip && *skip) return;                       // this frame's tracking diverged: no mapping (SlamSystem.cpp:948-967)
+    const ObserveParams* OP = OPdev ? OPdev : &OPv;
+    const int iw = cam.w - 6, ih = cam.h - 6;        // x in [3, w-3), y in [3, h-3)  (:118, :150)
+    const int nInterior = iw * ih;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    const int base = blockIdx.x * OBS_PIX_PER_CTA;
+#pragma unroll
+    for (int k = 0; k < OBS_PIX_PER_CTA / OBS_THREADS; k++) {
+        const int j = base + k * OBS_THREADS + threadIdx.x;
+        if (j < nInterior) {
+            const int x = 3 + j % iw, y = 3 + j / iw;
+            const int idx = x + y * cam.w;
+            float epx, epy;
+            const int refIdx = observeGate(cur, cam, G, kfImage, kfMaxGrad, OP, x, y, idx, epx, epy);
+            if (refIdx >= 0) sList[atomicAdd(&sCount, 1)] = idx;
+        }
+    }
+    __syncthreads();
+    const int n = sCount;
+    for (int e = threadIdx.x; e < n; e += OBS_THREADS) {
+        const int idx = sList[e];
+        const int x = idx % cam.w, y = idx / cam.w;
+        float epx, epy;
+        // the gates are re-evaluated (cheap, same inputs: nothing this pixel reads has been written in between)
+        const int refIdx = observeGate(cur, cam, G, kfImage, kfMaxGrad, OP, x, y, idx, epx, epy);
+        if (refIdx >= 0) observeStereo(cur, cam, G, kfImage, kfGrad, kfMaxGrad, OP, x, y, idx, refIdx, epx, epy);
     }
 }
 

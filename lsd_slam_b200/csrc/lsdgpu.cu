@@ -958,8 +958,8 @@ static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devP
     }
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
-    dim3 grid(divUp(cam.w - 6, 128), cam.h - 6);
-    k_observe<<<grid, 128, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs, devParams ? ctx->dObs : nullptr, skip);
+    const int grid = divUp((cam.w - 6) * (cam.h - 6), OBS_PIX_PER_CTA);
+    k_observe<<<grid, OBS_THREADS, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs, devParams ? ctx->dObs : nullptr, skip);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
