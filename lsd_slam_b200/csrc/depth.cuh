@@ -650,9 +650,10 @@ __global__ void __launch_bounds__(256) k_regularize(HypField src, HypField dst, 
 __device__ __forceinline__ void finishSumCount(double s, int c, double* __restrict__ partials, unsigned int* counter,
                                                double* __restrict__ out)
 {
-    __shared__ double ssum[8];
-    __shared__ double scnt[8];
+    __shared__ double ssum[16];
+    __shared__ double scnt[16];
     __shared__ bool isLast;
+    const int nWarps = blockDim.x >> 5;
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -661,7 +662,7 @@ __device__ __forceinline__ void finishSumCount(double s, int c, double* __restri
     __syncthreads();
     if (threadIdx.x == 0) {
         double t = 0, tc = 0;
-        for (int k = 0; k < 8; k++) { t += ssum[k]; tc += scnt[k]; }
+        for (int k = 0; k < nWarps; k++) { t += ssum[k]; tc += scnt[k]; }
         __stcg(partials + 2 * blockIdx.x, t);
         __stcg(partials + 2 * blockIdx.x + 1, tc);
         __threadfence();
@@ -682,7 +683,7 @@ __device__ __forceinline__ void finishSumCount(double s, int c, double* __restri
     __syncthreads();
     if (threadIdx.x == 0) {
         double S = 0, Cn = 0;
-        for (int k = 0; k < 8; k++) { S += ssum[k]; Cn += scnt[k]; }
+        for (int k = 0; k < nWarps; k++) { S += ssum[k]; Cn += scnt[k]; }
         out[0] = S; out[1] = Cn;
         out[2] = (double)((float)Cn / (float)S);
         *counter = 0;
@@ -713,23 +714,33 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
 }
 // regularizeDepthMapFillHoles (DepthMap.cpp:656-718) immediately followed by regularizeDepthMap(false, TH)
 // (:758-880) -- the pair that updateKeyframe (:1135-1143), createKeyFrame (:1270-1277) and finalizeKeyFrame
-// (:1373-1379) always run back to back -- as ONE kernel.  A CTA produces a 32x8 tile: stage 1 stages the 40x16 source
-// neighbourhood in shared memory, stage 2 evaluates fill-holes on the 36x12 region the regulariser will look at,
-// stage 3 regularises the tile.  Per-pixel arithmetic and its order are those of the two separate kernels, so the
-// result is bit-identical to running them one after the other; it saves a launch and one round trip of the
-// 9.8 MB hypothesis planes.
-__global__ void __launch_bounds__(256) k_fill_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
-                                                         const float* __restrict__ kfMaxGrad, int validityTH,
-                                                         const int* __restrict__ skip)
+// (:1373-1379) always run back to back -- as ONE kernel, optionally (SETDEPTH) followed in the same kernel by
+// Frame::setDepth + Frame::buildIDepthAndIDepthVar (Frame.cpp:199-243, 775-877; updateKeyframe :1150-1157,
+// finalizeKeyFrame :1385).  A CTA produces a 32x16 tile: stage 1 stages the 40x24 source neighbourhood in shared
+// memory, stage 2 evaluates fill-holes on the 36x20 region the regulariser will look at, stage 3 regularises the tile,
+// stage 4 exports idepth / idepthVar of the tile and its 16x8, 8x4, 4x2, 2x1 pyramid blocks and the ordered
+// sum / count.  Per-pixel arithmetic and its order are those of the separate kernels, so the result is bit-identical to
+// running them one after the other; it saves two launches and two round trips of the 9.8 MB hypothesis planes.
+#define FR_TW 32
+#define FR_TH 16
+#define FR_THREADS (FR_TW * FR_TH)
+template <bool SETDEPTH>
+__global__ void __launch_bounds__(FR_THREADS) k_fill_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
+                                                                const float* __restrict__ kfMaxGrad, int validityTH,
+                                                                const int* __restrict__ skip,
+                                                                PyrPtrs id, PyrPtrs var, double* __restrict__ partials,
+                                                                unsigned int* counter, double* __restrict__ statsOut)
 {
-    __shared__ float4 sA[16][40];        // source:      (idepth, idepth_var, validity_counter, isValid)
-    __shared__ float4 sB[12][36];        // after fill:  same fields
-    __shared__ unsigned char sCreated[12][36];
+    __shared__ float4 sA[FR_TH + 8][FR_TW + 8];      // source:      (idepth, idepth_var, validity_counter, isValid)
+    __shared__ float4 sB[FR_TH + 4][FR_TW + 4];      // after fill:  same fields
+    __shared__ unsigned char sCreated[FR_TH + 4][FR_TW + 4];
     if (skip && *skip) return;
     const int width = cam.w, height = cam.h;
-    const int ax0 = blockIdx.x * 32 - 4, ay0 = blockIdx.y * 8 - 4;
-    for (int t = threadIdx.x; t < 16 * 40; t += 256) {
-        const int lx = t % 40, ly = t / 40;
+    const int tilesX = (width + FR_TW - 1) / FR_TW;
+    const int bx = blockIdx.x % tilesX, by = blockIdx.x / tilesX;
+    const int ax0 = bx * FR_TW - 4, ay0 = by * FR_TH - 4;
+    for (int t = threadIdx.x; t < (FR_TH + 8) * (FR_TW + 8); t += FR_THREADS) {
+        const int lx = t % (FR_TW + 8), ly = t / (FR_TW + 8);
         const int gx = ax0 + lx, gy = ay0 + ly;
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gx >= 0 && gx < width && gy >= 0 && gy < height) {
@@ -742,9 +753,9 @@ __global__ void __launch_bounds__(256) k_fill_regularize(HypField src, HypField 
         sA[ly][lx] = e;
     }
     __syncthreads();
-    // stage 2: fill holes on the 36x12 region (tile + 2)
-    for (int t = threadIdx.x; t < 12 * 36; t += 256) {
-        const int lx = t % 36, ly = t / 36;
+    // stage 2: fill holes on the region the regulariser reads (tile + 2)
+    for (int t = threadIdx.x; t < (FR_TH + 4) * (FR_TW + 4); t += FR_THREADS) {
+        const int lx = t % (FR_TW + 4), ly = t / (FR_TW + 4);
         const int gx = ax0 + 2 + lx, gy = ay0 + 2 + ly;
         float4 e = sA[ly + 2][lx + 2];
         unsigned char created = 0;
@@ -779,47 +790,97 @@ __global__ void __launch_bounds__(256) k_fill_regularize(HypField src, HypField 
     }
     __syncthreads();
     // stage 3: regularizeDepthMapRow<false> on the tile
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int x = blockIdx.x * 32 + tx, y = blockIdx.y * 8 + ty;
-    if (x >= width || y >= height) return;
+    const int tx = threadIdx.x % FR_TW, ty = threadIdx.x / FR_TW;
+    const int x = bx * FR_TW + tx, y = by * FR_TH + ty;
+    const bool inside = x < width && y < height;
     const int idx = x + y * width;
-    float4 hf;
-    int4 hi;
-    if (sCreated[ty + 2][tx + 2]) {      // fresh DepthMapPixelHypothesis(idepth, var, 0): blacklisted = 0, smoothed = -1
-        const float4 c = sB[ty + 2][tx + 2];
-        hf = make_float4(c.x, c.y, -1.f, -1.f);
-        hi = make_int4(1, 0, 0, __float_as_int(0.f));
-    } else {
-        hf = src.hf[idx];
-        hi = src.hi[idx];
-    }
-    if (x >= 2 && x < width - 2 && y >= 2 && y < height - 2 && hi.x) {
-        const float regDistVar = G.regDistVar;
-        float sum = 0, val_sum = 0, sumIvar = 0;
-        for (int dx = -2; dx <= 2; dx++)                 // dx outer, dy inner as in the reference (:782-783)
-            for (int dy = -2; dy <= 2; dy++) {
-                const float4 q = sB[ty + 2 + dy][tx + 2 + dx];
-                if (!__float_as_int(q.w)) continue;
-                const float diff = q.x - hf.x;
-                if (DIFF_FAC_SMOOTHING * diff * diff > q.y + hf.y) continue;
-                val_sum += __float_as_int(q.z);
-                const float distFac = (float)(dx * dx + dy * dy) * regDistVar;
-                const float ivar = 1.0f / (q.y + distFac);
-                sum += q.x * ivar;
-                sumIvar += ivar;
-            }
-        if (val_sum < validityTH) {
-            hi.x = 0;
-            hi.y--;
+    float4 hf = make_float4(0.f, 0.f, 0.f, 0.f);
+    int4 hi = make_int4(0, 0, 0, 0);
+    if (inside) {
+        if (sCreated[ty + 2][tx + 2]) {  // fresh DepthMapPixelHypothesis(idepth, var, 0): blacklisted = 0, smoothed = -1
+            const float4 c = sB[ty + 2][tx + 2];
+            hf = make_float4(c.x, c.y, -1.f, -1.f);
+            hi = make_int4(1, 0, 0, __float_as_int(0.f));
         } else {
-            sum = sum / sumIvar;
-            sum = unzero_f(sum);
-            hf.z = sum;
-            hf.w = 1.0f / sumIvar;
+            hf = src.hf[idx];
+            hi = src.hi[idx];
         }
+        if (x >= 2 && x < width - 2 && y >= 2 && y < height - 2 && hi.x) {
+            const float regDistVar = G.regDistVar;
+            float sum = 0, val_sum = 0, sumIvar = 0;
+            for (int dx = -2; dx <= 2; dx++)             // dx outer, dy inner as in the reference (:782-783)
+                for (int dy = -2; dy <= 2; dy++) {
+                    const float4 q = sB[ty + 2 + dy][tx + 2 + dx];
+                    if (!__float_as_int(q.w)) continue;
+                    const float diff = q.x - hf.x;
+                    if (DIFF_FAC_SMOOTHING * diff * diff > q.y + hf.y) continue;
+                    val_sum += __float_as_int(q.z);
+                    const float distFac = (float)(dx * dx + dy * dy) * regDistVar;
+                    const float ivar = 1.0f / (q.y + distFac);
+                    sum += q.x * ivar;
+                    sumIvar += ivar;
+                }
+            if (val_sum < validityTH) {
+                hi.x = 0;
+                hi.y--;
+            } else {
+                sum = sum / sumIvar;
+                sum = unzero_f(sum);
+                hf.z = sum;
+                hf.w = 1.0f / sumIvar;
+            }
+        }
+        dst.hf[idx] = hf;
+        dst.hi[idx] = hi;
     }
-    dst.hf[idx] = hf;
-    dst.hi[idx] = hi;
+    if (!SETDEPTH) return;
+    // stage 4: Frame::setDepth (Frame.cpp:217-232) + idepth pyramid blocks of this tile + ordered sum / count
+    float2* t0 = reinterpret_cast<float2*>(&sA[0][0]);          // sA is dead: reuse it for the pyramid staging
+    float2* t1 = t0 + FR_TW * FR_TH;
+    float2* t2 = t1 + (FR_TW / 2) * (FR_TH / 2);
+    float2* t3 = t2 + (FR_TW / 4) * (FR_TH / 4);
+    __syncthreads();
+    double ssum = 0.0;
+    int scnt = 0;
+    float2 v = make_float2(-1.f, -1.f);
+    if (inside && hi.x && hf.z >= -0.05) { v = make_float2(hf.z, hf.w); ssum = hf.z; scnt = 1; }
+    if (inside) { id.l[0][idx] = v.x; var.l[0][idx] = v.y; }
+    t0[ty * FR_TW + tx] = v;
+    __syncthreads();
+    if (tx < FR_TW / 2 && ty < FR_TH / 2) {
+        const float2 r = mergeIdepth4(t0[(2 * ty) * FR_TW + 2 * tx], t0[(2 * ty) * FR_TW + 2 * tx + 1],
+                                      t0[(2 * ty + 1) * FR_TW + 2 * tx], t0[(2 * ty + 1) * FR_TW + 2 * tx + 1]);
+        t1[ty * (FR_TW / 2) + tx] = r;
+        const int ox = bx * (FR_TW / 2) + tx, oy = by * (FR_TH / 2) + ty;
+        if (ox < (width >> 1) && oy < (height >> 1)) { id.l[1][oy * (width >> 1) + ox] = r.x; var.l[1][oy * (width >> 1) + ox] = r.y; }
+    }
+    __syncthreads();
+    if (tx < FR_TW / 4 && ty < FR_TH / 4) {
+        const int W1 = FR_TW / 2;
+        const float2 r = mergeIdepth4(t1[(2 * ty) * W1 + 2 * tx], t1[(2 * ty) * W1 + 2 * tx + 1],
+                                      t1[(2 * ty + 1) * W1 + 2 * tx], t1[(2 * ty + 1) * W1 + 2 * tx + 1]);
+        t2[ty * (FR_TW / 4) + tx] = r;
+        const int ox = bx * (FR_TW / 4) + tx, oy = by * (FR_TH / 4) + ty;
+        if (ox < (width >> 2) && oy < (height >> 2)) { id.l[2][oy * (width >> 2) + ox] = r.x; var.l[2][oy * (width >> 2) + ox] = r.y; }
+    }
+    __syncthreads();
+    if (tx < FR_TW / 8 && ty < FR_TH / 8) {
+        const int W2 = FR_TW / 4;
+        const float2 r = mergeIdepth4(t2[(2 * ty) * W2 + 2 * tx], t2[(2 * ty) * W2 + 2 * tx + 1],
+                                      t2[(2 * ty + 1) * W2 + 2 * tx], t2[(2 * ty + 1) * W2 + 2 * tx + 1]);
+        t3[ty * (FR_TW / 8) + tx] = r;
+        const int ox = bx * (FR_TW / 8) + tx, oy = by * (FR_TH / 8) + ty;
+        if (ox < (width >> 3) && oy < (height >> 3)) { id.l[3][oy * (width >> 3) + ox] = r.x; var.l[3][oy * (width >> 3) + ox] = r.y; }
+    }
+    __syncthreads();
+    if (tx < FR_TW / 16 && ty < FR_TH / 16) {
+        const int W3 = FR_TW / 8;
+        const float2 r = mergeIdepth4(t3[(2 * ty) * W3 + 2 * tx], t3[(2 * ty) * W3 + 2 * tx + 1],
+                                      t3[(2 * ty + 1) * W3 + 2 * tx], t3[(2 * ty + 1) * W3 + 2 * tx + 1]);
+        const int ox = bx * (FR_TW / 16) + tx, oy = by * (FR_TH / 16) + ty;
+        if (ox < (width >> 4) && oy < (height >> 4)) { id.l[4][oy * (width >> 4) + ox] = r.x; var.l[4][oy * (width >> 4) + ox] = r.y; }
+    }
+    finishSumCount(ssum, scnt, partials, counter, statsOut);
 }
 
 // Frame::setDepth fused with Frame::buildIDepthAndIDepthVar for levels 1..4 (Frame.cpp:199-243 + :775-877): one CTA =

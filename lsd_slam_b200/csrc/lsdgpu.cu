@@ -776,16 +776,27 @@ static int runRegularize(lsdgpu_ctx* ctx, bool removeOcclusions, int validityTH,
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
 }
-// regularizeDepthMapFillHoles() + regularizeDepthMap(false, TH) as one kernel (see k_fill_regularize)
-static int runFillRegularize(lsdgpu_ctx* ctx, int validityTH, const int* skip = nullptr)
+// regularizeDepthMapFillHoles() + regularizeDepthMap(false, TH) as one kernel (see k_fill_regularize); with
+// setDepthOn != nullptr the kernel also does Frame::setDepth + the idepth pyramid of that keyframe
+static int runFillRegularize(lsdgpu_ctx* ctx, int validityTH, const int* skip = nullptr, FrameSlot* setDepthOn = nullptr)
 {
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "no active keyframe");
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
-    dim3 grid(divUp(cam.w, 32), divUp(cam.h, 8));
+    const int grid = divUp(cam.w, FR_TW) * divUp(cam.h, FR_TH);
     std::swap(ctx->cur, ctx->oth);
-    k_fill_regularize<<<grid, 256, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip);
+    PyrPtrs id, var;
+    for (int l = 0; l < LSD_LEVELS; l++) { id.l[l] = setDepthOn ? setDepthOn->idepth[l] : nullptr; var.l[l] = setDepthOn ? setDepthOn->idepthVar[l] : nullptr; }
+    if (setDepthOn) {
+        k_fill_regularize<true><<<grid, FR_THREADS, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip, id, var,
+                                                                      ctx->dScalars + 8, ctx->evCounter + 48, setDepthOn->dStats);
+        setDepthOn->statsPending = true;
+        setDepthOn->hasDepth = true; setDepthOn->idepthPyrValid = true;
+        setDepthOn->depthHasBeenUpdatedFlag = true;                    // Frame.cpp:242
+    } else
+        k_fill_regularize<false><<<grid, FR_THREADS, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip, id, var,
+                                                                       nullptr, nullptr, nullptr);
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -988,12 +999,9 @@ extern "C" int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids,
     if (!kf) return lsd_fail(ctx, "updateKeyframe: depth map is not valid (no active keyframe)");
     int r = runObserve(ctx, ref_ids, n_refs);                      // :1127
     if (r) return r;
-    r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP);              // :1135 + :1143
+    r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr,      // :1135 + :1143 (+ setDepth :1150-1157 in the same kernel)
+                          kf->depthHasBeenUpdatedFlag ? nullptr : kf);
     if (r) return r;
-    if (!kf->depthHasBeenUpdatedFlag) {                            // :1150-1157
-        r = setDepthOnKeyframe(ctx, kf);
-        if (r) return r;
-    }
     kf->numMappedOnThis++;                                         // :1165
     return 0;
 }
@@ -1079,9 +1087,7 @@ extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "finalizeKeyFrame: depth map is not valid");
-    int r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP);          // :1373 + :1379
-    if (r) return r;
-    return setDepthOnKeyframe(ctx, kf);
+    return runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr, kf);   // :1373 + :1379 + setDepth :1385
 }
 
 extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t* gray, int stage_index,
@@ -1118,11 +1124,10 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
         LAUNCH(ctx);
         r = runObserve(ctx, &frame_id, 1, true, ctx->dSkipFlag);          // DepthMap.cpp:1127
         if (r) return r;
-        r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, ctx->dSkipFlag);    // :1135 + :1143
-        if (r) return r;
         const bool didSetDepth = !kf->depthHasBeenUpdatedFlag;            // :1150-1157
         const bool prevPending = kf->statsPending, prevPyr = kf->idepthPyrValid;
-        if (didSetDepth) { r = setDepthOnKeyframe(ctx, kf, ctx->dSkipFlag); if (r) return r; }
+        r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, ctx->dSkipFlag, didSetDepth ? kf : nullptr);    // :1135 + :1143 (+ setDepth)
+        if (r) return r;
         r = trackPersistentFinish(ctx, fr, out);                          // the one synchronisation of the frame
         if (r) return r;
         if (out->diverged) {                 // nothing ran on the device: undo the host-side bookkeeping
