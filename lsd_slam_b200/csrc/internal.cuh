@@ -137,6 +137,7 @@ struct lsdgpu_ctx {
     int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
+    unsigned int trackSeq = 0;           // sequence number of the last tracking launch (TrackState::doneSeq)
     unsigned int barrierBase = 0;        // arrivals already counted on evCounter[0] by earlier launches
     uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
     int stageEntries = 0;
@@ -154,6 +155,7 @@ struct lsdgpu_ctx {
     long long trackKernelLaunches = 0;
     double trackKernelBytes = 0;
     bool profileTrackKernel = false;
+    bool trackProfilePending = false;
     void* encodeTiled = nullptr;         // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
 };
 

@@ -223,8 +223,10 @@ extern "C" int lsdgpu_timer_elapsed_ms(lsdgpu_ctx* ctx, int slot, float* ms)
     LSD_CHECK(ctx, cudaEventElapsedTime(ms, ctx->tBegin[slot], ctx->tEnd[slot]));
     return 0;
 }
+static void flushTrackProfile(lsdgpu_ctx* ctx);
 extern "C" int lsdgpu_track_kernel_stats(lsdgpu_ctx* ctx, int reset, double* ms, long long* launches, double* bytes)
 {
+    flushTrackProfile(ctx);
     if (ms) *ms = ctx->trackKernelMs;
     if (launches) *launches = ctx->trackKernelLaunches;
     if (bytes) *bytes = ctx->trackKernelBytes;

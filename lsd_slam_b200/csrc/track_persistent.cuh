@@ -51,6 +51,7 @@ struct alignas(64) TrackParams {
     int barrierMode;
     unsigned int barrierBase;        // arrivals counted by earlier launches (the counter is never reset)
     int debug;                       // 1: also write the per-CTA cycle table
+    unsigned int launchSeq;          // value the kernel stores in TrackState::doneSeq when the result block is complete
     int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
     int clusterLocalMaxPixels;       // levels up to this size are evaluated per cluster (0: never; needs a cluster launch)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
@@ -65,6 +66,7 @@ struct TrackState {
     int numCalcResidualCalls[LSD_LEVELS];
     int numCalcWarpUpdateCalls[LSD_LEVELS];
     int totalEvals;
+    volatile unsigned int doneSeq;   // written last (after a system-wide fence): the host polls it instead of a stream sync
     long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
     long long cycBlk[TP_MAXGRID_DBG][6];   // the same per CTA (debug)
 };
@@ -684,6 +686,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
         if (p.debug) for (int i = 0; i < 3; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
+        __threadfence_system();
+        out->doneSeq = p.launchSeq;
     }
 }
 
@@ -739,10 +743,21 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
 
 static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_result* out);
 
+// device time of the last profiled tracking launch (CUDA events on the context's stream), accumulated lazily
+static void flushTrackProfile(lsdgpu_ctx* ctx)
+{
+    if (!ctx->trackProfilePending) return;
+    float ms = 0;
+    cudaEventSynchronize(ctx->kEnd);
+    if (cudaEventElapsedTime(&ms, ctx->kBegin, ctx->kEnd) == cudaSuccess) { ctx->trackKernelMs += ms; ctx->trackKernelLaunches++; }
+    ctx->trackProfilePending = false;
+}
+
 // enqueue the tracking kernel of one frame on the context's stream (no host synchronisation)
 static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
                                   const lsdgpu_track_settings* st)
 {
+    flushTrackProfile(ctx);
     TrackParams P;
     memset(&P, 0, sizeof(P));
     for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++) {
@@ -780,6 +795,7 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     const bool dbg = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
     P.debug = dbg ? 1 : 0;
     P.barrierBase = ctx->barrierBase;
+    P.launchSeq = ++ctx->trackSeq;
     if (dbg) LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter + 40, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
     {
@@ -813,18 +829,25 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
     memset(out, 0, sizeof(*out));
     TrackState* hOut = (TrackState*)ctx->hTrackState;
     const int grid = ctx->trackGrid;
-    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));      // the result block is mapped host memory
+    // The result block lives in mapped pinned memory and its last word is a sequence number: spin on it (a few
+    // hundred ns of latency) instead of a stream synchronisation.  Later launches are stream-ordered anyway.
+    if (getenv("LSDGPU_TRACK_DEBUG")) LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    else {
+        bool done = false;
+        for (long long spin = 0; spin < 200000000LL; spin++) {
+            if (hOut->doneSeq == ctx->trackSeq) { done = true; break; }
+            if ((spin & 0xffff) == 0xffff && cudaStreamQuery(ctx->stream) != cudaErrorNotReady) { done = hOut->doneSeq == ctx->trackSeq; break; }
+        }
+        if (!done) LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
 
-    if (ctx->profileTrackKernel) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ctx->kBegin, ctx->kEnd);
-        ctx->trackKernelMs += ms;
-        ctx->trackKernelLaunches++;
+    if (ctx->profileTrackKernel) {           // the event pair is read lazily (flushTrackProfile): no extra sync on the path
         double bytes = 0;
         for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++)
             bytes += (double)hOut->numCalcResidualCalls[l] * ((double)ctx->cam[l].w * ctx->cam[l].h * (12.0 + 16.0 + (l == 1 ? 1.0 : 0.0)) + EV_NCH * 4.0);
         ctx->trackKernelBytes += bytes;
+        ctx->trackProfilePending = true;
     }
 
     if (getenv("LSDGPU_TRACK_DEBUG")) {
