@@ -219,6 +219,10 @@ struct WarpWindow {
     int ox, oy;                      // window origin in level pixels
     bool valid;
     unsigned int hits;               // low 16 bits: taps served from the window, high 16: taps through L1/L2
+    // the thread's first pixel of the current level, reconstructed once (see gridEvaluate)
+    int pcLvl, pcMode;
+    bool pcIsPoint;
+    float pcx, pcy, pcz, pcVar, pcColor;
 };
 
 enum { EVAL_GRID = 0, EVAL_CTA = 1, EVAL_CLUSTER = 2 };
@@ -257,20 +261,32 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
         const int i = base + laneId;
         const int x = i % w, y = i / w;
         bool isPoint = false;
-        float px = 0.f, py = 0.f, pz = 0.f, var = 0.f;
-        if (i < n && x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
-            const float idepth = __ldg(L.kfIdepth + i);
-            var = __ldg(L.kfVar + i);
-            if (!(var <= 0 || idepth == 0)) {
-                const float sc = 1.0f / idepth;
-                px = sc * (L.fxi * x + L.cxi); py = sc * (L.fyi * y + L.cyi); pz = sc * 1;
-                isPoint = true;
+        float px = 0.f, py = 0.f, pz = 0.f, var = 0.f, color = 0.f;
+        const bool firstChunk = (base == first - laneId);
+        if (firstChunk && W.pcLvl == lvl && W.pcMode == evalMode) {
+            // the thread's first pixel of a level never changes between the evaluations of that level: keep the
+            // reconstructed point in registers instead of re-reading the keyframe planes (an L2 round trip at the head
+            // of every evaluation's dependency chain)
+            isPoint = W.pcIsPoint; px = W.pcx; py = W.pcy; pz = W.pcz; var = W.pcVar; color = W.pcColor;
+        } else {
+            if (i < n && x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+                const float idepth = __ldg(L.kfIdepth + i);
+                var = __ldg(L.kfVar + i);
+                if (!(var <= 0 || idepth == 0)) {
+                    const float sc = 1.0f / idepth;
+                    px = sc * (L.fxi * x + L.cxi); py = sc * (L.fyi * y + L.cyi); pz = sc * 1;
+                    color = __ldg(L.kfColor + i);
+                    isPoint = true;
+                }
+            }
+            if (firstChunk) {
+                W.pcLvl = lvl; W.pcMode = evalMode; W.pcIsPoint = isPoint;
+                W.pcx = px; W.pcy = py; W.pcz = pz; W.pcVar = var; W.pcColor = color;
             }
         }
         // First chunk of this warp on a new level: stage the part of the frame's gradient level that the chunk
         // warps into (centred on the chunk under the level's initial pose) in shared memory with ONE TMA box copy.
         // All later evaluations of the level tap the window; taps that leave it fall back to L1/L2.
-        const bool firstChunk = (base == first - laneId);
         if (p.useTma && !local && firstChunk && W.lvl != lvl) {          // warp-uniform condition
             const int lane = threadIdx.x & 31;
             float u = 0.f, v = 0.f;
@@ -326,7 +342,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
                     interp43(fg, u, v, w, o0, o1, o2);
                 }
             };
-            int good = evalPoint(px, py, pz, __ldg(L.kfColor + i), var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
+            int good = evalPoint(px, py, pz, color, var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
             if (mask) mask[i] = (uint8_t)good;
         }
     }
@@ -621,7 +637,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     WarpWindow W;
     W.win = reinterpret_cast<const float4*>(winSmem) + (size_t)(threadIdx.x >> 5) * (TRK_WIN_W * TRK_WIN_H);
     W.bar = &winBar[threadIdx.x >> 5];
-    W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u;
+    W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u; W.pcLvl = -1; W.pcMode = -1; W.pcIsPoint = false;
+    W.pcx = W.pcy = W.pcz = W.pcVar = W.pcColor = 0.f;
     if (p.useTma && (threadIdx.x & 31) == 0) {
         mbarInit(W.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
