@@ -232,6 +232,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local_rank = rank_world()
+    metric = METRIC if (args.width, args.height) == (640, 480) else METRIC.replace("640x480", f"{args.width}x{args.height}")
     workload = f"synthetic {args.width}x{args.height} grayscale stream, full track+map loop, forced keyframe every {KF_EVERY} frames"
     config = {"workload": workload, "width": args.width, "height": args.height, "pyramid_levels_tracked": "L4..L1",
               "kf_every": KF_EVERY, "streams_per_gpu": 1, "parallelism": f"{world} independent stream(s), one per GPU, no collective",
@@ -245,7 +246,7 @@ def main():
         n_frames = args.warmup + args.steps + 1
         seq, frames = render_frames(args.width, args.height, 1234, n_frames)
         fps, ms, n, threads = cpu_loop(seq, frames, args.steps, args.warmup, time_budget_s=120.0)
-        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
+        line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
@@ -282,7 +283,7 @@ def main():
     except Exception:
         pass
     ach = (r["kbytes"] / max(r["klaunch"], 1)) / (r["kms"] * 1e-3 / max(r["klaunch"], 1)) / 1e9 if r["kms"] > 0 else 0.0
-    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": r["clocks"],
