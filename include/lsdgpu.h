@@ -174,6 +174,39 @@ int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t
                          const double frameToRef_init_qt[7], const lsdgpu_track_settings* s, int mode,
                          int keyframe_change, lsdgpu_track_result* out, double new_kf_thisToParent_qts[8]);
 
+/* ---- Sim3Tracker, batched --------------------------------------------------------------------
+ * Sim3 values cross the ABI as qts[8] = unit quaternion (x,y,z,w), translation, scale (like new_kf_thisToParent_qts).
+ * Everything SlamSystem::tryTrackSim3 (SlamSystem.cpp:1043-1127) reads from the tracker, Tracking/Sim3Tracker.h:66,127-138. */
+typedef struct {
+    double frameToRef_qts[8];          /* identity (Sim3()) on the early returns, Sim3Tracker.cpp:184-187, 212-217, 231-235, 363-367 */
+    float  lastSim3Hessian[49];        /* ls7.A row-major, NOT divided by num_constraints (:360); zero on the early returns */
+    float  lastResidual, lastDepthResidual, lastPhotometricResidual;
+    float  pointUsage;
+    float  affineEstimation_a, affineEstimation_b;
+    int    diverged;
+    int    numCalcResidualCalls[LSDGPU_LEVELS];
+    int    numCalcWarpUpdateCalls[LSDGPU_LEVELS];
+} lsdgpu_sim3_result;
+/* one fused evaluation (calcSim3Buffers :414-607 + calcSim3WeightsAndResidual :748-856 + calcSim3LGS :992-1047): parity hook */
+typedef struct {
+    float A[49], b[7];                 /* LGS7 (LGSX.h:411-443), undivided */
+    int   num_constraints;
+    float sumResD, sumResP; int numTermsD, numTermsP;
+    float mean, meanD, meanP;
+    int   warpedSize;
+    float pointUsage, affine_a_lastIt, affine_b_lastIt;
+} lsdgpu_sim3_eval_result;
+int lsdgpu_sim3_eval(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, int level, const double refToFrame_qts[8],
+                     float affine_a, float affine_b, const lsdgpu_track_settings* s, lsdgpu_sim3_eval_result* out);
+/* Sim3Tracker::trackFrameSim3(reference, frame, frameToReference_initialEstimate, startLevel, finalLevel) :149-382.
+ * Both frames must carry depth (keyframes).  s == NULL: DenseDepthTrackerSettings defaults (util/settings.h:355-386). */
+int lsdgpu_sim3_track(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, const double frameToRef_init_qts[8],
+                      int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* out);
+/* n independent trackings in ONE launch (one thread-block cluster per problem): problem i tracks frame frame_ids[i] on
+ * reference keyframe ref_kf_ids[i] from frameToRef_init_qts[8*i..]; n <= 1024. */
+int lsdgpu_sim3_track_batch(lsdgpu_ctx* ctx, int n, const int* ref_kf_ids, const int* frame_ids, const double* frameToRef_init_qts,
+                            int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* results);
+
 /* ---- permaRef tracking, batched ------------------------------------------------------------
  * Frame::setPermaRef Frame.cpp:149-174: freeze the keyframe's CURRENT level-4 point cloud (positions, colour, variance). */
 int lsdgpu_frame_set_perma_ref(lsdgpu_ctx* ctx, int kf_id, int* num_points_out);

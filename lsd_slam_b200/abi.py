@@ -68,6 +68,21 @@ class EvalResult(C.Structure):
 
 # every symbol include/lsdgpu.h declares: (name, restype, argtypes)
 _vp, _fp, _dp, _ip, _u8p = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint8)
+class Sim3Result(C.Structure):
+    _fields_ = [("frameToRef_qts", C.c_double * 8), ("lastSim3Hessian", C.c_float * 49),
+                ("lastResidual", C.c_float), ("lastDepthResidual", C.c_float), ("lastPhotometricResidual", C.c_float),
+                ("pointUsage", C.c_float), ("affineEstimation_a", C.c_float), ("affineEstimation_b", C.c_float),
+                ("diverged", C.c_int),
+                ("numCalcResidualCalls", C.c_int * LEVELS), ("numCalcWarpUpdateCalls", C.c_int * LEVELS)]
+
+
+class Sim3EvalResult(C.Structure):
+    _fields_ = [("A", C.c_float * 49), ("b", C.c_float * 7), ("num_constraints", C.c_int),
+                ("sumResD", C.c_float), ("sumResP", C.c_float), ("numTermsD", C.c_int), ("numTermsP", C.c_int),
+                ("mean", C.c_float), ("meanD", C.c_float), ("meanP", C.c_float), ("warpedSize", C.c_int),
+                ("pointUsage", C.c_float), ("affine_a_lastIt", C.c_float), ("affine_b_lastIt", C.c_float)]
+
+
 SYMBOLS = [
     ("lsdgpu_create", C.c_int, [C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.POINTER(_vp)]),
     ("lsdgpu_destroy", None, [_vp]),
@@ -100,6 +115,9 @@ SYMBOLS = [
     ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
     ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
     ("lsdgpu_track_and_map", C.c_int, [_vp, C.c_int, C.c_int, _u8p, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.POINTER(TrackResult), _dp]),
+    ("lsdgpu_sim3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.POINTER(Sim3EvalResult)]),
+    ("lsdgpu_sim3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result)]),
+    ("lsdgpu_sim3_track_batch", C.c_int, [_vp, C.c_int, _ip, _ip, _dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result)]),
     ("lsdgpu_frame_set_perma_ref", C.c_int, [_vp, C.c_int, _ip]),
     ("lsdgpu_perma_overlap_batch", C.c_int, [_vp, C.c_int, _ip, _dp, _fp]),
     ("lsdgpu_perma_track_batch", C.c_int, [_vp, C.c_int, _ip, C.c_int, _dp, C.POINTER(TrackResult)]),
@@ -343,6 +361,54 @@ class SE3Tracker:
         self.ctx._ck(self.ctx.L.lsdgpu_se3_eval(self.ctx.ptr, kf_id, frame_id, level, q.ctypes.data_as(_fp), a, b,
                                                 C.byref(self.settings), int(write_mask), C.byref(r)))
         return r
+
+
+class Sim3Tracker:
+    """Mirror of lsd_slam::Sim3Tracker (Tracking/Sim3Tracker.h:59-160); members as the reference names them."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        self.settings = default_track_settings(main_tracker=False)     # DenseDepthTrackerSettings(), Sim3Tracker.cpp:57
+        self.diverged = False
+        self.pointUsage = 0.0
+        self.lastResidual = self.lastDepthResidual = self.lastPhotometricResidual = 0.0
+        self.affineEstimation_a, self.affineEstimation_b = 1.0, 0.0
+        self.lastSim3Hessian = np.zeros((7, 7), np.float32)
+        self.last: Sim3Result | None = None
+
+    def trackFrameSim3(self, reference_kf_id: int, frame_id: int, frameToReference_initialEstimate, startLevel: int, finalLevel: int) -> np.ndarray:
+        """-> frameToReference as qts[8] (unit quaternion, translation, scale)"""
+        q = np.ascontiguousarray(frameToReference_initialEstimate, np.float64)
+        r = Sim3Result()
+        self.ctx._ck(self.ctx.L.lsdgpu_sim3_track(self.ctx.ptr, reference_kf_id, frame_id, q.ctypes.data_as(_dp), startLevel, finalLevel,
+                                                  C.byref(self.settings), C.byref(r)))
+        self._take(r)
+        return np.array(r.frameToRef_qts)
+
+    def trackFrameSim3Batch(self, reference_kf_ids, frame_ids, inits, startLevel: int, finalLevel: int):
+        """n independent trackings in one launch -> list of Sim3Result"""
+        a = np.ascontiguousarray(reference_kf_ids, np.int32)
+        b = np.ascontiguousarray(frame_ids, np.int32)
+        q = np.ascontiguousarray(inits, np.float64).reshape(len(a), 8)
+        res = (Sim3Result * len(a))()
+        self.ctx._ck(self.ctx.L.lsdgpu_sim3_track_batch(self.ctx.ptr, len(a), a.ctypes.data_as(_ip), b.ctypes.data_as(_ip), q.ctypes.data_as(_dp),
+                                                        startLevel, finalLevel, C.byref(self.settings), res))
+        return list(res)
+
+    def eval(self, reference_kf_id: int, frame_id: int, level: int, refToFrame_qts, a=1.0, b=0.0) -> Sim3EvalResult:
+        q = np.ascontiguousarray(refToFrame_qts, np.float64)
+        r = Sim3EvalResult()
+        self.ctx._ck(self.ctx.L.lsdgpu_sim3_eval(self.ctx.ptr, reference_kf_id, frame_id, level, q.ctypes.data_as(_dp), a, b,
+                                                 C.byref(self.settings), C.byref(r)))
+        return r
+
+    def _take(self, r: Sim3Result):
+        self.last = r
+        self.diverged = bool(r.diverged)
+        self.pointUsage = r.pointUsage
+        self.lastResidual, self.lastDepthResidual, self.lastPhotometricResidual = r.lastResidual, r.lastDepthResidual, r.lastPhotometricResidual
+        self.affineEstimation_a, self.affineEstimation_b = r.affineEstimation_a, r.affineEstimation_b
+        self.lastSim3Hessian = np.array(r.lastSim3Hessian, np.float32).reshape(7, 7)
 
 
 class DepthMap:

@@ -162,12 +162,11 @@ LSD_HD void mat3Inverse(const float m[9], float r[9])
     r[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
 }
 
-// x = A^-1 b for a symmetric 6x6 via LDL^T with largest-diagonal pivoting (float)
-LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6])
+// x = A^-1 b for a symmetric NxN via LDL^T with largest-diagonal pivoting (float)
+template <int N> LSD_HD void ldltSolve(const float* Ain, const float* bin, float* x)
 {
-    const int N = 6;
-    float A[6][6];
-    int tr[6];
+    float A[N][N];
+    int tr[N];
     for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++) A[i][j] = Ain[i * N + j];
     for (int k = 0; k < N; k++) {
@@ -183,7 +182,7 @@ LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6])
             float t = A[k][k]; A[k][k] = A[p][p]; A[p][p] = t;
         }
         if (k > 0) {
-            float temp[6];
+            float temp[N];
             for (int j = 0; j < k; j++) temp[j] = A[j][j] * A[k][j];
             float s = 0;
             for (int j = 0; j < k; j++) s += A[k][j] * temp[j];
@@ -198,7 +197,7 @@ LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6])
         if (fabsf(d) > 0)
             for (int i = k + 1; i < N; i++) A[i][k] /= d;
     }
-    float y[6];
+    float y[N];
     for (int i = 0; i < N; i++) y[i] = bin[i];
     for (int k = 0; k < N; k++)
         if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
@@ -208,6 +207,137 @@ LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6])
     for (int k = N - 1; k >= 0; k--)
         if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
     for (int i = 0; i < N; i++) x[i] = y[i];
+}
+LSD_HD void ldlt6Solve(const float Ain[36], const float bin[6], float x[6]) { ldltSolve<6>(Ain, bin, x); }
+
+// ---- Sim3 as Sophus stores it: NON-unit quaternion (|q| = scale) + translation, double -------------------------
+// thirdparty/Sophus/sophus/sim3.hpp:159-173 (inverse), :257-260 (operator*=), :418-428 (exp), :609-648 (calcW);
+// rxso3.hpp:194-200 (inverse), :221-228 (matrix), :262-269 (operator* on a point), :299-305 (rotationMatrix), :416-425 (exp)
+struct Sim3 {
+    double q[4];
+    double t[3];
+    LSD_HD Sim3() { q[0] = q[1] = q[2] = 0; q[3] = 1; t[0] = t[1] = t[2] = 0; }
+};
+LSD_HD double sim3Scale(const Sim3& a) { return sqrt(a.q[0] * a.q[0] + a.q[1] * a.q[1] + a.q[2] * a.q[2] + a.q[3] * a.q[3]); }
+// qts[8] = unit quaternion (x,y,z,w), translation, scale  (the ABI's Sim3 layout, like thisToParent_qts)
+LSD_HD Sim3 sim3FromQts(const double a[8])
+{
+    Sim3 r;
+    for (int i = 0; i < 4; i++) r.q[i] = a[i] * a[7];
+    for (int i = 0; i < 3; i++) r.t[i] = a[4 + i];
+    return r;
+}
+LSD_HD void sim3ToQts(const Sim3& a, double o[8])
+{
+    const double s = sim3Scale(a);
+    for (int i = 0; i < 4; i++) o[i] = a.q[i] / s;
+    for (int i = 0; i < 3; i++) o[4 + i] = a.t[i];
+    o[7] = s;
+}
+LSD_HD void rxso3Apply(const double q[4], const double p[3], double o[3])
+{
+    const double scale = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    const double nq[4] = { q[0] / scale, q[1] / scale, q[2] / scale, q[3] / scale };
+    double r[3];
+    quatRotate(nq, p, r);
+    o[0] = scale * r[0]; o[1] = scale * r[1]; o[2] = scale * r[2];
+}
+LSD_HD Sim3 sim3Mul(const Sim3& a, const Sim3& b)
+{
+    Sim3 r;
+    double rt[3];
+    rxso3Apply(a.q, b.t, rt);
+    r.t[0] = a.t[0] + rt[0]; r.t[1] = a.t[1] + rt[1]; r.t[2] = a.t[2] + rt[2];
+    quatMul(a.q, b.q, r.q);
+    return r;
+}
+LSD_HD Sim3 sim3Inverse(const Sim3& a)
+{
+    const double n2 = a.q[0] * a.q[0] + a.q[1] * a.q[1] + a.q[2] * a.q[2] + a.q[3] * a.q[3];
+    Sim3 r;
+    r.q[0] = -a.q[0] / n2; r.q[1] = -a.q[1] / n2; r.q[2] = -a.q[2] / n2; r.q[3] = a.q[3] / n2;
+    const double nt[3] = { a.t[0] * -1.0, a.t[1] * -1.0, a.t[2] * -1.0 };
+    rxso3Apply(r.q, nt, r.t);
+    return r;
+}
+// exp of a = [upsilon | omega | sigma]
+LSD_HD Sim3 sim3Exp(const double a[7])
+{
+    const double* ups = a;
+    const double* om = a + 3;
+    const double sigma = a[6];
+    const double scale = exp(sigma);
+    const double theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    const double theta = sqrt(theta_sq), half_theta = 0.5 * theta;
+    double imag, real;
+    if (theta < 1e-10) {
+        const double theta_po4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real = 1.0 - 0.5 * theta_sq + (1.0 / 384.0) * theta_po4;
+    } else {
+        imag = sin(half_theta) / theta;
+        real = cos(half_theta);
+    }
+    Sim3 r;
+    r.q[0] = imag * om[0]; r.q[1] = imag * om[1]; r.q[2] = imag * om[2]; r.q[3] = real;
+    quatNormalize(r.q);
+    for (int i = 0; i < 4; i++) r.q[i] *= scale;
+    const double rs = sim3Scale(r);
+    const double Om[9] = { 0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0 };
+    double Om2[9];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++)
+            Om2[i * 3 + j] = (Om[i * 3 + 0] * Om[0 * 3 + j] + Om[i * 3 + 1] * Om[1 * 3 + j]) + Om[i * 3 + 2] * Om[2 * 3 + j];
+    double A, B, C;
+    if (fabs(sigma) < 1e-10) {
+        C = 1.0;
+        if (fabs(theta) < 1e-10) { A = 0.5; B = 1.0 / 6.0; }
+        else { A = (1.0 - cos(theta)) / theta_sq; B = (theta - sin(theta)) / (theta_sq * theta); }
+    } else {
+        C = (rs - 1.0) / sigma;
+        if (fabs(theta) < 1e-10) {
+            const double sigma_sq = sigma * sigma;
+            A = ((sigma - 1.0) * rs + 1.0) / sigma_sq;
+            B = ((0.5 * sigma * sigma - sigma + 1.0) * rs) / (sigma_sq * sigma);
+        } else {
+            const double sa = rs * sin(theta), sb = rs * cos(theta), sc = theta_sq + sigma * sigma;
+            A = (sa * sigma + (1.0 - sb) * theta) / (theta * sc);
+            B = (C - ((sb - 1.0) * sigma + sa * theta) / (sc)) * 1.0 / (theta_sq);
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        double w[3];
+        for (int j = 0; j < 3; j++) w[j] = (A * Om[i * 3 + j] + B * Om2[i * 3 + j]) + C * (i == j ? 1.0 : 0.0);
+        r.t[i] = (w[0] * ups[0] + w[1] * ups[1]) + w[2] * ups[2];
+    }
+    return r;
+}
+// The per-pose constants of Sim3Tracker::calcSim3Buffers (Sim3Tracker.cpp:447-460): rxso3().matrix(), translation and
+// the roll of the unscaled rotation about the optical axis (Eigen Quaternion::setFromTwoVectors + toRotationMatrix),
+// all cast to float as the reference does.  The 180-degree SVD branch of setFromTwoVectors is not restated (NaN).
+LSD_HD void sim3PoseConstants(const Sim3& a, float rotMat[9], float transVec[3], float roll[4])
+{
+    const double scale = sim3Scale(a);
+    const double nq[4] = { a.q[0] / scale, a.q[1] / scale, a.q[2] / scale, a.q[3] / scale };
+    double R[9];
+    quatToMatrix(nq, R);
+    float Ru[9];
+    for (int i = 0; i < 9; i++) { rotMat[i] = (float)(scale * R[i]); Ru[i] = (float)R[i]; }
+    for (int i = 0; i < 3; i++) transVec[i] = (float)a.t[i];
+    const float rf[3] = { (Ru[0] * 0.f + Ru[1] * 0.f) + Ru[2] * -1.f, (Ru[3] * 0.f + Ru[4] * 0.f) + Ru[5] * -1.f, (Ru[6] * 0.f + Ru[7] * 0.f) + Ru[8] * -1.f };
+    const float n = sqrtf((rf[0] * rf[0] + rf[1] * rf[1]) + rf[2] * rf[2]);
+    const float v0[3] = { rf[0] / n, rf[1] / n, rf[2] / n }, v1[3] = { 0.f, 0.f, -1.f };
+    const float c = (v1[0] * v0[0] + v1[1] * v0[1]) + v1[2] * v0[2];
+    if (c < -1.0f + 1e-5f) { roll[0] = roll[1] = roll[2] = roll[3] = nanf(""); return; }
+    const float ax[3] = { v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0] };
+    const float s = sqrtf((1.f + c) * 2.f), invs = 1.f / s;
+    const float q[4] = { ax[0] * invs, ax[1] * invs, ax[2] * invs, s * 0.5f };
+    float Rb[9];
+    quatToMatrix(q, Rb);
+    roll[0] = (Rb[0] * Ru[0] + Rb[1] * Ru[3]) + Rb[2] * Ru[6];
+    roll[1] = (Rb[0] * Ru[1] + Rb[1] * Ru[4]) + Rb[2] * Ru[7];
+    roll[2] = (Rb[3] * Ru[0] + Rb[4] * Ru[3]) + Rb[5] * Ru[6];
+    roll[3] = (Rb[3] * Ru[1] + Rb[4] * Ru[4]) + Rb[5] * Ru[7];
 }
 
 }  // namespace lsd

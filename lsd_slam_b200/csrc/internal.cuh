@@ -134,6 +134,8 @@ struct lsdgpu_ctx {
     int trackUseTma = 1;
     void* dPermaItems = nullptr;         // batched permaRef tracking: candidate descriptors / results (device)
     void* dPermaResults = nullptr;
+    void* dSim3Items = nullptr;          // batched Sim3 tracking: problem descriptors / results (device)
+    void* dSim3Outs = nullptr;
     int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe

@@ -7,6 +7,7 @@
 #include "depth.cuh"
 #include "track_persistent.cuh"
 #include "perma.cuh"
+#include "sim3.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -88,7 +89,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
                         + 2 * alignUp(n0 * 4, 256) + alignUp(n0 * 16, 256);              // prop head/next/val
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
-                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256)) * (size_t)max_frames + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024
+                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256)) * (size_t)max_frames + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024 + alignUp(S3_MAX_BATCH * sizeof(Sim3Item), 256) + alignUp(S3_MAX_BATCH * sizeof(Sim3Out), 256)
                      + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
@@ -148,6 +149,8 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     }
     ctx->dPermaItems = take(LSD_MAX_PERMA_BATCH * sizeof(PermaItem));
     ctx->dPermaResults = take(LSD_MAX_PERMA_BATCH * sizeof(PermaResult));
+    ctx->dSim3Items = take(S3_MAX_BATCH * sizeof(Sim3Item));
+    ctx->dSim3Outs = take(S3_MAX_BATCH * sizeof(Sim3Out));
     ctx->dStageF = (float*)take(n0 * 32);
     ctx->dScalars = (double*)take((size_t)maxBlocks * 2 * 8 + 64);
     ctx->dTrackState = take(sizeof(TrackState));
@@ -1282,4 +1285,118 @@ extern "C" int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_id
         for (int k = 0; k < 3; k++) o.frameToRef_qt[4 + k] = Td.t[k];
     }
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sim3 tracking, batched
+// ------------------------------------------------------------------------------------------------------
+static int sim3Launch(lsdgpu_ctx* ctx, int n, const int* ref_ids, const int* frame_ids, const double* qts, bool qtsIsRefToFrame,
+                      int startLevel, int finalLevel, const lsdgpu_track_settings* s, int evalOnly, float evalA, float evalB,
+                      std::vector<Sim3Out>& hout)
+{
+    if (n <= 0 || n > S3_MAX_BATCH) return lsd_fail(ctx, "bad problem count");
+    if (startLevel < 0 || startLevel >= LSD_LEVELS || finalLevel < 0 || finalLevel > startLevel) return lsd_fail(ctx, "bad level range");
+    std::vector<Sim3Item> items(n);
+    for (int i = 0; i < n; i++) {
+        FrameSlot* kf = findSlot(ctx, ref_ids[i]);
+        FrameSlot* fr = findSlot(ctx, frame_ids[i]);
+        if (!kf || !fr) return lsd_fail(ctx, "unknown frame id");
+        int r = ensureIdepthPyramid(ctx, kf);       // reference->makePointCloud(lvl), Sim3Tracker.cpp:174
+        if (r) return r;
+        r = ensureIdepthPyramid(ctx, fr);           // frame->idepth(level) / idepthVar(level), :467-468
+        if (r) return r;
+        for (int l = 0; l < LSD_LEVELS; l++) {
+            items[i].kfIdepth[l] = kf->idepth[l]; items[i].kfVar[l] = kf->idepthVar[l]; items[i].kfGrad[l] = kf->grad[l];
+            items[i].frGrad[l] = fr->grad[l]; items[i].frIdepth[l] = fr->idepth[l]; items[i].frVar[l] = fr->idepthVar[l];
+        }
+        lsd::Sim3 T = lsd::sim3FromQts(qts + 8 * i);
+        if (!qtsIsRefToFrame) T = lsd::sim3Inverse(T);                  // :161
+        for (int k = 0; k < 4; k++) items[i].refToFrame[k] = T.q[k];
+        for (int k = 0; k < 3; k++) items[i].refToFrame[4 + k] = T.t[k];
+    }
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dSim3Items, items.data(), n * sizeof(Sim3Item), cudaMemcpyHostToDevice, ctx->stream));
+    Sim3Params P;
+    memset(&P, 0, sizeof(P));
+    for (int l = 0; l < LSD_LEVELS; l++) {
+        const LevelCam& c = ctx->cam[l];
+        Sim3Level& L = P.lvl[l];
+        L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy; L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+    }
+    lsdgpu_track_settings ds;
+    if (!s) { lsdgpu_default_track_settings(&ds); s = &ds; }
+    P.st = *s;
+    P.cameraPixelNoise2 = ctx->g.cameraPixelNoise2;
+    P.useAffine = ctx->g.useAffineLightningEstimation;
+    P.W = ctx->w; P.H = ctx->h;
+    P.startLevel = startLevel; P.finalLevel = finalLevel;
+    P.evalOnly = evalOnly; P.evalA = evalA; P.evalB = evalB;
+    // one cluster per problem: 8 CTAs (the portable maximum) unless the batch alone fills the GPU
+    int cs = 8;
+    if (const char* e = getenv("LSDGPU_SIM3_CLUSTER")) cs = atoi(e);
+    else if (n >= 2 * ctx->smCount) cs = 1;
+    else if (n * 8 > 2 * ctx->smCount) cs = (n * 4 > 2 * ctx->smCount) ? ((n * 2 > 2 * ctx->smCount) ? 1 : 2) : 4;
+    if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 8;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(n * cs); cfg.blockDim = dim3(S3_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    LSD_CHECK(ctx, cudaLaunchKernelEx(&cfg, k_sim3_track, P, (const Sim3Item*)ctx->dSim3Items, (Sim3Out*)ctx->dSim3Outs));
+    LAUNCH(ctx);
+    hout.resize(n);
+    LSD_CHECK(ctx, cudaMemcpyAsync(hout.data(), ctx->dSim3Outs, n * sizeof(Sim3Out), cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_sim3_eval(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, int level, const double refToFrame_qts[8],
+                                float affine_a, float affine_b, const lsdgpu_track_settings* s, lsdgpu_sim3_eval_result* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    std::vector<Sim3Out> h;
+    int r = sim3Launch(ctx, 1, &ref_kf_id, &frame_id, refToFrame_qts, true, level, level, s, 1, affine_a, affine_b, h);
+    if (r) return r;
+    const float* sm = h[0].sums;
+    sim3AssembleLGS7(sm, out->A, out->b);
+    const Sim3Res res = sim3Finish(sm);
+    out->num_constraints = 2 * res.warpedSize;
+    out->sumResD = sm[S3_RESD]; out->sumResP = sm[S3_RESP]; out->numTermsD = (int)sm[S3_NUMD]; out->numTermsP = (int)sm[S3_NUMP];
+    out->mean = res.mean; out->meanD = res.meanD; out->meanP = res.meanP;
+    out->warpedSize = res.warpedSize; out->pointUsage = res.pointUsage;
+    out->affine_a_lastIt = res.a_lastIt; out->affine_b_lastIt = res.b_lastIt;
+    return 0;
+}
+
+extern "C" int lsdgpu_sim3_track_batch(lsdgpu_ctx* ctx, int n, const int* ref_kf_ids, const int* frame_ids, const double* frameToRef_init_qts,
+                                       int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* results)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    std::vector<Sim3Out> h;
+    int r = sim3Launch(ctx, n, ref_kf_ids, frame_ids, frameToRef_init_qts, false, start_level, final_level, s, 0, 1.f, 0.f, h);
+    if (r) return r;
+    for (int i = 0; i < n; i++) {
+        lsdgpu_sim3_result& o = results[i];
+        const Sim3Out& d = h[i];
+        memset(&o, 0, sizeof(o));
+        o.frameToRef_qts[3] = 1; o.frameToRef_qts[7] = 1;                               // Sim3()
+        o.pointUsage = d.pointUsage; o.affineEstimation_a = d.affine_a; o.affineEstimation_b = d.affine_b;
+        for (int l = 0; l < LSD_LEVELS; l++) { o.numCalcResidualCalls[l] = d.nRes[l]; o.numCalcWarpUpdateCalls[l] = d.nUpd[l]; }
+        if (d.early) { o.diverged = (d.early == 1); continue; }                         // :184-187, :212-217, :231-235
+        float b7[7];
+        sim3AssembleLGS7(d.lgs, o.lastSim3Hessian, b7);                                 // lastSim3Hessian = ls7.A, :360
+        lsd::Sim3 T;
+        for (int k = 0; k < 4; k++) T.q[k] = d.refToFrame[k];
+        for (int k = 0; k < 3; k++) T.t[k] = d.refToFrame[4 + k];
+        if (lsd::sim3Scale(T) <= 0) { o.diverged = 1; continue; }                       // :363-367
+        o.lastResidual = d.resMean; o.lastDepthResidual = d.resMeanD; o.lastPhotometricResidual = d.resMeanP;   // :369-371
+        lsd::sim3ToQts(lsd::sim3Inverse(T), o.frameToRef_qts);                          // :374
+    }
+    return 0;
+}
+
+extern "C" int lsdgpu_sim3_track(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, const double frameToRef_init_qts[8],
+                                 int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* out)
+{
+    return lsdgpu_sim3_track_batch(ctx, 1, &ref_kf_id, &frame_id, frameToRef_init_qts, start_level, final_level, s, out);
 }

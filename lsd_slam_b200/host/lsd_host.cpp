@@ -146,6 +146,68 @@ SE3 SE3Tracker::trackFrame(TrackingReference* reference, Frame* frame, const SE3
     return out;
 }
 
+Sim3Tracker::Sim3Tracker(DeviceContext& dev, int w, int h, const Matrix3f&) : dev_(dev), width_(w), height_(h)
+{
+    if (w != dev.width() || h != dev.height()) throw LsdGpuError("Sim3Tracker: size differs from the device context");
+    lastSim3Hessian.setZero();
+}
+
+static void sim3ToQts(const Sim3& a, double o[8])
+{
+    for (int i = 0; i < 4; i++) o[i] = a.q[i];
+    for (int i = 0; i < 3; i++) o[4 + i] = a.t[i];
+    o[7] = a.s;
+}
+
+Sim3 Sim3Tracker::take(const lsdgpu_sim3_result& r)
+{
+    // members a diverged / rejected tracking leaves untouched keep their previous values (Sim3Tracker.cpp:184-187, 212-217)
+    pointUsage = r.pointUsage;
+    affineEstimation_a = r.affineEstimation_a; affineEstimation_b = r.affineEstimation_b;
+    diverged = r.diverged != 0;
+    Sim3 out;                                                          // Sim3()
+    bool hessianZero = true;
+    for (float v : r.lastSim3Hessian) hessianZero = hessianZero && v == 0.f;
+    if (diverged && hessianZero) return out;                           // :184-187, :231-235
+    for (int i = 0; i < 49; i++) lastSim3Hessian.m[i] = r.lastSim3Hessian[i];     // :360 (also zeroed by :215)
+    if (diverged || hessianZero) return out;                           // :363-367, :212-217
+    lastResidual = r.lastResidual; lastDepthResidual = r.lastDepthResidual; lastPhotometricResidual = r.lastPhotometricResidual;
+    for (int i = 0; i < 4; i++) out.q[i] = r.frameToRef_qts[i];
+    for (int i = 0; i < 3; i++) out.t[i] = r.frameToRef_qts[4 + i];
+    out.s = r.frameToRef_qts[7];
+    return out;
+}
+
+Sim3 Sim3Tracker::trackFrameSim3(TrackingReference* reference, Frame* frame, const Sim3& frameToReference_initialEstimate,
+                                 int startLevel, int finalLevel)
+{
+    double init[8];
+    sim3ToQts(frameToReference_initialEstimate, init);
+    lsdgpu_sim3_result r;
+    dev_.check(lsdgpu_sim3_track(dev_.raw(), reference->keyframe->id(), frame->id(), init, startLevel, finalLevel, &settings, &r),
+               "Sim3Tracker::trackFrameSim3");
+    return take(r);
+}
+
+void Sim3Tracker::trackFrameSim3Batch(const std::vector<TrackingReference*>& references, const std::vector<Frame*>& frames,
+                                      const std::vector<Sim3>& inits, int startLevel, int finalLevel,
+                                      std::vector<Sim3>& frameToReference, std::vector<lsdgpu_sim3_result>& results)
+{
+    const size_t n = references.size();
+    if (frames.size() != n || inits.size() != n) throw LsdGpuError("Sim3Tracker::trackFrameSim3Batch: list lengths differ");
+    std::vector<int> refIds(n), frIds(n);
+    std::vector<double> q(8 * n);
+    for (size_t i = 0; i < n; i++) {
+        refIds[i] = references[i]->keyframe->id(); frIds[i] = frames[i]->id();
+        sim3ToQts(inits[i], &q[8 * i]);
+    }
+    results.resize(n);
+    dev_.check(lsdgpu_sim3_track_batch(dev_.raw(), (int)n, refIds.data(), frIds.data(), q.data(), startLevel, finalLevel, &settings, results.data()),
+               "Sim3Tracker::trackFrameSim3Batch");
+    frameToReference.resize(n);
+    for (size_t i = 0; i < n; i++) frameToReference[i] = take(results[i]);
+}
+
 DepthMap::DepthMap(DeviceContext& dev, int w, int h, const Matrix3f&) : dev_(dev), width_(w), height_(h)
 {
     if (w != dev.width() || h != dev.height()) throw LsdGpuError("DepthMap: size differs from the device context");

@@ -149,6 +149,38 @@ private:
     int width_, height_;
 };
 
+// Tracking/Sim3Tracker.h:59-160
+struct Matrix7x7 {
+    float m[49];                                     // row-major
+    float operator()(int r, int c) const { return m[r * 7 + c]; }
+    void setZero() { for (float& v : m) v = 0.f; }
+};
+class Sim3Tracker {
+public:
+    Sim3Tracker(DeviceContext& dev, int w, int h, const Matrix3f& K);
+    Sim3Tracker(const Sim3Tracker&) = delete;
+
+    Sim3 trackFrameSim3(TrackingReference* reference, Frame* frame, const Sim3& frameToReference_initialEstimate,
+                        int startLevel, int finalLevel);
+    // n independent (reference, frame) pairs in one launch; members below then describe the LAST problem,
+    // results[] all of them (SlamSystem::tryTrackSim3 runs two per candidate, SlamSystem.cpp:1043-1127)
+    void trackFrameSim3Batch(const std::vector<TrackingReference*>& references, const std::vector<Frame*>& frames,
+                             const std::vector<Sim3>& frameToReference_initialEstimates, int startLevel, int finalLevel,
+                             std::vector<Sim3>& frameToReference, std::vector<lsdgpu_sim3_result>& results);
+
+    DenseDepthTrackerSettings settings;
+    Matrix7x7 lastSim3Hessian;
+    float pointUsage = 0;
+    float lastResidual = 0, lastDepthResidual = 0, lastPhotometricResidual = 0;
+    float affineEstimation_a = 1, affineEstimation_b = 0;
+    bool diverged = false;
+
+private:
+    Sim3 take(const lsdgpu_sim3_result& r);
+    DeviceContext& dev_;
+    int width_, height_;
+};
+
 // DepthEstimation/DepthMap.h
 class DepthMap {
 public:

@@ -110,11 +110,10 @@ void lsdo_mat3_inverse(const float m[9], float r[9])
 #undef M
 }
 
-/* Eigen LDLT (Cholesky/LDLT.h, unblocked lower, largest-|diagonal| pivoting) + solve, float */
-int lsdo_ldlt6_solve(const float Ain[36], const float bin[6], float x[6])
+/* Eigen LDLT (Cholesky/LDLT.h, unblocked lower, largest-|diagonal| pivoting) + solve, float; N <= 8 */
+static int ldlt_solve_n(int N, const float* Ain, const float* bin, float* x)
 {
-    enum { N = 6 };
-    float A[N][N]; int tr[N];
+    float A[8][8]; int tr[8];
     for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) A[i][j] = Ain[i*N+j];
     for (int k = 0; k < N; k++) {
         int p = k; float big = fabsf(A[k][k]);
@@ -128,7 +127,7 @@ int lsdo_ldlt6_solve(const float Ain[36], const float bin[6], float x[6])
         }
         /* A[k][k] -= sum_j L[k][j]^2 D[j] ; column below */
         if (k > 0) {
-            float temp[N];
+            float temp[8];
             for (int j = 0; j < k; j++) temp[j] = A[j][j]*A[k][j];
             float s = 0; for (int j = 0; j < k; j++) s += A[k][j]*temp[j];
             A[k][k] -= s;
@@ -140,7 +139,7 @@ int lsdo_ldlt6_solve(const float Ain[36], const float bin[6], float x[6])
         float d = A[k][k];
         if (fabsf(d) > 0) for (int i = k+1; i < N; i++) A[i][k] /= d;
     }
-    float y[N];
+    float y[8];
     for (int i = 0; i < N; i++) y[i] = bin[i];
     for (int k = 0; k < N; k++) if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
     for (int i = 0; i < N; i++) { float s = y[i]; for (int j = 0; j < i; j++) s -= A[i][j]*y[j]; y[i] = s; }
@@ -150,6 +149,8 @@ int lsdo_ldlt6_solve(const float Ain[36], const float bin[6], float x[6])
     for (int i = 0; i < N; i++) x[i] = y[i];
     return 0;
 }
+int lsdo_ldlt6_solve(const float Ain[36], const float bin[6], float x[6]) { return ldlt_solve_n(6, Ain, bin, x); }
+int lsdo_ldlt7_solve(const float Ain[49], const float bin[7], float x[7]) { return ldlt_solve_n(7, Ain, bin, x); }
 
 /* ---- Sophus SE3 in float and double; qt = (qx,qy,qz,qw, tx,ty,tz) ----
  * generated twice through a macro so that the float flavour really computes in float
@@ -1181,4 +1182,5 @@ int lsdo_trackFrameOnPermaref(int w0, int h0, const float* permaPos, const float
     return 0;
 }
 
+#include "lsd_oracle_sim3.inc"
 #include "lsd_oracle_depth.inc"

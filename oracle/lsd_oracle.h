@@ -96,6 +96,28 @@ typedef struct {
     float sxx, syy, sx, sy, sw;
 } lsdo_eval_result;
 
+/* Sim3Tracker: everything SlamSystem::tryTrackSim3 reads back, Tracking/Sim3Tracker.h:66,127-138 */
+typedef struct {
+    double frameToRef_qts[8];         /* unit (qx,qy,qz,qw), (tx,ty,tz), scale; Sim3() = identity on the early returns */
+    float  lastSim3Hessian[49];       /* ls7.A, NOT divided by num_constraints (Sim3Tracker.cpp:360) */
+    float  lastResidual, lastDepthResidual, lastPhotometricResidual;
+    float  pointUsage;
+    float  affineEstimation_a, affineEstimation_b;
+    int    diverged;
+    int    numCalcResidualCalls[LSDO_LEVELS];
+    int    numCalcWarpUpdateCalls[LSDO_LEVELS];
+} lsdo_sim3_result;
+
+/* one fused evaluation: calcSim3Buffers + calcSim3WeightsAndResidual + calcSim3LGS */
+typedef struct {
+    float A[49], b[7];                /* LGS7, undivided */
+    int   num_constraints;            /* 2 * warpedSize */
+    float sumResD, sumResP; int numTermsD, numTermsP;
+    float mean, meanD, meanP;
+    int   warpedSize;
+    float pointUsage, affine_a_lastIt, affine_b_lastIt;
+} lsdo_sim3_eval_result;
+
 typedef struct lsdo_frame lsdo_frame;
 typedef struct lsdo_depthmap lsdo_depthmap;
 
@@ -115,6 +137,13 @@ void lsdo_se3f_inverse(const float a[7], float out[7]);
 void lsdo_se3f_matrix(const float a[7], float R[9], float t[3]);
 void lsdo_se3d_log(const double a[7], double out[6]);
 int  lsdo_ldlt6_solve(const float A[36], const float b[6], float x[6]);
+int  lsdo_ldlt7_solve(const float A[49], const float b[7], float x[7]);
+/* Sim3 as qts[8] = unit quaternion (x,y,z,w), translation, scale  (thirdparty/Sophus/sophus/sim3.hpp, rxso3.hpp) */
+void lsdo_sim3d_exp(const double a[7], double out_qts[8]);
+void lsdo_sim3d_mul(const double a[8], const double b[8], double out[8]);
+void lsdo_sim3d_inverse(const double a[8], double out[8]);
+/* the per-pose constants of calcSim3Buffers (Sim3Tracker.cpp:447-460): rxso3 matrix, translation, xRoll0/1 yRoll0/1 */
+void lsdo_sim3_pose_constants(const double refToFrame_qts[8], float rotMat[9], float transVec[3], float roll[4]);
 void lsdo_mat3_inverse(const float K[9], float Kinv[9]);
 
 /* ---- Frame (DataStructures/Frame.{h,cpp}) ---- */
@@ -157,6 +186,12 @@ int lsdo_se3_eval(lsdo_frame* kf, lsdo_frame* frame, int level, const float refT
                   int writeGoodMask, lsdo_eval_result* out);
 int lsdo_se3_track(lsdo_frame* kf, lsdo_frame* frame, const double frameToRef_init_qt[7],
                    const lsdo_track_settings* s, lsdo_track_result* out);
+
+/* ---- Sim3Tracker (Tracking/Sim3Tracker.cpp); `frame` must carry depth (a keyframe) ---- */
+int lsdo_sim3_eval(lsdo_frame* ref_kf, lsdo_frame* frame, int level, const double refToFrame_qts[8],
+                   float affine_a, float affine_b, const lsdo_track_settings* s, lsdo_sim3_eval_result* out);
+int lsdo_sim3_track(lsdo_frame* ref_kf, lsdo_frame* frame, const double frameToRef_init_qts[8],
+                    int startLevel, int finalLevel, const lsdo_track_settings* s, lsdo_sim3_result* out);
 
 /* ---- permaRef tracking, SURVEY 8f row 2 (Frame.cpp:149-174, SE3Tracker.cpp:121-272) ---- */
 int   lsdo_frame_setPermaRef(lsdo_frame* kf, float* posData, float* colorAndVarData);      /* returns permaRefNumPts */

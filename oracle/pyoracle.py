@@ -59,6 +59,21 @@ class EvalResult(C.Structure):
                 ("sxx", C.c_float), ("syy", C.c_float), ("sx", C.c_float), ("sy", C.c_float), ("sw", C.c_float)]
 
 
+class Sim3Result(C.Structure):
+    _fields_ = [("frameToRef_qts", C.c_double * 8), ("lastSim3Hessian", C.c_float * 49),
+                ("lastResidual", C.c_float), ("lastDepthResidual", C.c_float), ("lastPhotometricResidual", C.c_float),
+                ("pointUsage", C.c_float), ("affineEstimation_a", C.c_float), ("affineEstimation_b", C.c_float),
+                ("diverged", C.c_int),
+                ("numCalcResidualCalls", C.c_int * LEVELS), ("numCalcWarpUpdateCalls", C.c_int * LEVELS)]
+
+
+class Sim3EvalResult(C.Structure):
+    _fields_ = [("A", C.c_float * 49), ("b", C.c_float * 7), ("num_constraints", C.c_int),
+                ("sumResD", C.c_float), ("sumResP", C.c_float), ("numTermsD", C.c_int), ("numTermsP", C.c_int),
+                ("mean", C.c_float), ("meanD", C.c_float), ("meanP", C.c_float), ("warpedSize", C.c_int),
+                ("pointUsage", C.c_float), ("affine_a_lastIt", C.c_float), ("affine_b_lastIt", C.c_float)]
+
+
 def build(force: bool = False) -> None:
     """Compile the oracle with the committed Makefile (gcc only)."""
     if force or not (os.path.exists(os.path.join(_HERE, "liblsd_oracle.so"))
@@ -123,6 +138,13 @@ def lib(fast: bool = False):
     sig("lsdo_make_point_cloud", C.c_int, vp, C.c_int, fp, fp, fp, ip)
     sig("lsdo_se3_eval", C.c_int, vp, vp, C.c_int, fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult))
     sig("lsdo_se3_track", C.c_int, vp, vp, dp, C.POINTER(TrackSettings), C.POINTER(TrackResult))
+    sig("lsdo_ldlt7_solve", C.c_int, fp, fp, fp)
+    sig("lsdo_sim3d_exp", None, dp, dp)
+    sig("lsdo_sim3d_mul", None, dp, dp, dp)
+    sig("lsdo_sim3d_inverse", None, dp, dp)
+    sig("lsdo_sim3_pose_constants", None, dp, fp, fp, fp)
+    sig("lsdo_sim3_eval", C.c_int, vp, vp, C.c_int, dp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.POINTER(Sim3EvalResult))
+    sig("lsdo_sim3_track", C.c_int, vp, vp, dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result))
     sig("lsdo_frame_setPermaRef", C.c_int, vp, fp, fp)
     sig("lsdo_checkPermaRefOverlap", C.c_float, C.c_int, C.c_int, fp, fp, C.c_int, dp)
     sig("lsdo_trackFrameOnPermaref", C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, vp, dp, C.POINTER(TrackResult))
@@ -281,6 +303,24 @@ def se3_track(kf: Frame, frame: Frame, init_frameToRef_qt, settings: TrackSettin
     r = TrackResult()
     q = np.ascontiguousarray(init_frameToRef_qt, np.float64)
     kf.L.lsdo_se3_track(kf.ptr, frame.ptr, _dp(q), C.byref(s), C.byref(r))
+    return r
+
+
+def sim3_track(ref_kf: Frame, frame: Frame, init_frameToRef_qts, start_level=4, final_level=1,
+               settings: TrackSettings | None = None) -> Sim3Result:
+    """Sim3Tracker::trackFrameSim3 (Sim3Tracker.cpp:149-382); `frame` must carry depth."""
+    s = settings or default_track_settings(main_tracker=False)      # constraintTracker keeps the class defaults
+    r = Sim3Result()
+    q = np.ascontiguousarray(init_frameToRef_qts, np.float64)
+    ref_kf.L.lsdo_sim3_track(ref_kf.ptr, frame.ptr, _dp(q), start_level, final_level, C.byref(s), C.byref(r))
+    return r
+
+
+def sim3_eval(ref_kf: Frame, frame: Frame, level: int, refToFrame_qts, a=1.0, b=0.0, settings=None) -> Sim3EvalResult:
+    s = settings or default_track_settings(main_tracker=False)
+    r = Sim3EvalResult()
+    q = np.ascontiguousarray(refToFrame_qts, np.float64)
+    ref_kf.L.lsdo_sim3_eval(ref_kf.ptr, frame.ptr, level, _dp(q), a, b, C.byref(s), C.byref(r))
     return r
 
 

@@ -17,7 +17,8 @@ def test_host_adapter_compiles_and_links():
     syms = subprocess.run(["nm", "-DC", build.HOST_OUT], capture_output=True, text=True).stdout
     for s in ("lsd_slam::SE3Tracker::trackFrame(lsd_slam::TrackingReference*, lsd_slam::Frame*, lsd_slam::SE3 const&)",
               "lsd_slam::DepthMap::updateKeyframe(std::deque<std::shared_ptr<lsd_slam::Frame>",
-              "lsd_slam::DepthMap::createKeyFrame(lsd_slam::Frame*)"):
+              "lsd_slam::DepthMap::createKeyFrame(lsd_slam::Frame*)",
+              "lsd_slam::Sim3Tracker::trackFrameSim3(lsd_slam::TrackingReference*, lsd_slam::Frame*, lsd_slam::Sim3 const&, int, int)"):
         assert s in syms, s
 
 
