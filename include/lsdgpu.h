@@ -174,6 +174,40 @@ int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t
                          const double frameToRef_init_qt[7], const lsdgpu_track_settings* s, int mode,
                          int keyframe_change, lsdgpu_track_result* out, double new_kf_thisToParent_qts[8]);
 
+/* ---- input staging: UndistorterPTAM fused into the Frame construction ----------------------------
+ * UndistorterPTAM::UndistorterPTAM, util/Undistorter.cpp:171-317, with the four lines of the calibration file already parsed:
+ * input_calibration = fx fy cx cy dist (relative to the input size); output_calibration[0] = -1 for "crop", -2 for "full",
+ * otherwise fx fy cx cy 0 (relative to the output size).  Host-only (no context needed): fills the two remap tables
+ * (out_width*out_height floats each, may be NULL) and K_out (row-major, the matrix main_on_images.cpp:164-173 hands to
+ * SlamSystem).  Returns 0 = tables valid, 1 = undistort() passes the image through (:370-375), -2 = invalid arguments.
+ * UndistorterOpenCV (:449-567) delegates to cv::initUndistortRectifyMap / cv::remap and stays on the host. */
+int lsdgpu_undistorter_ptam_prepare(const float input_calibration[5], int in_width, int in_height, const float output_calibration[5],
+                                    int out_width, int out_height, float* remapX, float* remapY, float K_out[9]);
+/* install remap tables (host pointers, w*h floats each; w, h = the context's size) for raw images of in_width x in_height;
+ * NULL tables = pass-through (then in_width/in_height must equal the context's size) */
+int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const float* remapX, const float* remapY);
+/* UndistorterPTAM::undistort, util/Undistorter.cpp:355-411: raw (in_width*in_height) -> out (w*h), 8 bit */
+int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t* out);
+/* undistort + Frame::Frame(id, w, h, K, ts, const uchar*) + buildImage/buildGradients/buildMaxGradients of all levels:
+ * the raw image is copied to the device once and the remap feeds the pyramid kernel directly
+ * (main_on_images.cpp:236-246: undistorter->undistort(imageDist, image); system->trackFrame(image.data, ...)) */
+int lsdgpu_frame_upload_distorted_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* raw);
+
+/* ---- keyframe output formats, packed on the device ----------------------------------------------
+ * InputPointDense, IOWrapper/ROS/ROSOutput3DWrapper.h:34-39 = one record of keyframeMsg.pointcloud (lsd_slam_viewer/msg/keyframeMsg.msg:20-22) */
+typedef struct { float idepth; float idepth_var; unsigned char color[4]; } lsdgpu_input_point_dense;
+/* the packing loop of ROSOutput3DWrapper::publishKeyframe (ROSOutput3DWrapper.cpp:91-110) for level `publish_level`:
+ * out receives (w >> level) * (h >> level) records, one device-to-host copy in wire layout */
+int lsdgpu_keyframe_pack_pointcloud(lsdgpu_ctx* ctx, int kf_id, int publish_level, lsdgpu_input_point_dense* out);
+/* Frame::takeReActivationData(currentDepthMap), DataStructures/Frame.cpp:107-145: snapshot of the ACTIVE depth map into the
+ * keyframe's idepth_reAct / idepthVar_reAct / validity_reAct -- kept on the device.  lsdgpu_depth_finalize_keyframe calls it
+ * (DepthMap.cpp:1387); exposed for re-activation bookkeeping outside finalize. */
+int lsdgpu_frame_take_reactivation_data(lsdgpu_ctx* ctx, int kf_id);
+/* copies of the three reactivation arrays (w*h each), for host consumers and the parity tests; any pointer may be NULL */
+int lsdgpu_frame_download_reactivation_data(lsdgpu_ctx* ctx, int kf_id, float* idepth_reAct, float* idepthVar_reAct, uint8_t* validity_reAct);
+/* DepthMap::setFromExistingKF(kf), DepthEstimation/DepthMap.cpp:920-962, from the keyframe's device-resident reactivation data */
+int lsdgpu_depth_set_from_existing_kf(lsdgpu_ctx* ctx, int kf_id);
+
 /* ---- Sim3Tracker, batched --------------------------------------------------------------------
  * Sim3 values cross the ABI as qts[8] = unit quaternion (x,y,z,w), translation, scale (like new_kf_thisToParent_qts).
  * Everything SlamSystem::tryTrackSim3 (SlamSystem.cpp:1043-1127) reads from the tracker, Tracking/Sim3Tracker.h:66,127-138. */

@@ -35,6 +35,9 @@ HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, 3), ("blackliste
                       ("idepth_smoothed", np.float32), ("idepth_var_smoothed", np.float32)])
 
 
+POINT_DENSE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])     # InputPointDense
+
+
 class Globals(C.Structure):
     _fields_ = [("minUseGrad", C.c_float), ("cameraPixelNoise2", C.c_float), ("depthSmoothingFactor", C.c_float),
                 ("allowNegativeIdepths", C.c_int), ("useSubpixelStereo", C.c_int),
@@ -115,6 +118,14 @@ SYMBOLS = [
     ("lsdgpu_se3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult)]),
     ("lsdgpu_se3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.POINTER(TrackResult)]),
     ("lsdgpu_track_and_map", C.c_int, [_vp, C.c_int, C.c_int, _u8p, C.c_int, _dp, C.POINTER(TrackSettings), C.c_int, C.c_int, C.POINTER(TrackResult), _dp]),
+    ("lsdgpu_undistorter_ptam_prepare", C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, _fp, _fp]),
+    ("lsdgpu_set_undistorter", C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp]),
+    ("lsdgpu_undistort_u8", C.c_int, [_vp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]),
+    ("lsdgpu_frame_upload_distorted_u8", C.c_int, [_vp, C.c_int, C.POINTER(C.c_uint8)]),
+    ("lsdgpu_keyframe_pack_pointcloud", C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    ("lsdgpu_frame_take_reactivation_data", C.c_int, [_vp, C.c_int]),
+    ("lsdgpu_frame_download_reactivation_data", C.c_int, [_vp, C.c_int, _fp, _fp, C.POINTER(C.c_uint8)]),
+    ("lsdgpu_depth_set_from_existing_kf", C.c_int, [_vp, C.c_int]),
     ("lsdgpu_sim3_eval", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _dp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.POINTER(Sim3EvalResult)]),
     ("lsdgpu_sim3_track", C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result)]),
     ("lsdgpu_sim3_track_batch", C.c_int, [_vp, C.c_int, _ip, _ip, _dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result)]),
@@ -161,6 +172,40 @@ def load():
 
 class LsdGpuError(RuntimeError):
     pass
+
+
+class UndistorterPTAM:
+    """Mirror of lsd_slam::UndistorterPTAM (util/Undistorter.h:96-160) with the calibration file's lines already parsed.
+    out_calib: "crop", "full" or (fx, fy, cx, cy, 0).  Host-only; `install(ctx)` puts the tables on the device."""
+
+    def __init__(self, in_calib, in_size, out_calib, out_size):
+        self.in_w, self.in_h = in_size
+        self.out_w, self.out_h = out_size
+        ic = np.ascontiguousarray(in_calib, np.float32)
+        oc = np.zeros(5, np.float32)
+        if isinstance(out_calib, str):
+            oc[0] = {"crop": -1, "full": -2}[out_calib]
+        else:
+            oc[:] = out_calib
+        self.remapX = np.zeros((self.out_h, self.out_w), np.float32)
+        self.remapY = np.zeros((self.out_h, self.out_w), np.float32)
+        K = np.zeros(9, np.float32)
+        self.status = load().lsdgpu_undistorter_ptam_prepare(ic.ctypes.data_as(_fp), self.in_w, self.in_h, oc.ctypes.data_as(_fp),
+                                                             self.out_w, self.out_h, self.remapX.ctypes.data_as(_fp),
+                                                             self.remapY.ctypes.data_as(_fp), K.ctypes.data_as(_fp))
+        if self.status < 0:
+            raise LsdGpuError("UndistorterPTAM: invalid calibration")
+        self.K = K.reshape(3, 3)
+
+    def getK(self) -> np.ndarray:
+        return self.K
+
+    def install(self, ctx: "Context"):
+        assert (ctx.w, ctx.h) == (self.out_w, self.out_h)
+        if self.status == 1:
+            ctx._ck(ctx.L.lsdgpu_set_undistorter(ctx.ptr, self.in_w, self.in_h, None, None))
+        else:
+            ctx._ck(ctx.L.lsdgpu_set_undistorter(ctx.ptr, self.in_w, self.in_h, self.remapX.ctypes.data_as(_fp), self.remapY.ctypes.data_as(_fp)))
 
 
 def default_track_settings(main_tracker: bool = True) -> TrackSettings:
@@ -299,6 +344,36 @@ class Context:
         f = C.c_int()
         self._ck(self.L.lsdgpu_frame_get_depth_stats(self.ptr, fid, None, None, C.byref(f)))
         return bool(f.value)
+
+    def undistort(self, raw_u8: np.ndarray) -> np.ndarray:
+        """UndistorterPTAM::undistort (Undistorter.cpp:355-411) through the installed tables"""
+        raw = np.ascontiguousarray(raw_u8, np.uint8)
+        out = np.zeros((self.h, self.w), np.uint8)
+        self._ck(self.L.lsdgpu_undistort_u8(self.ptr, raw.ctypes.data_as(C.POINTER(C.c_uint8)), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
+
+    def upload_distorted(self, fid: int, raw_u8: np.ndarray):
+        """undistort + Frame construction fused (one H2D copy of the raw image, remap feeds the pyramid kernel)"""
+        raw = np.ascontiguousarray(raw_u8, np.uint8)
+        self._ck(self.L.lsdgpu_frame_upload_distorted_u8(self.ptr, fid, raw.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+    def pack_pointcloud(self, kf_id: int, level: int = 0) -> np.ndarray:
+        """keyframeMsg.pointcloud of ROSOutput3DWrapper::publishKeyframe (ROSOutput3DWrapper.cpp:91-110), packed on the device"""
+        n = (self.w >> level) * (self.h >> level)
+        out = np.zeros(n, POINT_DENSE)
+        self._ck(self.L.lsdgpu_keyframe_pack_pointcloud(self.ptr, kf_id, level, out.ctypes.data_as(_vp)))
+        return out
+
+    def take_reactivation_data(self, kf_id: int):
+        self._ck(self.L.lsdgpu_frame_take_reactivation_data(self.ptr, kf_id))
+
+    def reactivation_data(self, kf_id: int):
+        """(idepth_reAct, idepthVar_reAct, validity_reAct) of Frame::takeReActivationData (Frame.cpp:107-145)"""
+        a, b = np.zeros((self.h, self.w), np.float32), np.zeros((self.h, self.w), np.float32)
+        c = np.zeros((self.h, self.w), np.uint8)
+        self._ck(self.L.lsdgpu_frame_download_reactivation_data(self.ptr, kf_id, a.ctypes.data_as(_fp), b.ctypes.data_as(_fp),
+                                                                c.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return a, b, c
 
     def clear_good_mask(self, fid: int):
         self._ck(self.L.lsdgpu_frame_clear_good_mask(self.ptr, fid))
@@ -441,6 +516,10 @@ class DepthMap:
         assert a.dtype == HYP_DTYPE
         self.ctx._ck(self.ctx.L.lsdgpu_depth_set_hypotheses(self.ctx.ptr, kf_id, a.ctypes.data_as(C.POINTER(Hyp)),
                                                             int(reactivated), int(do_set_depth)))
+
+    def setFromExistingKF(self, kf_id: int):
+        """DepthMap::setFromExistingKF (DepthMap.cpp:920-962) from the keyframe's device-resident reactivation data"""
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_set_from_existing_kf(self.ctx.ptr, kf_id))
 
     def updateKeyframe(self, referenceFrames):
         a, p, n = self._ids(referenceFrames)

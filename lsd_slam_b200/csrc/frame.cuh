@@ -19,13 +19,37 @@ struct PyrPtrs {
 // One CTA = one 16x16 level-0 tile -> 8x8, 4x4, 2x2, 1x1 on levels 1..4 (w, h are multiples of 16,
 // SlamSystem.cpp:55).  The 2x2 box sum is exact in fp32 for u8-origin data and is
 // associated like the scalar loop (Frame.cpp:621-624).
-__global__ void __launch_bounds__(256) k_image_pyramid(const uint8_t* __restrict__ src, PyrPtrs p, int w, int h)
+// REMAP = true fuses UndistorterPTAM::undistort (util/Undistorter.cpp:380-410) in front: level 0 is gathered bilinearly from
+// the RAW (distorted, in_w wide) image through the remap tables, truncated to 8 bits exactly as the reference's
+// `data[idx] = float expression` does, and converted to float as Frame::Frame does (Frame.cpp:44-52) -- the undistorted u8 image
+// never exists in memory unless `undist` is given (parity hook / host consumers).
+__device__ __forceinline__ unsigned char undistortPixel(const uint8_t* __restrict__ raw, int in_w, float xx, float yy)
+{
+    if (xx < 0) return 0;
+    const int xxi = (int)xx, yyi = (int)yy;
+    xx -= xxi;
+    yy -= yyi;
+    const float xxyy = xx * yy;
+    const uint8_t* src = raw + xxi + yyi * in_w;
+    const float v = xxyy * src[1 + in_w] + (yy - xxyy) * src[in_w] + (xx - xxyy) * src[1] + (1 - xx - yy + xxyy) * src[0];
+    return (unsigned char)v;
+}
+template <bool REMAP>
+__global__ void __launch_bounds__(256) k_image_pyramid(const uint8_t* __restrict__ src, PyrPtrs p, int w, int h,
+                                                       const float* __restrict__ remapX = nullptr, const float* __restrict__ remapY = nullptr,
+                                                       int in_w = 0, uint8_t* __restrict__ undist = nullptr)
 {
     __shared__ float s0[16][17], s1[8][9], s2[4][5], s3[2][3];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int bx = blockIdx.x, by = blockIdx.y;
     const int x = bx * 16 + tx, y = by * 16 + ty;
-    float v = (float)src[y * w + x];
+    float v;
+    if (REMAP) {
+        const unsigned char u = undistortPixel(src, in_w, __ldg(remapX + y * w + x), __ldg(remapY + y * w + x));
+        if (undist) undist[y * w + x] = u;
+        v = (float)u;
+    } else
+        v = (float)src[y * w + x];
     p.l[0][y * w + x] = v;
     s0[ty][tx] = v;
     __syncthreads();
@@ -181,4 +205,12 @@ __global__ void __launch_bounds__(256) k_idepth_pyramid(PyrPtrs id, PyrPtrs var,
         int o = by * (w >> 4) + bx;
         id.l[4][o] = r.x; var.l[4][o] = r.y;
     }
+}
+
+// UndistorterPTAM::undistort alone (u8 -> u8), util/Undistorter.cpp:380-410
+__global__ void __launch_bounds__(256) k_undistort(const uint8_t* __restrict__ raw, int in_w, const float* __restrict__ remapX,
+                                                   const float* __restrict__ remapY, int n, uint8_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = undistortPixel(raw, in_w, __ldg(remapX + i), __ldg(remapY + i));
 }

@@ -45,6 +45,10 @@ struct FrameSlot {
     float4* permaPC = nullptr;           // permaRef: (x, y, z, colour) per level-4 point (Frame::setPermaRef)
     float* permaVar = nullptr;
     int permaNumPts = 0;
+    float* reactIdepth = nullptr;        // Frame::idepth_reAct / idepthVar_reAct / validity_reAct (Frame.cpp:107-145), device-resident
+    float* reactVar = nullptr;
+    uint8_t* reactValidity = nullptr;
+    bool reactAllocated = false, reactValid = false;
     CUtensorMap gradMap[LSD_LEVELS];     // TMA descriptors of grad[l] (float4 texels as 4 x f32), box = tracker window
     bool hasDepth = false, idepthPyrValid = false, hasGoodMask = false;
     bool depthHasBeenUpdatedFlag = false;
@@ -136,6 +140,13 @@ struct lsdgpu_ctx {
     void* dPermaResults = nullptr;
     void* dSim3Items = nullptr;          // batched Sim3 tracking: problem descriptors / results (device)
     void* dSim3Outs = nullptr;
+    float* dRemapX = nullptr;            // UndistorterPTAM remap tables (separate allocation), raw-image staging
+    float* dRemapY = nullptr;
+    uint8_t* dRaw = nullptr;
+    uint8_t* hRaw = nullptr;
+    int rawW = 0, rawH = 0;
+    bool undistorterSet = false;
+    uint32_t* dPacked = nullptr;         // keyframeMsg.pointcloud staging: w*h InputPointDense records (device)
     int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe

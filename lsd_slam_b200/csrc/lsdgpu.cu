@@ -8,6 +8,7 @@
 #include "track_persistent.cuh"
 #include "perma.cuh"
 #include "sim3.cuh"
+#include "output.cuh"
 
 #include <algorithm>
 #include <stdlib.h>
@@ -89,7 +90,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
                         + 2 * alignUp(n0 * 4, 256) + alignUp(n0 * 16, 256);              // prop head/next/val
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
-                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256)) * (size_t)max_frames + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024 + alignUp(S3_MAX_BATCH * sizeof(Sim3Item), 256) + alignUp(S3_MAX_BATCH * sizeof(Sim3Out), 256)
+                     + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256) + 2 * alignUp(n0 * 4, 256) + alignUp(n0, 256)) * (size_t)max_frames + alignUp(n0 * 12, 256) + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024 + alignUp(S3_MAX_BATCH * sizeof(Sim3Item), 256) + alignUp(S3_MAX_BATCH * sizeof(Sim3Out), 256)
                      + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
@@ -146,7 +147,11 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
         s.dStats = (double*)take(64);
         s.permaPC = (float4*)take((n0 >> 8) * 16);
         s.permaVar = (float*)take((n0 >> 8) * 4);
+        s.reactIdepth = (float*)take(n0 * 4);
+        s.reactVar = (float*)take(n0 * 4);
+        s.reactValidity = (uint8_t*)take(n0);
     }
+    ctx->dPacked = (uint32_t*)take(n0 * 12);
     ctx->dPermaItems = take(LSD_MAX_PERMA_BATCH * sizeof(PermaItem));
     ctx->dPermaResults = take(LSD_MAX_PERMA_BATCH * sizeof(PermaResult));
     ctx->dSim3Items = take(S3_MAX_BATCH * sizeof(Sim3Item));
@@ -187,6 +192,10 @@ extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->arena);
     if (ctx->stageRing) cudaFree(ctx->stageRing);
+    if (ctx->dRemapX) cudaFree(ctx->dRemapX);
+    if (ctx->dRemapY) cudaFree(ctx->dRemapY);
+    if (ctx->dRaw) cudaFree(ctx->dRaw);
+    if (ctx->hRaw) cudaFreeHost(ctx->hRaw);
     cudaFreeHost(ctx->hEvOut); cudaFreeHost(ctx->hStage[0]); cudaFreeHost(ctx->hStage[1]); cudaFreeHost(ctx->hStageF);
     cudaEventDestroy(ctx->stageDone[0]); cudaEventDestroy(ctx->stageDone[1]);
     cudaFreeHost(ctx->hScalars); cudaFreeHost(ctx->hTrackState);
@@ -257,13 +266,14 @@ static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
             fresh.parentId = -1; fresh.initialTrackedResidual = 0;
             fresh.numFramesTrackedOnThis = fresh.numMappedOnThis = 0;
             fresh.permaNumPts = 0;
+            fresh.reactAllocated = false; fresh.reactValid = false;
             c = fresh;
             return &c;
         }
     return nullptr;
 }
 
-static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc);
+static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc, bool remap = false);
 
 extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray)
 {
@@ -316,13 +326,14 @@ extern "C" int lsdgpu_frame_from_stage(lsdgpu_ctx* ctx, int frame_id, int index)
     return buildFrameFromDeviceU8(ctx, s, ctx->stageRing + (size_t)index * ctx->w * ctx->h);
 }
 
-static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc)
+static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc, bool remap)
 {
     const int w = ctx->w, h = ctx->h;
     const size_t n0 = (size_t)w * h;
     PyrPtrs pp;
     for (int l = 0; l < LSD_LEVELS; l++) pp.l[l] = s->image[l];
-    k_image_pyramid<<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(dsrc, pp, w, h);
+    if (remap) k_image_pyramid<true><<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(dsrc, pp, w, h, ctx->dRemapX, ctx->dRemapY, ctx->rawW, nullptr);
+    else k_image_pyramid<false><<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(dsrc, pp, w, h);
     LAUNCH(ctx);
     GradPtrs gp;
     for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }
@@ -1087,12 +1098,32 @@ extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, doub
     return setDepthOnKeyframe(ctx, nk);                            // :1311
 }
 
+// Frame::takeReActivationData(currentDepthMap), Frame.cpp:107-145.  The pool buffers of a fresh Frame are defined as
+// zero-filled; later takes of the same frame keep the entries of invalid pixels, as the reference does.
+static int takeReactivationData(lsdgpu_ctx* ctx, FrameSlot* kf)
+{
+    const int n = ctx->w * ctx->h;
+    if (!kf->reactAllocated) {
+        LSD_CHECK(ctx, cudaMemsetAsync(kf->reactIdepth, 0, (size_t)n * 4, ctx->stream));
+        LSD_CHECK(ctx, cudaMemsetAsync(kf->reactVar, 0, (size_t)n * 4, ctx->stream));
+        LSD_CHECK(ctx, cudaMemsetAsync(kf->reactValidity, 0, (size_t)n, ctx->stream));
+        kf->reactAllocated = true;
+    }
+    k_take_reactivation<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->cur, kf->reactIdepth, kf->reactVar, kf->reactValidity, n);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    kf->reactValid = true;
+    return 0;
+}
+
 extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
 {   // DepthMap::finalizeKeyFrame :1363-1395
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "finalizeKeyFrame: depth map is not valid");
-    return runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr, kf);   // :1373 + :1379 + setDepth :1385
+    int r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr, kf);   // :1373 + :1379 + setDepth :1385
+    if (r) return r;
+    return takeReactivationData(ctx, kf);                                // :1387 (calculateMeanInformation :1386 returns at once, Frame.cpp:178)
 }
 
 extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t* gray, int stage_index,
@@ -1399,4 +1430,208 @@ extern "C" int lsdgpu_sim3_track(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, c
                                  int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* out)
 {
     return lsdgpu_sim3_track_batch(ctx, 1, &ref_kf_id, &frame_id, frameToRef_init_qts, start_level, final_level, s, out);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// keyframe output formats
+// ------------------------------------------------------------------------------------------------------
+extern "C" int lsdgpu_keyframe_pack_pointcloud(lsdgpu_ctx* ctx, int kf_id, int publish_level, lsdgpu_input_point_dense* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (publish_level < 0 || publish_level >= LSD_LEVELS) return lsd_fail(ctx, "bad level");
+    int r = ensureIdepthPyramid(ctx, kf);                      // f->idepth(publishLvl), ROSOutput3DWrapper.cpp:96-97
+    if (r) return r;
+    const int n = (ctx->w >> publish_level) * (ctx->h >> publish_level);
+    k_pack_pointcloud<<<divUp(3 * n, 256), 256, 0, ctx->stream>>>(kf->idepth[publish_level], kf->idepthVar[publish_level],
+                                                                  kf->image[publish_level], n, ctx->dPacked);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    LSD_CHECK(ctx, cudaMemcpyAsync(out, ctx->dPacked, (size_t)n * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_take_reactivation_data(lsdgpu_ctx* ctx, int kf_id)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (ctx->activeKf != kf_id) return lsd_fail(ctx, "takeReActivationData: the keyframe is not the active one");
+    return takeReactivationData(ctx, kf);
+}
+
+extern "C" int lsdgpu_frame_download_reactivation_data(lsdgpu_ctx* ctx, int kf_id, float* idepth_reAct, float* idepthVar_reAct, uint8_t* validity_reAct)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (!kf->reactValid) return lsd_fail(ctx, "keyframe has no reactivation data");
+    const size_t n = (size_t)ctx->w * ctx->h;
+    if (idepth_reAct) LSD_CHECK(ctx, cudaMemcpyAsync(idepth_reAct, kf->reactIdepth, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (idepthVar_reAct) LSD_CHECK(ctx, cudaMemcpyAsync(idepthVar_reAct, kf->reactVar, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (validity_reAct) LSD_CHECK(ctx, cudaMemcpyAsync(validity_reAct, kf->reactValidity, n, cudaMemcpyDeviceToHost, ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_set_from_existing_kf(lsdgpu_ctx* ctx, int kf_id)
+{   // DepthMap::setFromExistingKF :920-962
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, kf_id);
+    if (!kf) return lsd_fail(ctx, "unknown keyframe id");
+    if (!kf->hasDepth) return lsd_fail(ctx, "setFromExistingKF: keyframe has no depth");          // assert(kf->hasIDepthBeenSet()), :922
+    if (!kf->reactValid) return lsd_fail(ctx, "setFromExistingKF: keyframe has no reactivation data");
+    const int n = ctx->w * ctx->h;
+    k_set_from_existing<<<divUp(n, 256), 256, 0, ctx->stream>>>(kf->reactIdepth, kf->reactVar, kf->reactValidity, ctx->cur, n);
+    LAUNCH(ctx);
+    LSD_CHECK(ctx, cudaGetLastError());
+    ctx->activeKf = kf_id; ctx->activeKfReactivated = true;                                       // :925, :935
+    kf->numMappedOnThis = 0; kf->numFramesTrackedOnThis = 0;                                      // :932-933
+    return runRegularize(ctx, false, VAL_SUM_MIN_FOR_KEEP);                                       // :961
+}
+
+// ------------------------------------------------------------------------------------------------------
+// input staging: UndistorterPTAM
+// ------------------------------------------------------------------------------------------------------
+// Output camera of UndistorterPTAM for the "crop" / "full" / explicit modes and the remap tables (Undistorter.cpp:171-317).
+// The expressions keep the reference's float / double mixing (int and 0.5 literals promote as written there); math calls on
+// float arguments use the float overloads.
+extern "C" int lsdgpu_undistorter_ptam_prepare(const float ic[5], int iw, int ih, const float ocIn[5], int ow, int oh,
+                                               float* remapX, float* remapY, float K_out[9])
+{
+    if (!ic || !ocIn || iw <= 0 || ih <= 0 || ow <= 0 || oh <= 0) return -2;
+    const float dist = ic[4];
+    const float d2t = 2.0f * tanf(dist / 2.0f);
+    float fx = ic[0] * iw, fy = ic[1] * ih;
+    float cx = (float)((double)(ic[2] * iw) - 0.5), cy = (float)((double)(ic[3] * ih) - 0.5);
+    // the reference rescales by in_width / in_width == 1.0 in double (:187-192): exact no-ops, including (c + 0.5) - 0.5
+    auto undistRadius = [&](float r) { return tanf(r * dist) / d2t; };
+    float ofx, ofy, ocx, ocy;
+    if (ic[4] == 0) {
+        ofx = ic[0] * ow; ofy = ic[1] * oh;
+        ocx = (float)((double)(ic[2] * ow) - 0.5); ocy = (float)((double)(ic[3] * oh) - 0.5);
+    } else if (ocIn[0] == -1 || ocIn[0] == -2) {
+        const float rl = cx / fx, rr = (iw - 1 - cx) / fx, rt = cy / fy, rb = (ih - 1 - cy) / fy;
+        const float sx = (float)ow / (float)iw, sy = (float)oh / (float)ih;
+        if (ocIn[0] == -1) {            // "crop": the axis-aligned extremes
+            const float tl = undistRadius(rl), tr = undistRadius(rr), tt = undistRadius(rt), tb = undistRadius(rb);
+            ofy = fy * ((rt + rb) / (tt + tb)) * sy;
+            ocy = (tt / rt) * ofy * cy / fy;
+            ofx = fx * ((rl + rr) / (tl + tr)) * sx;
+            ocx = (tl / rl) * ofx * cx / fx;
+        } else {                        // "full": the four corners
+            const float c_tl = sqrtf(rl * rl + rt * rt), c_tr = sqrtf(rr * rr + rt * rt);
+            const float c_bl = sqrtf(rl * rl + rb * rb), c_br = sqrtf(rr * rr + rb * rb);
+            const float u_tl = undistRadius(c_tl), u_tr = undistRadius(c_tr), u_bl = undistRadius(c_bl), u_br = undistRadius(c_br);
+            const float hor = fmaxf(c_br, c_tr) + fmaxf(c_bl, c_tl), vert = fmaxf(c_tr, c_tl) + fmaxf(c_bl, c_br);
+            const float uhor = fmaxf(u_br, u_tr) + fmaxf(u_bl, u_tl), uvert = fmaxf(u_tr, u_tl) + fmaxf(u_bl, u_br);
+            ofy = fy * ((vert) / (uvert)) * sy;
+            ocy = fmaxf(u_tl / c_tl, u_tr / c_tr) * ofy * cy / fy;
+            ofx = fx * ((hor) / (uhor)) * sx;
+            ocx = fmaxf(u_bl / c_bl, u_tl / c_tl) * ofx * cx / fx;
+        }
+    } else {
+        ofx = ocIn[0] * ow; ofy = ocIn[1] * oh;
+        ocx = (float)((double)(ocIn[2] * ow) - 0.5); ocy = (float)((double)(ocIn[3] * oh) - 0.5);
+    }
+    // outputCalibration (:268-272) and K_ as main_on_images.cpp:164-167 reads it back
+    const float oc0 = ofx / ow, oc1 = ofy / oh;
+    const float oc2 = (float)(((double)ocx + 0.5) / ow), oc3 = (float)(((double)ocy + 0.5) / oh);
+    if (K_out) {
+        for (int i = 0; i < 9; i++) K_out[i] = 0.f;
+        K_out[0] = oc0 * ow; K_out[4] = oc1 * oh;
+        K_out[2] = (float)((double)(oc2 * ow) - 0.5); K_out[5] = (float)((double)(oc3 * oh) - 0.5);
+        K_out[8] = 1.f;
+    }
+    if (remapX && remapY)
+        for (int y = 0; y < oh; y++)
+            for (int x = 0; x < ow; x++) {
+                float ix = (x - ocx) / ofx, iy = (y - ocy) / ofy;
+                const float r = sqrtf(ix * ix + iy * iy);
+                const float fac = (r == 0 || dist == 0) ? 1 : atanf(r * d2t) / (dist * r);
+                ix = fx * fac * ix + cx;
+                iy = fy * fac * iy + cy;
+                // "make rounding resistant" (:299-303; the last line assigns ix in the reference, kept)
+                if (ix == 0) ix = (float)0.01;
+                if (iy == 0) iy = (float)0.01;
+                if (ix == iw - 1) ix = (float)(iw - 1.01);
+                if (iy == ih - 1) ix = (float)(ih - 1.01);
+                const bool inside = ix > 0 && iy > 0 && ix < iw - 1 && iy < ih - 1;
+                remapX[x + y * ow] = inside ? ix : -1.f;
+                remapY[x + y * ow] = inside ? iy : -1.f;
+            }
+    return (ih == oh && iw == ow && ic[4] == 0) ? 1 : 0;
+}
+
+extern "C" int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const float* remapX, const float* remapY)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (in_width <= 0 || in_height <= 0) return lsd_fail(ctx, "bad input size");
+    const size_t n = (size_t)ctx->w * ctx->h, nr = (size_t)in_width * in_height;
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->dRemapX) { cudaFree(ctx->dRemapX); ctx->dRemapX = nullptr; }
+    if (ctx->dRemapY) { cudaFree(ctx->dRemapY); ctx->dRemapY = nullptr; }
+    if (ctx->dRaw) { cudaFree(ctx->dRaw); ctx->dRaw = nullptr; }
+    if (ctx->hRaw) { cudaFreeHost(ctx->hRaw); ctx->hRaw = nullptr; }
+    ctx->undistorterSet = false;
+    if (!remapX || !remapY) {
+        if (in_width != ctx->w || in_height != ctx->h) return lsd_fail(ctx, "pass-through undistorter needs input size == context size");
+    } else {
+        LSD_CHECK(ctx, cudaMalloc((void**)&ctx->dRemapX, n * 4));
+        LSD_CHECK(ctx, cudaMalloc((void**)&ctx->dRemapY, n * 4));
+        LSD_CHECK(ctx, cudaMemcpy(ctx->dRemapX, remapX, n * 4, cudaMemcpyHostToDevice));
+        LSD_CHECK(ctx, cudaMemcpy(ctx->dRemapY, remapY, n * 4, cudaMemcpyHostToDevice));
+    }
+    LSD_CHECK(ctx, cudaMalloc((void**)&ctx->dRaw, nr));
+    LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hRaw, nr, cudaHostAllocDefault));
+    ctx->rawW = in_width; ctx->rawH = in_height;
+    ctx->undistorterSet = true;
+    return 0;
+}
+
+static int uploadRaw(lsdgpu_ctx* ctx, const uint8_t* raw)
+{
+    if (!ctx->undistorterSet) return lsd_fail(ctx, "no undistorter installed (lsdgpu_set_undistorter)");
+    const size_t nr = (size_t)ctx->rawW * ctx->rawH;
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, raw) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) {
+        cudaGetLastError();
+        LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));          // the previous raw image may still be in flight
+        memcpy(ctx->hRaw, raw, nr);
+    }
+    LSD_CHECK(ctx, cudaMemcpyAsync(ctx->dRaw, pinned ? raw : ctx->hRaw, nr, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t* out)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    int r = uploadRaw(ctx, raw);
+    if (r) return r;
+    const int n = ctx->w * ctx->h;
+    if (!ctx->dRemapX) {                                              // result = image, Undistorter.cpp:370-375
+        LSD_CHECK(ctx, cudaMemcpyAsync(out, ctx->dRaw, n, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+        uint8_t* dOut = ctx->dStageU8[ctx->stageIdx];
+        LSD_CHECK(ctx, cudaEventSynchronize(ctx->stageDone[ctx->stageIdx]));
+        k_undistort<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->dRaw, ctx->rawW, ctx->dRemapX, ctx->dRemapY, n, dOut);
+        LAUNCH(ctx);
+        LSD_CHECK(ctx, cudaGetLastError());
+        LSD_CHECK(ctx, cudaMemcpyAsync(out, dOut, n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int lsdgpu_frame_upload_distorted_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* raw)
+{
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* s = acquireSlot(ctx, frame_id);
+    if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
+    int r = uploadRaw(ctx, raw);
+    if (r) return r;
+    return buildFrameFromDeviceU8(ctx, s, ctx->dRaw, ctx->dRemapX != nullptr);
 }

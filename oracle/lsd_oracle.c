@@ -307,6 +307,7 @@ struct lsdo_frame {
     float* idepthVar[LSDO_LEVELS];   int idepthVarValid[LSDO_LEVELS];
     int hasIDepthBeenSet, depthHasBeenUpdatedFlag;
     uint8_t* refPixelWasGood;
+    float* idepth_reAct; float* idepthVar_reAct; uint8_t* validity_reAct; int reActivationDataValid;   /* Frame.h data.*_reAct */
     int numMappablePixels;
     float meanIdepth; int numPoints;
     int numFramesTrackedOnThis, numMappedOnThis, numMappedOnThisTotal;
@@ -368,6 +369,7 @@ void lsdo_frame_destroy(lsdo_frame* f)
         free(f->image[l]); free(f->gradients[l]); free(f->maxGradients[l]); free(f->idepth[l]); free(f->idepthVar[l]);
     }
     free(f->refPixelWasGood);
+    free(f->idepth_reAct); free(f->idepthVar_reAct); free(f->validity_reAct);
     free(f);
 }
 
@@ -571,6 +573,52 @@ void lsdo_frame_setDepthFromGroundTruth(lsdo_frame* f, const float* depth, float
     f->idepthValid[0] = 1; f->idepthVarValid[0] = 1;
     frame_releaseIDepthPyr(f);
     f->hasIDepthBeenSet = 1;
+}
+
+/* Frame::takeReActivationData, DataStructures/Frame.cpp:107-145.  Pool buffers are defined zero-filled;
+ * entries of invalid pixels keep their previous content, as in the reference. */
+void lsdo_frame_takeReActivationData(lsdo_frame* f, const lsdo_hyp* depthMap)
+{
+    size_t n = (size_t)f->width[0]*f->height[0];
+    if (f->validity_reAct == 0) f->validity_reAct = (uint8_t*)calloc(n, 1);
+    if (f->idepth_reAct == 0) f->idepth_reAct = (float*)calloc(n, sizeof(float));
+    if (f->idepthVar_reAct == 0) f->idepthVar_reAct = (float*)calloc(n, sizeof(float));
+    float* id_pt = f->idepth_reAct; float* id_pt_max = f->idepth_reAct + n;
+    float* idv_pt = f->idepthVar_reAct; uint8_t* val_pt = f->validity_reAct;
+    for (; id_pt < id_pt_max; ++id_pt, ++idv_pt, ++val_pt, ++depthMap) {
+        if (depthMap->isValid) {
+            *id_pt = depthMap->idepth;
+            *idv_pt = depthMap->idepth_var;
+            *val_pt = depthMap->validity_counter;
+        } else if (depthMap->blacklisted < MIN_BLACKLIST) {
+            *idv_pt = -2;
+        } else {
+            *idv_pt = -1;
+        }
+    }
+    f->reActivationDataValid = 1;
+}
+const float* lsdo_frame_idepth_reAct(const lsdo_frame* f) { return f->idepth_reAct; }
+const float* lsdo_frame_idepthVar_reAct(const lsdo_frame* f) { return f->idepthVar_reAct; }
+const uint8_t* lsdo_frame_validity_reAct(const lsdo_frame* f) { return f->validity_reAct; }
+
+/* ROSOutput3DWrapper::publishKeyframe packing loop, IOWrapper/ROS/ROSOutput3DWrapper.cpp:91-110; InputPointDense
+ * {float idepth; float idepth_var; uchar color[4];} ROSOutput3DWrapper.h:34-39 (= keyframeMsg.pointcloud, 12 B per pixel) */
+void lsdo_pack_pointcloud(lsdo_frame* f, int publishLvl, void* out)
+{
+    int w = f->width[publishLvl], h = f->height[publishLvl];
+    struct { float idepth; float idepth_var; unsigned char color[4]; }* pc = out;
+    const float* idepth = lsdo_frame_idepth(f, publishLvl);
+    const float* idepthVar = lsdo_frame_idepthVar(f, publishLvl);
+    const float* color = lsdo_frame_image(f, publishLvl);
+    for (int idx = 0; idx < w*h; idx++) {
+        pc[idx].idepth = idepth[idx];
+        pc[idx].idepth_var = idepthVar[idx];
+        pc[idx].color[0] = color[idx];
+        pc[idx].color[1] = color[idx];
+        pc[idx].color[2] = color[idx];
+        pc[idx].color[3] = color[idx];
+    }
 }
 
 int   lsdo_frame_numMappablePixels(lsdo_frame* f) { lsdo_frame_maxGradients(f, 0); return f->numMappablePixels; }

@@ -176,6 +176,12 @@ int   lsdo_frame_numMappedOnThis(const lsdo_frame* f);
 void  lsdo_frame_set_counters(lsdo_frame* f, int tracked, int mapped);
 
 /* ---- TrackingReference point cloud (Tracking/TrackingReference.cpp:96-147) ---- */
+/* Frame::takeReActivationData (Frame.cpp:107-145) and the keyframeMsg packing loop (ROSOutput3DWrapper.cpp:91-110), SURVEY 8f row 4 */
+void  lsdo_frame_takeReActivationData(lsdo_frame* f, const lsdo_hyp* depthMap);
+const float* lsdo_frame_idepth_reAct(const lsdo_frame* f);
+const float* lsdo_frame_idepthVar_reAct(const lsdo_frame* f);
+const uint8_t* lsdo_frame_validity_reAct(const lsdo_frame* f);
+void  lsdo_pack_pointcloud(lsdo_frame* f, int publishLvl, void* out /* w_l*h_l records of 12 bytes */);
 /* returns numData[level]; out arrays sized w_l*h_l by the caller (NULL = skip) */
 int lsdo_make_point_cloud(lsdo_frame* kf, int level, float* posData /*3/pt*/, float* gradData /*2/pt*/,
                           float* colorAndVarData /*2/pt*/, int* pointPosInXYGrid);
@@ -192,6 +198,13 @@ int lsdo_sim3_eval(lsdo_frame* ref_kf, lsdo_frame* frame, int level, const doubl
                    float affine_a, float affine_b, const lsdo_track_settings* s, lsdo_sim3_eval_result* out);
 int lsdo_sim3_track(lsdo_frame* ref_kf, lsdo_frame* frame, const double frameToRef_init_qts[8],
                     int startLevel, int finalLevel, const lsdo_track_settings* s, lsdo_sim3_result* out);
+
+/* ---- UndistorterPTAM (util/Undistorter.cpp:171-317, 355-411), SURVEY 8f row 3.  outputCalibration[0] = -1 "crop", -2 "full";
+ * returns 0 tables valid, 1 undistort() is the identity (:370-375), -1 invalid ---- */
+int  lsdo_undistorter_ptam_prepare(const float inputCalibration[5], int in_width, int in_height, const float outputCalibration[5],
+                                   int out_width, int out_height, float* remapX, float* remapY, float K_out[9]);
+void lsdo_undistort(const float* remapX, const float* remapY, int in_width, int out_width, int out_height,
+                    const uint8_t* image, uint8_t* out);
 
 /* ---- permaRef tracking, SURVEY 8f row 2 (Frame.cpp:149-174, SE3Tracker.cpp:121-272) ---- */
 int   lsdo_frame_setPermaRef(lsdo_frame* kf, float* posData, float* colorAndVarData);      /* returns permaRefNumPts */

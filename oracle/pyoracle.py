@@ -28,6 +28,9 @@ HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, 3), ("blackliste
 assert HYP_DTYPE.itemsize == 32 and C.sizeof(Hyp) == 32
 
 
+POINT_DENSE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])     # InputPointDense
+
+
 class Globals(C.Structure):
     _fields_ = [("minUseGrad", C.c_float), ("cameraPixelNoise2", C.c_float), ("depthSmoothingFactor", C.c_float),
                 ("allowNegativeIdepths", C.c_int), ("useSubpixelStereo", C.c_int),
@@ -136,6 +139,11 @@ def lib(fast: bool = False):
     sig("lsdo_frame_numMappedOnThis", C.c_int, vp)
     sig("lsdo_frame_set_counters", None, vp, C.c_int, C.c_int)
     sig("lsdo_make_point_cloud", C.c_int, vp, C.c_int, fp, fp, fp, ip)
+    sig("lsdo_frame_takeReActivationData", None, vp, C.POINTER(Hyp))
+    sig("lsdo_frame_idepth_reAct", fp, vp)
+    sig("lsdo_frame_idepthVar_reAct", fp, vp)
+    sig("lsdo_frame_validity_reAct", u8p, vp)
+    sig("lsdo_pack_pointcloud", None, vp, C.c_int, vp)
     sig("lsdo_se3_eval", C.c_int, vp, vp, C.c_int, fp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.c_int, C.POINTER(EvalResult))
     sig("lsdo_se3_track", C.c_int, vp, vp, dp, C.POINTER(TrackSettings), C.POINTER(TrackResult))
     sig("lsdo_ldlt7_solve", C.c_int, fp, fp, fp)
@@ -145,6 +153,8 @@ def lib(fast: bool = False):
     sig("lsdo_sim3_pose_constants", None, dp, fp, fp, fp)
     sig("lsdo_sim3_eval", C.c_int, vp, vp, C.c_int, dp, C.c_float, C.c_float, C.POINTER(TrackSettings), C.POINTER(Sim3EvalResult))
     sig("lsdo_sim3_track", C.c_int, vp, vp, dp, C.c_int, C.c_int, C.POINTER(TrackSettings), C.POINTER(Sim3Result))
+    sig("lsdo_undistorter_ptam_prepare", C.c_int, fp, C.c_int, C.c_int, fp, C.c_int, C.c_int, fp, fp, fp)
+    sig("lsdo_undistort", None, fp, fp, C.c_int, C.c_int, C.c_int, u8p, u8p)
     sig("lsdo_frame_setPermaRef", C.c_int, vp, fp, fp)
     sig("lsdo_checkPermaRefOverlap", C.c_float, C.c_int, C.c_int, fp, fp, C.c_int, dp)
     sig("lsdo_trackFrameOnPermaref", C.c_int, C.c_int, C.c_int, fp, fp, C.c_int, vp, dp, C.POINTER(TrackResult))
@@ -237,6 +247,23 @@ class Frame:
     def idepthVar(self, level=0):
         return self._arr("idepthVar", level)
 
+    def reactivation_data(self):
+        """copies of (idepth_reAct, idepthVar_reAct, validity_reAct) (Frame.cpp:107-145) or None before the first take"""
+        p = self.L.lsdo_frame_idepthVar_reAct(self.ptr)
+        if not p:
+            return None
+        sh = (self.h, self.w)
+        return (np.ctypeslib.as_array(self.L.lsdo_frame_idepth_reAct(self.ptr), shape=sh).copy(),
+                np.ctypeslib.as_array(p, shape=sh).copy(),
+                np.ctypeslib.as_array(self.L.lsdo_frame_validity_reAct(self.ptr), shape=sh).copy())
+
+    def pack_pointcloud(self, level=0) -> np.ndarray:
+        """keyframeMsg.pointcloud as InputPointDense records (ROSOutput3DWrapper.cpp:91-110)"""
+        w, h = self.size(level)
+        out = np.zeros(w * h, POINT_DENSE)
+        self.L.lsdo_pack_pointcloud(self.ptr, level, out.ctypes.data_as(C.c_void_p))
+        return out
+
     def K(self, level=0):
         K = np.zeros(9, np.float32)
         Ki = np.zeros(9, np.float32)
@@ -298,6 +325,38 @@ class PermaRef:
         return r
 
 
+class UndistorterPTAM:
+    """util/Undistorter.cpp:91-411 with the calibration file's four lines already parsed.  out_calib: "crop", "full" or
+    (fx, fy, cx, cy, 0) relative to the output size."""
+
+    def __init__(self, in_calib, in_size, out_calib, out_size, fast: bool = False):
+        self.L = lib(fast)
+        self.in_w, self.in_h = in_size
+        self.out_w, self.out_h = out_size
+        ic = np.ascontiguousarray(in_calib, np.float32)
+        oc = np.zeros(5, np.float32)
+        if isinstance(out_calib, str):
+            oc[0] = {"crop": -1, "full": -2}[out_calib]
+        else:
+            oc[:] = out_calib
+        self.remapX = np.zeros((self.out_h, self.out_w), np.float32)
+        self.remapY = np.zeros((self.out_h, self.out_w), np.float32)
+        self.K = np.zeros(9, np.float32)
+        self.status = self.L.lsdo_undistorter_ptam_prepare(_fp(ic), self.in_w, self.in_h, _fp(oc), self.out_w, self.out_h,
+                                                           _fp(self.remapX), _fp(self.remapY), _fp(self.K))
+        self.K = self.K.reshape(3, 3)
+
+    def undistort(self, image_u8: np.ndarray) -> np.ndarray:
+        img = np.ascontiguousarray(image_u8, np.uint8)
+        assert img.shape == (self.in_h, self.in_w)
+        if self.status == 1:
+            return img.copy()
+        out = np.zeros((self.out_h, self.out_w), np.uint8)
+        u8p = C.POINTER(C.c_uint8)
+        self.L.lsdo_undistort(_fp(self.remapX), _fp(self.remapY), self.in_w, self.out_w, self.out_h, img.ctypes.data_as(u8p), out.ctypes.data_as(u8p))
+        return out
+
+
 def se3_track(kf: Frame, frame: Frame, init_frameToRef_qt, settings: TrackSettings | None = None) -> TrackResult:
     s = settings or default_track_settings()
     r = TrackResult()
@@ -355,8 +414,11 @@ class DepthMap:
         self._keep.append(f)
         self.L.lsdo_depthmap_initializeRandomly(self.ptr, f.ptr)
 
-    def setFromExistingKF(self, kf: Frame, idepth, idepthVar, validity):
+    def setFromExistingKF(self, kf: Frame, idepth=None, idepthVar=None, validity=None):
         self._keep.append(kf)
+        if idepth is None:                # the keyframe's own reactivation data, as DepthMap.cpp:926-928 reads them
+            self.L.lsdo_depthmap_setFromExistingKF(self.ptr, kf.ptr, None, None, None)
+            return
         a, b = np.ascontiguousarray(idepth, np.float32), np.ascontiguousarray(idepthVar, np.float32)
         c = np.ascontiguousarray(validity, np.uint8)
         self.L.lsdo_depthmap_setFromExistingKF(self.ptr, kf.ptr, _fp(a), _fp(b), c.ctypes.data_as(C.POINTER(C.c_uint8)))
