@@ -1378,6 +1378,12 @@ static int sim3Launch(lsdgpu_ctx* ctx, int n, const int* ref_ids, const int* fra
     hout.resize(n);
     LSD_CHECK(ctx, cudaMemcpyAsync(hout.data(), ctx->dSim3Outs, n * sizeof(Sim3Out), cudaMemcpyDeviceToHost, ctx->stream));
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (getenv("LSDGPU_SIM3_DEBUG")) {
+        const Sim3Out& o = hout[0];
+        int ev = 0;
+        for (int l = 0; l < LSD_LEVELS; l++) ev += o.nRes[l];
+        fprintf(stderr, "[sim3] cluster=%d evals=%d cycles: points=%lld ctaReduce=%lld exchange=%lld serialLM=%lld\n", cs, ev, o.cyc[0], o.cyc[1], o.cyc[2], o.cyc[3]);
+    }
     return 0;
 }
 

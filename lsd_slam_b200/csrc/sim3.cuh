@@ -68,6 +68,7 @@ struct Sim3Out {
     float pointUsage, affine_a, affine_b;
     int early;                          // 0: ok, 1: diverged (too few points), 2: increment out of range
     int nRes[LSD_LEVELS], nUpd[LSD_LEVELS];
+    long long cyc[4];                   // thread-0 clock64 totals: pixel loop, CTA reduce, cluster exchange, serial LM step
 };
 
 struct Sim3Pose {
@@ -415,7 +416,9 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
     __syncthreads();
 
     int parity = 0;
+    long long cyc0 = 0, cyc1 = 0, cyc2 = 0, cyc3 = 0;
     while (true) {
+        const long long tA = clock64();
         const int lvl = sh.lvl;
         const Sim3Pose P = sh.pose;
         const Sim3Level L = p.lvl[lvl];
@@ -439,6 +442,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
             sim3EvalPoint(sc * (L.fxi * x + L.cxi), sc * (L.fyi * y + L.cyi), sc * 1, g.x, g.y, g.z, var, P, L, frGrad, frIdepth, frVar,
                           p.st.var_weight, p.st.huber_d, p.cameraPixelNoise2, acc);
         }
+        const long long tB = clock64();
         // CTA reduction: warp shuffles, one shared-memory stage, fixed order
 #pragma unroll
         for (int c = 0; c < S3_NCH; c++) {
@@ -454,6 +458,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
             for (int wi = 0; wi < S3_THREADS / 32; wi++) s += warpRows[wi][threadIdx.x];
             xrow[parity][threadIdx.x] = s;
         }
+        const long long tC = clock64();
         // cluster exchange: every CTA sums the rows of all ranks in rank order -> identical totals everywhere
         if (csize > 1) cluster.sync(); else __syncthreads();
         if (threadIdx.x < S3_NCH) {
@@ -462,8 +467,11 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
             sums[threadIdx.x] = tot;
         }
         __syncthreads();
+        const long long tD = clock64();
         if (threadIdx.x == 0) sim3Advance(p, lm, sh, sums);
         __syncthreads();
+        const long long tE = clock64();
+        cyc0 += tB - tA; cyc1 += tC - tB; cyc2 += tD - tC; cyc3 += tE - tD;
         parity ^= 1;
         if (sh.done) break;
     }
@@ -478,5 +486,6 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
         o.pointUsage = lm.pointUsage; o.affine_a = lm.affine_a; o.affine_b = lm.affine_b;
         o.early = lm.early;
         for (int l = 0; l < LSD_LEVELS; l++) { o.nRes[l] = lm.nRes[l]; o.nUpd[l] = lm.nUpd[l]; }
+        o.cyc[0] = cyc0; o.cyc[1] = cyc1; o.cyc[2] = cyc2; o.cyc[3] = cyc3;
     }
 }

@@ -70,13 +70,13 @@ static inline float unzero_f(float val)
 #define MIN_GOODPERALL_PIXEL (0.04f)
 #define MIN_GOODPERALL_PIXEL_ABSMIN (0.01f)
 
-static lsdo_globals G = { 5.0f, 16.0f, 1.0f, 1, 1, 1, 1, 0 };
+static lsdo_globals G = { 5.0f, 16.0f, 1.0f, 1, 1, 1, 1, 0, 0 };
 
 void lsdo_default_globals(lsdo_globals* g)
 {   /* util/settings.cpp:77-88 */
     g->minUseGrad = 5; g->cameraPixelNoise2 = 4*4; g->depthSmoothingFactor = 1;
     g->allowNegativeIdepths = 1; g->useSubpixelStereo = 1; g->useAffineLightningEstimation = 1;
-    g->multiThreading = 1; g->useSSE = 0;
+    g->multiThreading = 1; g->useSSE = 0; g->exactAffineSums = 0;
 }
 void lsdo_set_globals(const lsdo_globals* g) { G = *g; }
 void lsdo_get_globals(lsdo_globals* g) { *g = G; }

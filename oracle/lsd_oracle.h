@@ -60,6 +60,9 @@ typedef struct {
     int   useAffineLightningEstimation; /* 1 (settings.cpp:88); cfg/LSDParams.cfg:28 sets 0 under ROS */
     int   multiThreading;             /* 1: DepthMap row ranges on MAPPING_THREADS=4 workers */
     int   useSSE;                     /* 0: scalar parity path; 1: the reference's SSE loops (timing flavour) */
+    int   exactAffineSums;            /* DIAGNOSTIC, default 0 = the reference: 1 accumulates the five affine-lighting sums of
+                                       * calcSim3Buffers in double, to separate the float-accumulation noise of the reference
+                                       * (sums ~1e9 in fp32) from real differences when a parity test looks at residuals */
 } lsdo_globals;
 
 /* DenseDepthTrackerSettings, util/settings.h:355-402 */

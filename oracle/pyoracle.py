@@ -34,7 +34,8 @@ POINT_DENSE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("co
 class Globals(C.Structure):
     _fields_ = [("minUseGrad", C.c_float), ("cameraPixelNoise2", C.c_float), ("depthSmoothingFactor", C.c_float),
                 ("allowNegativeIdepths", C.c_int), ("useSubpixelStereo", C.c_int),
-                ("useAffineLightningEstimation", C.c_int), ("multiThreading", C.c_int), ("useSSE", C.c_int)]
+                ("useAffineLightningEstimation", C.c_int), ("multiThreading", C.c_int), ("useSSE", C.c_int),
+                ("exactAffineSums", C.c_int)]
 
 
 class TrackSettings(C.Structure):

@@ -64,7 +64,7 @@ def test_sim3_eval_matches_oracle(oracle):
     ctx.close()
 
 
-def _check_track(got, want, tight=True):
+def _check_track(got, want, res_tol=2e-2):
     assert got.diverged == want.diverged
     assert list(got.numCalcResidualCalls) == list(want.numCalcResidualCalls)
     assert list(got.numCalcWarpUpdateCalls) == list(want.numCalcWarpUpdateCalls)
@@ -72,14 +72,26 @@ def _check_track(got, want, tight=True):
     assert dt <= POSE_TOL and ang <= POSE_TOL and ds <= POSE_TOL, (dt, ang, ds)
     H, Hw = np.array(got.lastSim3Hessian), np.array(want.lastSim3Hessian)
     assert np.abs(H - Hw).max() <= 1e-3 * np.abs(Hw).max()
-    # The residuals depend on the affine offset b = (sy - a sx) / sw, a difference of two ~1e7 float sums: the oracle adds
-    # 77k terms sequentially in float (as the reference does), the kernel in a tree, so b moves by ~1e-2 grey levels and
-    # the mean weighted residual by a few 1e-3 relative.  Pose, scale and iteration counts are unaffected (checked above).
     for f in ("lastResidual", "lastDepthResidual", "lastPhotometricResidual"):
-        assert abs(getattr(got, f) - getattr(want, f)) <= 5e-3 * abs(getattr(want, f)) + 1e-7, f
-    for f in ("pointUsage", "affineEstimation_a"):
-        assert abs(getattr(got, f) - getattr(want, f)) <= 1e-3 * abs(getattr(want, f)) + 1e-7, f
-    assert abs(got.affineEstimation_b - want.affineEstimation_b) <= 5e-2
+        assert abs(getattr(got, f) - getattr(want, f)) <= res_tol * abs(getattr(want, f)) + 1e-7, f
+    assert abs(got.pointUsage - want.pointUsage) <= 1e-3 * want.pointUsage
+    assert abs(got.affineEstimation_a - want.affineEstimation_a) <= 0.25 * res_tol
+    assert abs(got.affineEstimation_b - want.affineEstimation_b) <= 25 * res_tol
+
+
+def _oracle_track(oracle, ref, fr, init, lo=4, hi=1):
+    """-> (the reference's arithmetic, the same with the five affine-lighting sums accumulated in double).
+    calcSim3Buffers adds ~60k terms of ~1.6e4 into fp32 sums of ~1e9 (ulp 64): a_lastIt / b_lastIt carry that noise, it is
+    fed back through every accepted step and moves the final residuals by up to ~6e-3 relative -- the kernel's tree sums
+    do not have it.  Pose, scale, Hessian and iteration counts are checked against the reference arithmetic; the residuals
+    tightly against the exact-sum twin and loosely against the reference arithmetic."""
+    want = oracle.sim3_track(ref, fr, init, lo, hi)
+    oracle.set_globals(exactAffineSums=1)
+    try:
+        exact = oracle.sim3_track(ref, fr, init, lo, hi)
+    finally:
+        oracle.set_globals()
+    return want, exact
 
 
 def test_track_frame_sim3_matches_oracle(oracle):
@@ -87,9 +99,10 @@ def test_track_frame_sim3_matches_oracle(oracle):
     for ref, fr in ((0, 6), (6, 0)):
         init = _init(seq, fr, ref)
         est = trk.trackFrameSim3(ref, fr, init, 4, 1)
-        want = oracle.sim3_track(of[ref], of[fr], init, 4, 1)
+        want, exact = _oracle_track(oracle, of[ref], of[fr], init)
         assert not want.diverged and abs(want.frameToRef_qts[7] - 1) < 5e-3
         _check_track(trk.last, want)
+        _check_track(trk.last, exact, res_tol=5e-4)
         assert np.array_equal(est, np.array(trk.last.frameToRef_qts))
         assert np.allclose(trk.lastSim3Hessian, trk.lastSim3Hessian.T, rtol=1e-5)
     ctx.close()
@@ -100,13 +113,15 @@ def test_track_frame_sim3_scale_and_level_range(oracle):
     seq, ctx, trk, of = _setup(oracle)
     init = np.concatenate([seq.frame_to_ref_qt(12, 0), [1.0]])
     trk.trackFrameSim3(0, 12, init, 4, 1)
-    want = oracle.sim3_track(of[0], of[12], init, 4, 1)
+    want, exact = _oracle_track(oracle, of[0], of[12], init)
     assert abs(want.frameToRef_qts[7] - 1 / 1.05) < 5e-3
     _check_track(trk.last, want)
+    _check_track(trk.last, exact, res_tol=5e-4)
     trk.trackFrameSim3(0, 12, init, 3, 2)
-    want = oracle.sim3_track(of[0], of[12], init, 3, 2)
+    want, exact = _oracle_track(oracle, of[0], of[12], init, 3, 2)
     assert want.numCalcResidualCalls[4] == 0 and want.numCalcResidualCalls[1] == 0
     _check_track(trk.last, want)
+    _check_track(trk.last, exact, res_tol=5e-4)
     ctx.close()
 
 
@@ -150,5 +165,5 @@ def test_cluster_sizes_agree(oracle, monkeypatch):
     for cs in (1, 2, 4):
         assert list(out[cs].numCalcResidualCalls) == list(out[8].numCalcResidualCalls)
         dt, ang, ds = _sim3_err(out[cs].frameToRef_qts, out[8].frameToRef_qts)
-        assert max(dt, ang, ds) < 1e-5
+        assert max(dt, ang, ds) < POSE_TOL
     ctx.close()
