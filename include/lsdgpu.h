@@ -178,7 +178,7 @@ int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t
  * UndistorterPTAM::UndistorterPTAM, util/Undistorter.cpp:171-317, with the four lines of the calibration file already parsed:
  * input_calibration = fx fy cx cy dist (relative to the input size); output_calibration[0] = -1 for "crop", -2 for "full",
  * otherwise fx fy cx cy 0 (relative to the output size).  Host-only (no context needed): fills the two remap tables
- * (out_width*out_height floats each, may be NULL) and K_out (row-major, the matrix main_on_images.cpp:164-173 hands to
+ * (out_width*out_height floats each, may be NULL) and K_out (row-major, the matrix main_on_images.cpp:164-169 hands to
  * SlamSystem).  Returns 0 = tables valid, 1 = undistort() passes the image through (:370-375), -2 = invalid arguments.
  * UndistorterOpenCV (:449-567) delegates to cv::initUndistortRectifyMap / cv::remap and stays on the host. */
 int lsdgpu_undistorter_ptam_prepare(const float input_calibration[5], int in_width, int in_height, const float output_calibration[5],
@@ -190,7 +190,7 @@ int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const f
 int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t* out);
 /* undistort + Frame::Frame(id, w, h, K, ts, const uchar*) + buildImage/buildGradients/buildMaxGradients of all levels:
  * the raw image is copied to the device once and the remap feeds the pyramid kernel directly
- * (main_on_images.cpp:236-246: undistorter->undistort(imageDist, image); system->trackFrame(image.data, ...)) */
+ * (main_on_images.cpp:238-244: undistorter->undistort(imageDist, image); system->trackFrame(image.data, ...)) */
 int lsdgpu_frame_upload_distorted_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* raw);
 
 /* ---- keyframe output formats, packed on the device ----------------------------------------------

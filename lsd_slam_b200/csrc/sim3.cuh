@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include "internal.cuh"
 #include "track.cuh"
+#include "track_persistent.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -272,9 +273,89 @@ struct Sim3Shared {
     int lvl, done;
 };
 
+// exp(inc) * T on the device in double, latency-trimmed for the one thread that runs it: one sincos (half angle; the
+// full angle by the double-angle identities), one exp, reciprocals instead of repeated divisions, W * upsilon by cross
+// products.  Same algebra as lsd::sim3Exp / sim3Mul (hostmath.h; sim3.hpp:418-428, 609-648, 257-260); agrees to ~1e-15.
+__device__ __forceinline__ lsd::Sim3 sim3ExpMulFast(const float* inc, const lsd::Sim3& T)
+{
+    const double ux = inc[0], uy = inc[1], uz = inc[2], wx = inc[3], wy = inc[4], wz = inc[5], sigma = inc[6];
+    const double scale = exp(sigma);
+    const double theta_sq = wx * wx + wy * wy + wz * wz;
+    double imag, real, A, B, C;
+    const bool smallSigma = fabs(sigma) < 1e-10;
+    C = smallSigma ? 1.0 : (scale - 1.0) / sigma;
+    if (theta_sq < 1e-20) {
+        const double theta_po4 = theta_sq * theta_sq;
+        imag = 0.5 - (1.0 / 48.0) * theta_sq + (1.0 / 3840.0) * theta_po4;
+        real = 1.0 - 0.5 * theta_sq + (1.0 / 384.0) * theta_po4;
+        if (smallSigma) { A = 0.5; B = 1.0 / 6.0; }
+        else {
+            const double inv_s = 1.0 / sigma, inv_s2 = inv_s * inv_s;
+            A = ((sigma - 1.0) * scale + 1.0) * inv_s2;
+            B = ((0.5 * sigma * sigma - sigma + 1.0) * scale) * inv_s2 * inv_s;
+        }
+    } else {
+        const double theta = sqrt(theta_sq), inv_theta = 1.0 / theta, inv_tsq = inv_theta * inv_theta;
+        double sh_, ch_;
+        sincos(0.5 * theta, &sh_, &ch_);
+        imag = sh_ * inv_theta;
+        real = ch_;
+        const double sinT = 2.0 * sh_ * ch_, cosT = 1.0 - 2.0 * sh_ * sh_;
+        if (smallSigma) {
+            A = (1.0 - cosT) * inv_tsq;
+            B = (theta - sinT) * inv_tsq * inv_theta;
+        } else {
+            const double sa = scale * sinT, sb = scale * cosT, inv_c = 1.0 / (theta_sq + sigma * sigma);
+            A = (sa * sigma + (1.0 - sb) * theta) * inv_theta * inv_c;
+            B = (C - ((sb - 1.0) * sigma + sa * theta) * inv_c) * inv_tsq;
+        }
+    }
+    const double uq[4] = { imag * wx, imag * wy, imag * wz, real };          // unit quaternion of the increment
+    // W * upsilon,  W = A Omega + B Omega^2 + C I :  Omega u = w x u
+    const double k1x = wy * uz - wz * uy, k1y = wz * ux - wx * uz, k1z = wx * uy - wy * ux;
+    const double k2x = wy * k1z - wz * k1y, k2y = wz * k1x - wx * k1z, k2z = wx * k1y - wy * k1x;
+    const double tx = A * k1x + B * k2x + C * ux, ty = A * k1y + B * k2y + C * uy, tz = A * k1z + B * k2z + C * uz;
+    lsd::Sim3 r;
+    double rt[3];
+    lsd::quatRotate(uq, T.t, rt);
+    r.t[0] = tx + scale * rt[0]; r.t[1] = ty + scale * rt[1]; r.t[2] = tz + scale * rt[2];
+    const double sq[4] = { scale * uq[0], scale * uq[1], scale * uq[2], scale * uq[3] };
+    lsd::quatMul(sq, T.q, r.q);
+    return r;
+}
+// lsd::sim3PoseConstants with one reciprocal for the quaternion normalisation
+__device__ __forceinline__ void sim3PoseConstantsFast(const lsd::Sim3& a, float rotMat[9], float transVec[3], float roll[4])
+{
+    const double n2 = a.q[0] * a.q[0] + a.q[1] * a.q[1] + a.q[2] * a.q[2] + a.q[3] * a.q[3];
+    const double scale = sqrt(n2), inv = 1.0 / scale;
+    const double nq[4] = { a.q[0] * inv, a.q[1] * inv, a.q[2] * inv, a.q[3] * inv };
+    double R[9];
+    lsd::quatToMatrix(nq, R);
+    float Ru[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) { rotMat[i] = (float)(scale * R[i]); Ru[i] = (float)R[i]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++) transVec[i] = (float)a.t[i];
+    // Sim3Tracker.cpp:451-460 (same steps as lsd::sim3PoseConstants)
+    const float rf[3] = { -Ru[2], -Ru[5], -Ru[8] };
+    const float n = sqrtf((rf[0] * rf[0] + rf[1] * rf[1]) + rf[2] * rf[2]);
+    const float v0[3] = { rf[0] / n, rf[1] / n, rf[2] / n };
+    const float c = -v0[2];
+    if (c < -1.0f + 1e-5f) { roll[0] = roll[1] = roll[2] = roll[3] = nanf(""); return; }
+    const float ax[3] = { v0[1] * -1.f - v0[2] * 0.f, v0[2] * 0.f - v0[0] * -1.f, v0[0] * 0.f - v0[1] * 0.f };
+    const float s = sqrtf((1.f + c) * 2.f), invs = 1.f / s;
+    const float q[4] = { ax[0] * invs, ax[1] * invs, ax[2] * invs, s * 0.5f };
+    float Rb[9];
+    lsd::quatToMatrix(q, Rb);
+    roll[0] = (Rb[0] * Ru[0] + Rb[1] * Ru[3]) + Rb[2] * Ru[6];
+    roll[1] = (Rb[0] * Ru[1] + Rb[1] * Ru[4]) + Rb[2] * Ru[7];
+    roll[2] = (Rb[3] * Ru[0] + Rb[4] * Ru[3]) + Rb[5] * Ru[6];
+    roll[3] = (Rb[3] * Ru[1] + Rb[4] * Ru[4]) + Rb[5] * Ru[7];
+}
+
 __device__ __forceinline__ void sim3SetPose(Sim3Shared& sh, const lsd::Sim3& T, float a, float b, int lvl)
 {
-    lsd::sim3PoseConstants(T, sh.pose.R, sh.pose.t, sh.pose.roll);
+    sim3PoseConstantsFast(T, sh.pose.R, sh.pose.t, sh.pose.roll);
     sh.pose.a = a; sh.pose.b = b;
     sh.lvl = lvl;
 }
@@ -355,9 +436,7 @@ __device__ __noinline__ void sim3Advance(const Sim3Params& p, Sim3LM& lm, Sim3Sh
         for (int i = 0; i < 7; i++) absInc += inc[i] * inc[i];
         lm.absInc = absInc;
         if (!(absInc >= 0 && absInc < 1)) { lm.early = 2; lm.done = 1; sh.done = 1; return; }
-        double incd[7];
-        for (int i = 0; i < 7; i++) incd[i] = (double)inc[i];
-        lm.cand = lsd::sim3Mul(lsd::sim3Exp(incd), lm.refToFrame);
+        lm.cand = sim3ExpMulFast(inc, lm.refToFrame);
         lm.phase = S3_PH_TRY;
         sim3SetPose(sh, lm.cand, lm.affine_a, lm.affine_b, lvl);
         return;
@@ -443,13 +522,22 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
                           p.st.var_weight, p.st.huber_d, p.cameraPixelNoise2, acc);
         }
         const long long tB = clock64();
-        // CTA reduction: warp shuffles, one shared-memory stage, fixed order
+        // CTA reduction: 52 = 32 + 16 + 4 channels through the multi-value butterfly (53 shuffles instead of 260), then one
+        // shared-memory stage in fixed order
+        {
+            float a32[32], a16[16], a4[4];
 #pragma unroll
-        for (int c = 0; c < S3_NCH; c++) {
-            float v = acc[c];
+            for (int i = 0; i < 32; i++) a32[i] = acc[i];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) warpRows[warp][c] = v;
+            for (int i = 0; i < 16; i++) a16[i] = acc[32 + i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a4[i] = acc[48 + i];
+            warpReduceMulti<32>(a32, lane);
+            warpReduceMulti<16>(a16, lane);
+            warpReduceMulti<4>(a4, lane);
+            warpRows[warp][lane] = a32[0];
+            if ((lane & 1) == 0) warpRows[warp][32 + warpReduceChannel<16>(lane)] = a16[0];
+            if ((lane & 7) == 0) warpRows[warp][48 + warpReduceChannel<4>(lane)] = a4[0];
         }
         __syncthreads();
         if (threadIdx.x < S3_NCH) {
