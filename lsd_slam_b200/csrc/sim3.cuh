@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
     __shared__ float warpRows[S3_THREADS / 32][S3_NCH];
     __shared__ float xrow[2][S3_NCH];          // this CTA's partial sums, double-buffered by evaluation parity
     __shared__ float sums[S3_NCH];
+    __shared__ int queue[S3_THREADS / 32][64];   // per-warp compaction queue of valid reference pixels
     const Sim3Item& it = items[prob];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
@@ -511,16 +512,45 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
 #pragma unroll
         for (int c = 0; c < S3_NCH; c++) acc[c] = 0.f;
         const int n = L.w * L.h;
-        for (int i = crank * S3_THREADS + threadIdx.x; i < n; i += csize * S3_THREADS) {
+        // Only ~40 % of the reference pixels carry a hypothesis (semi-dense map) and the per-point body is ~600 instructions:
+        // each warp first compacts the indices of its valid pixels into a small shared-memory queue and runs the body on
+        // full warps (same per-CTA compaction idea as k_observe).  The order is fixed by the data => still deterministic.
+        auto body = [&](int i) {
             const int x = i % L.w, y = i / L.w;
-            if (x < 1 || x >= L.w - 1 || y < 1 || y >= L.h - 1) continue;                 // TrackingReference.cpp:128-129
             const float idepth = __ldg(kfIdepth + i), var = __ldg(kfVar + i);
-            if (var <= 0 || idepth == 0) continue;                                         // :133
             const float4 g = __ldg(kfGrad + i);
-            const float sc = 1.0f / idepth;                                                // :135-136
+            const float sc = 1.0f / idepth;                                                // TrackingReference.cpp:135-136
             sim3EvalPoint(sc * (L.fxi * x + L.cxi), sc * (L.fyi * y + L.cyi), sc * 1, g.x, g.y, g.z, var, P, L, frGrad, frIdepth, frVar,
                           p.st.var_weight, p.st.huber_d, p.cameraPixelNoise2, acc);
+        };
+        int* q = queue[warp];
+        int qCount = 0;
+        for (int base = crank * S3_THREADS + warp * 32; base < n; base += csize * S3_THREADS) {      // warp-uniform trip count
+            const int i = base + lane;
+            bool valid = false;
+            if (i < n) {
+                const int x = i % L.w, y = i / L.w;
+                if (!(x < 1 || x >= L.w - 1 || y < 1 || y >= L.h - 1)) {                   // TrackingReference.cpp:128-129
+                    const float idepth = __ldg(kfIdepth + i), var = __ldg(kfVar + i);
+                    valid = !(var <= 0 || idepth == 0);                                    // :133
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, valid);
+            if (valid) q[qCount + __popc(m & ((1u << lane) - 1u))] = i;
+            qCount += __popc(m);
+            __syncwarp();
+            if (qCount >= 32) {
+                body(q[lane]);
+                __syncwarp();
+                const int rest = qCount - 32;
+                const int moved = lane < rest ? q[32 + lane] : 0;
+                __syncwarp();
+                if (lane < rest) q[lane] = moved;
+                qCount = rest;
+                __syncwarp();
+            }
         }
+        if (lane < qCount) body(q[lane]);
         const long long tB = clock64();
         // CTA reduction: 52 = 32 + 16 + 4 channels through the multi-value butterfly (53 shuffles instead of 260), then one
         // shared-memory stage in fixed order
