@@ -104,31 +104,79 @@ __device__ __forceinline__ float vmax3Img(const float* __restrict__ img, int t, 
     if (g1 < g2) g1 = g2;
     return (g1 < g3) ? g3 : g1;
 }
+// Level 0 is processed in 32x8 tiles (blockIdx.y == 0): |grad| of the tile + 1-cell halo is computed ONCE into shared
+// memory (1.33 evaluations per pixel instead of 9), then the vertical and the horizontal 3-max run on shared memory.
+// Cells are addressed by LINEAR index t = y*w + x, so the halo column x = -1 / x = w is the neighbouring row's last /
+// first pixel exactly as the reference's linear sweeps see it.  Levels 1..4 (blockIdx.y = level) only need the gradient.
+#define GR_TW 32
+#define GR_TH 8
 __global__ void __launch_bounds__(256) k_gradients(const __grid_constant__ GradPtrs p)
 {
     const int lvl = blockIdx.y;
     const int w = p.w[lvl], h = p.h[lvl];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w * h) return;
     const float* __restrict__ img = p.img[lvl];
+    if (lvl != 0) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= w * h) return;
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i >= w && i < w * (h - 1)) {
+            g.x = 0.5f * (img[i + 1] - img[i - 1]);
+            g.y = 0.5f * (img[i + w] - img[i - w]);
+            g.z = img[i];
+        }
+        p.grad[lvl][i] = g;
+        return;
+    }
+    __shared__ float ag[GR_TH + 2][GR_TW + 2];      // |grad| at linear index (y0 - 1 + r) * w + (x0 - 1 + c)
+    __shared__ float vm[GR_TH][GR_TW + 2];          // vertical 3-max (Frame.cpp:721-734)
+    const int tilesX = (w + GR_TW - 1) / GR_TW, tilesY = (h + GR_TH - 1) / GR_TH;
+    if ((int)blockIdx.x >= tilesX * tilesY) return;
+    const int x0 = (blockIdx.x % tilesX) * GR_TW, y0 = (blockIdx.x / tilesX) * GR_TH;
+    const int n = w * h;
+    for (int c = threadIdx.x; c < (GR_TH + 2) * (GR_TW + 2); c += 256) {
+        const int cx = c % (GR_TW + 2), cy = c / (GR_TW + 2);
+        const int gy = y0 - 1 + cy, gx = x0 - 1 + cx;
+        float v = 0.f;
+        if (gy >= 0 && gy < h && gx <= w) {
+            const int t = gy * w + gx;
+            if (t >= 0 && t < n) v = absGradImg(img, t, w, h);
+        }
+        ag[cy][cx] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < GR_TH * (GR_TW + 2); c += 256) {
+        const int cx = c % (GR_TW + 2), cy = c / (GR_TW + 2);
+        const int gy = y0 + cy, gx = x0 - 1 + cx;
+        const int t = gy * w + gx;
+        float v = 0.f;
+        if (gy < h && gx <= w && !(t < w + 1 || t >= w * (h - 1) - 1)) {
+            float g1 = ag[cy][cx], g2 = ag[cy + 1][cx], g3 = ag[cy + 2][cx];
+            if (g1 < g2) g1 = g2;
+            v = (g1 < g3) ? g3 : g1;
+        }
+        vm[cy][cx] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x % GR_TW, ty = threadIdx.x / GR_TW;
+    const int x = x0 + tx, y = y0 + ty;
+    if (x >= w || y >= h) return;
+    const int i = y * w + x;
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i >= w && i < w * (h - 1)) {
         g.x = 0.5f * (img[i + 1] - img[i - 1]);
         g.y = 0.5f * (img[i + w] - img[i - w]);
         g.z = img[i];
     }
-    p.grad[lvl][i] = g;
-    if (lvl == 0) {
-        float r;
-        if (i >= w + 1 && i < w * (h - 1) - 1) {
-            float g1 = vmax3Img(img, i - 1, w, h), g2 = vmax3Img(img, i, w, h), g3 = vmax3Img(img, i + 1, w, h);
-            if (g1 < g2) g1 = g2;
-            r = (g1 < g3) ? g3 : g1;
-        } else {
-            r = (i >= w && i < w * (h - 1)) ? sqrtf(g.x * g.x + g.y * g.y) : 0.f;   // cells w and w*(h-1)-1 keep the raw |grad|
-        }
-        p.maxgrad0[i] = r;
+    p.grad[0][i] = g;
+    float r;
+    if (i >= w + 1 && i < w * (h - 1) - 1) {        // horizontal 3-max (Frame.cpp:740-759)
+        float g1 = vm[ty][tx], g2 = vm[ty][tx + 1], g3 = vm[ty][tx + 2];
+        if (g1 < g2) g1 = g2;
+        r = (g1 < g3) ? g3 : g1;
+    } else {
+        r = (i >= w && i < w * (h - 1)) ? sqrtf(g.x * g.x + g.y * g.y) : 0.f;   // cells w and w*(h-1)-1 keep the raw |grad|
     }
+    p.maxgrad0[i] = r;
 }
 
 // Frame::setDepthFromGroundTruth, Frame.cpp:264-285

@@ -338,7 +338,8 @@ static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* 
     GradPtrs gp;
     for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }
     gp.maxgrad0 = s->maxgrad;
-    k_gradients<<<dim3(divUp((int)n0, 256), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);      // + maxGradients of level 0
+    // blockIdx.y = level; level 0 runs as 32x8 tiles, levels 1..4 linearly (their block counts are smaller than the tile count)
+    k_gradients<<<dim3(divUp(w, GR_TW) * divUp(h, GR_TH), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);      // + maxGradients of level 0
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     s->hasDepth = false; s->idepthPyrValid = false; s->hasGoodMask = false;
