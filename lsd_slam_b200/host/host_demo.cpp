@@ -4,6 +4,7 @@
 // Prints one line per tracked frame: "<id> qx qy qz qw tx ty tz good".
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "lsd_host.h"
@@ -12,7 +13,24 @@ using namespace lsd_slam;
 
 int main(int argc, char** argv)
 {
-    if (argc < 2) { std::fprintf(stderr, "usage: host_demo <frames.bin> [kf_every]\n"); return 2; }
+    if (argc < 2) { std::fprintf(stderr, "usage: host_demo <frames.bin> [kf_every] | host_demo --undistorter <calib.cfg> <tables.bin>\n"); return 2; }
+    if (std::string(argv[1]) == "--undistorter" && argc >= 4) {
+        // host-only (no GPU needed): parse a PTAM/ATAN calibration file as util/Undistorter.cpp:100-166 does, print K and the
+        // sizes, dump the remap tables for the parity test
+        UndistorterPTAM u(argv[2]);
+        std::printf("%d %d %d %d %d %d\n", u.isValid() ? 1 : 0, u.isPassThrough() ? 1 : 0, u.getInputWidth(), u.getInputHeight(),
+                    u.getOutputWidth(), u.getOutputHeight());
+        for (int i = 0; i < 9; i++) std::printf("%.9g ", u.getK().m[i]);
+        std::printf("\n");
+        if (u.isValid()) {
+            FILE* o = std::fopen(argv[3], "wb");
+            if (!o) return 2;
+            std::fwrite(u.remapTableX().data(), 4, u.remapTableX().size(), o);
+            std::fwrite(u.remapTableY().data(), 4, u.remapTableY().size(), o);
+            std::fclose(o);
+        }
+        return 0;
+    }
     const int kfEvery = argc > 2 ? std::atoi(argv[2]) : 0;
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) { std::perror("open"); return 2; }

@@ -1,6 +1,10 @@
 // lsd_host.cpp -- implementation of lsd_host.h over the C ABI.  See the header for the reference citations.
 #include "lsd_host.h"
 
+#include <cstdio>
+#include <fstream>
+#include <string>
+
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -64,12 +68,12 @@ void DeviceContext::check(int rc, const char* where) const
     if (rc != 0) throw LsdGpuError(std::string(where) + ": " + lsdgpu_last_error(ctx_));
 }
 
-Frame::Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f&, double timestamp, const unsigned char* image)
+Frame::Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f&, double timestamp, const unsigned char* image, bool distorted)
     : dev_(dev), id_(id), w_(width), h_(height), timestamp_(timestamp)
 {
     pose = new FramePoseStruct();
     pose->frameID = id;
-    dev_.check(lsdgpu_frame_upload_u8(dev_.raw(), id, image), "Frame::Frame");
+    dev_.check(distorted ? lsdgpu_frame_upload_distorted_u8(dev_.raw(), id, image) : lsdgpu_frame_upload_u8(dev_.raw(), id, image), "Frame::Frame");
 }
 Frame::~Frame()
 {
@@ -206,6 +210,51 @@ void Sim3Tracker::trackFrameSim3Batch(const std::vector<TrackingReference*>& ref
                "Sim3Tracker::trackFrameSim3Batch");
     frameToReference.resize(n);
     for (size_t i = 0; i < n; i++) frameToReference[i] = take(results[i]);
+}
+
+UndistorterPTAM::UndistorterPTAM(const char* configFileName)
+{   // parsing as Undistorter.cpp:100-166; everything after that is lsdgpu_undistorter_ptam_prepare (:171-317)
+    for (int i = 0; i < 9; i++) K_.m[i] = 0.f;
+    std::ifstream infile(configFileName);
+    if (!infile.good()) return;
+    std::string l1, l2, l3, l4;
+    std::getline(infile, l1); std::getline(infile, l2); std::getline(infile, l3); std::getline(infile, l4);
+    float probe[8];
+    if (std::sscanf(l1.c_str(), "%f %f %f %f %f %f %f %f", &probe[0], &probe[1], &probe[2], &probe[3], &probe[4], &probe[5], &probe[6], &probe[7]) == 8)
+        return;                                                        // OpenCV camera model (:70-79)
+    valid = std::sscanf(l1.c_str(), "%f %f %f %f %f", &inputCalibration[0], &inputCalibration[1], &inputCalibration[2],
+                        &inputCalibration[3], &inputCalibration[4]) == 5
+            && std::sscanf(l2.c_str(), "%d %d", &in_width, &in_height) == 2;
+    for (float& v : outputCalibration) v = 0.f;
+    bool none = false;
+    if (l3 == "crop") outputCalibration[0] = -1;
+    else if (l3 == "full") outputCalibration[0] = -2;
+    else if (l3 == "none") none = true;                                // "NO RECTIFICATION" (:138-141): explicit zeros
+    else if (std::sscanf(l3.c_str(), "%f %f %f %f %f", &outputCalibration[0], &outputCalibration[1], &outputCalibration[2],
+                         &outputCalibration[3], &outputCalibration[4]) != 5)
+        valid = false;
+    (void)none;
+    if (std::sscanf(l4.c_str(), "%d %d", &out_width, &out_height) != 2) valid = false;
+    if (!valid) return;
+    remapX.resize((size_t)out_width * out_height);
+    remapY.resize((size_t)out_width * out_height);
+    const int st = lsdgpu_undistorter_ptam_prepare(inputCalibration, in_width, in_height, outputCalibration, out_width, out_height,
+                                                   remapX.data(), remapY.data(), K_.m);
+    if (st < 0) { valid = false; return; }
+    passThrough = (st == 1);
+}
+
+void UndistorterPTAM::install(DeviceContext& dev) const
+{
+    if (!valid) throw LsdGpuError("UndistorterPTAM: invalid calibration");
+    if (dev.width() != out_width || dev.height() != out_height) throw LsdGpuError("UndistorterPTAM: output size differs from the device context");
+    dev.check(lsdgpu_set_undistorter(dev.raw(), in_width, in_height, passThrough ? nullptr : remapX.data(), passThrough ? nullptr : remapY.data()),
+              "UndistorterPTAM::install");
+}
+
+void UndistorterPTAM::undistort(DeviceContext& dev, const unsigned char* image, unsigned char* result) const
+{
+    dev.check(lsdgpu_undistort_u8(dev.raw(), image, result), "UndistorterPTAM::undistort");
 }
 
 DepthMap::DepthMap(DeviceContext& dev, int w, int h, const Matrix3f&) : dev_(dev), width_(w), height_(h)

@@ -87,7 +87,10 @@ struct FramePoseStruct {
 // DataStructures/Frame.h -- device-resident frame; host keeps the bookkeeping the callers read
 class Frame {
 public:
-    Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f& K, double timestamp, const unsigned char* image);
+    // `distorted` = true: `image` is the RAW camera image of the installed UndistorterPTAM's input size; undistortion is
+    // fused into the pyramid construction on the device (replaces undistort() + this constructor, main_on_images.cpp:238-244)
+    Frame(DeviceContext& dev, int id, int width, int height, const Matrix3f& K, double timestamp, const unsigned char* image,
+          bool distorted = false);
     ~Frame();
     Frame(const Frame&) = delete;
     int id() const { return id_; }
@@ -179,6 +182,34 @@ private:
     Sim3 take(const lsdgpu_sim3_result& r);
     DeviceContext& dev_;
     int width_, height_;
+};
+
+// util/Undistorter.h:96-160.  The ATAN/PTAM calibration file has four lines:
+//   fx fy cx cy dist   |   in_width in_height   |   "crop" / "full" / "none" / fx fy cx cy 0   |   out_width out_height
+// An OpenCV-model file (8 numbers on the first line, Undistorter.cpp:70-79) is rejected: that model stays on the host.
+class UndistorterPTAM {
+public:
+    explicit UndistorterPTAM(const char* configFileName);
+    // undistort a raw 8-bit image (in_width x in_height) on the device of `dev`, whose size must be the output size
+    void undistort(DeviceContext& dev, const unsigned char* image, unsigned char* result) const;
+    // install the tables so that Frame(dev, id, w, h, K, ts, rawImage, /*distorted=*/true) feeds raw images to the device
+    void install(DeviceContext& dev) const;
+    const Matrix3f& getK() const { return K_; }
+    int getOutputWidth() const { return out_width; }
+    int getOutputHeight() const { return out_height; }
+    int getInputWidth() const { return in_width; }
+    int getInputHeight() const { return in_height; }
+    bool isValid() const { return valid; }
+    bool isPassThrough() const { return passThrough; }
+    const std::vector<float>& remapTableX() const { return remapX; }
+    const std::vector<float>& remapTableY() const { return remapY; }
+
+private:
+    Matrix3f K_;
+    float inputCalibration[5], outputCalibration[5];
+    int out_width = 0, out_height = 0, in_width = 0, in_height = 0;
+    std::vector<float> remapX, remapY;
+    bool valid = false, passThrough = false;
 };
 
 // DepthEstimation/DepthMap.h

@@ -18,7 +18,8 @@ def test_host_adapter_compiles_and_links():
     for s in ("lsd_slam::SE3Tracker::trackFrame(lsd_slam::TrackingReference*, lsd_slam::Frame*, lsd_slam::SE3 const&)",
               "lsd_slam::DepthMap::updateKeyframe(std::deque<std::shared_ptr<lsd_slam::Frame>",
               "lsd_slam::DepthMap::createKeyFrame(lsd_slam::Frame*)",
-              "lsd_slam::Sim3Tracker::trackFrameSim3(lsd_slam::TrackingReference*, lsd_slam::Frame*, lsd_slam::Sim3 const&, int, int)"):
+              "lsd_slam::Sim3Tracker::trackFrameSim3(lsd_slam::TrackingReference*, lsd_slam::Frame*, lsd_slam::Sim3 const&, int, int)",
+              "lsd_slam::UndistorterPTAM::UndistorterPTAM(char const*)"):
         assert s in syms, s
 
 
@@ -48,3 +49,30 @@ def test_host_demo_matches_python_loop(tmp_path, seq_small, frames_small):
     assert np.allclose(rows[:, 1:8], py, atol=1e-9), np.abs(rows[:, 1:8] - py).max()
     assert rows[:, 8].all()
     ctx.close()
+
+
+def test_undistorter_config_file_parsing(tmp_path, oracle):
+    """lsd_slam::UndistorterPTAM(configFileName) of the C++ adapter (util/Undistorter.cpp:100-166) -- host-only, no GPU --
+    against the oracle's tables for the same four lines"""
+    from lsd_slam_b200 import build
+    build.build()
+    build.build_host()
+    fov = [0.535719308086809, 0.669566858850269, 0.493248545285398, 0.500408664348414, 0.897966326944875]
+    for mode, out in (("crop", (640, 480)), ("full", (320, 240)), ("0.6 0.8 0.5 0.5 0", (320, 240))):
+        cfg = tmp_path / "cam.cfg"
+        cfg.write_text(" ".join(repr(v) for v in fov) + "\n640 480\n" + mode + "\n%d %d\n" % out)
+        tables = tmp_path / "tables.bin"
+        r = subprocess.run([build.DEMO_OUT, "--undistorter", str(cfg), str(tables)], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 0, r.stderr
+        l1, l2 = r.stdout.strip().splitlines()
+        assert [int(v) for v in l1.split()] == [1, 0, 640, 480, out[0], out[1]]
+        oc = mode if mode in ("crop", "full") else [float(v) for v in mode.split()]
+        want = oracle.UndistorterPTAM(fov, (640, 480), oc, out)
+        K = np.array([float(v) for v in l2.split()], np.float32).reshape(3, 3)
+        assert np.array_equal(K, want.K)
+        t = np.fromfile(tables, np.float32).reshape(2, out[1], out[0])
+        assert t[0].tobytes() == want.remapX.tobytes() and t[1].tobytes() == want.remapY.tobytes()
+    # an OpenCV-model file (8 numbers on the first line) is not taken by the PTAM class
+    cfg.write_text("500 500 320 240 0.1 0.01 0 0\n640 480\ncrop\n640 480\n")
+    r = subprocess.run([build.DEMO_OUT, "--undistorter", str(cfg), str(tables)], capture_output=True, text=True, timeout=60)
+    assert r.stdout.split()[0] == "0"
