@@ -44,6 +44,38 @@ def compute(oracle, seq, frames):
     return out
 
 
+def compute_8f(oracle, seq, frames):
+    """Sim3 tracking, keyframe output formats, UndistorterPTAM"""
+    import zlib
+    out = {}
+    kfs = {}
+    for k in (0, 4):
+        f = oracle.Frame(k, frames[k][0], seq.K)
+        f.setDepthFromGroundTruth(frames[k][1])
+        kfs[k] = f
+    init = np.concatenate([seq.frame_to_ref_qt(4, 0), [1.02]])
+    init[4:7] += [0.01, -0.005, 0.004]
+    r = oracle.sim3_track(kfs[0], kfs[4], init, 4, 1)
+    out["sim3_frameToRef_qts"] = np.array(r.frameToRef_qts)
+    out["sim3_hessian"] = np.array(r.lastSim3Hessian, np.float32)
+    out["sim3_residuals"] = np.array([r.lastResidual, r.lastDepthResidual, r.lastPhotometricResidual, r.pointUsage,
+                                      r.affineEstimation_a, r.affineEstimation_b], np.float32)
+    out["sim3_calls"] = np.array([list(r.numCalcResidualCalls), list(r.numCalcWarpUpdateCalls)], np.int32)
+    dm = oracle.DepthMap(seq.w, seq.h, seq.K)
+    dm.initializeFromGTDepth(kfs[0])
+    dm.finalizeKeyFrame()
+    a, b, c = kfs[0].reactivation_data()
+    out["react_var_row120"] = b[120].copy()
+    out["react_validity_hist"] = np.bincount(c.ravel(), minlength=256).astype(np.int64)
+    out["pointcloud_l1_crc"] = np.array([zlib.crc32(kfs[0].pack_pointcloud(1).tobytes())], np.uint64)
+    u = oracle.UndistorterPTAM([0.535719308086809, 0.669566858850269, 0.493248545285398, 0.500408664348414, 0.897966326944875],
+                               (seq.w, seq.h), "crop", (seq.w, seq.h))
+    out["undist_K"] = u.K.copy()
+    out["undist_remapX_row60"] = u.remapX[60].copy()
+    out["undist_image_crc"] = np.array([zlib.crc32(u.undistort(frames[0][0]).tobytes())], np.uint64)
+    return out
+
+
 if __name__ == "__main__":
     sys.path.insert(0, ROOT)
     from lsd_slam_b200 import synth
@@ -54,4 +86,7 @@ if __name__ == "__main__":
     frames = {k: seq.render(k) for k in range(0, 6)}
     res = compute(pyoracle, seq, frames)
     np.savez_compressed(os.path.join(HERE, "oracle_320x240.npz"), **res)
+    print({k: v.shape for k, v in res.items()})
+    res = compute_8f(pyoracle, seq, frames)
+    np.savez_compressed(os.path.join(HERE, "oracle_8f_320x240.npz"), **res)
     print({k: v.shape for k, v in res.items()})

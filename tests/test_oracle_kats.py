@@ -85,3 +85,12 @@ def test_golden_fixture_reproduces(oracle, seq_small, frames_small):
     gold = np.load(GOLD)
     for k in gold.files:
         assert np.array_equal(gold[k], now[k]), k
+
+
+def test_golden_fixture_8f_reproduces(oracle, seq_small, frames_small):
+    """same for the SURVEY 8f rows (Sim3 tracking, re-activation data, keyframeMsg packing, UndistorterPTAM)"""
+    from tests.golden import make_golden
+    now = make_golden.compute_8f(oracle, seq_small, frames_small)
+    gold = np.load(os.path.join(os.path.dirname(GOLD), "oracle_8f_320x240.npz"))
+    for k in gold.files:
+        assert np.array_equal(gold[k], now[k]), k
