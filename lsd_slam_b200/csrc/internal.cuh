@@ -215,3 +215,65 @@ __device__ __forceinline__ float interpF(const float* __restrict__ mat, float x,
     const float* bp = mat + ix + iy * width;
     return dxdy * __ldg(bp + 1 + width) + (dy - dxdy) * __ldg(bp + width) + (dx - dxdy) * __ldg(bp + 1) + (1 - dx - dy + dxdy) * __ldg(bp);
 }
+
+// Frame::prepareForStereoWith, DataStructures/Frame.cpp:295-317 (double -> float like the reference).  Host and
+// device: the same IEEE operations, so k_prepare_observe produces bit-identical constants on the GPU.
+LSD_HD void prepareStereoConsts(const float K[9], const double q[4], const double t[3], const double s, RefConst& rc)
+{
+    double qi[4] = { -q[0], -q[1], -q[2], q[3] };
+    const double si = 1.0 / s;
+    double nt[3] = { t[0] * -1.0, t[1] * -1.0, t[2] * -1.0 }, rt[3];
+    lsd::quatRotate(qi, nt, rt);
+    const double oTt[3] = { si * rt[0], si * rt[1], si * rt[2] };      // otherToThis.translation()
+    double Ri[9], R[9];
+    lsd::quatToMatrix(qi, Ri);
+    lsd::quatToMatrix(q, R);
+    float Rif[9];
+    for (int i = 0; i < 9; i++) Rif[i] = (float)Ri[i];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            float kr = (K[i * 3 + 0] * Rif[0 * 3 + j] + K[i * 3 + 1] * Rif[1 * 3 + j]) + K[i * 3 + 2] * Rif[2 * 3 + j];
+            rc.K_otherToThis_R[i * 3 + j] = kr * (float)si;
+        }
+    for (int i = 0; i < 3; i++) rc.otherToThis_t[i] = (float)oTt[i];
+    for (int i = 0; i < 3; i++)
+        rc.K_otherToThis_t[i] = (K[i * 3 + 0] * rc.otherToThis_t[0] + K[i * 3 + 1] * rc.otherToThis_t[1]) + K[i * 3 + 2] * rc.otherToThis_t[2];
+    for (int i = 0; i < 3; i++) rc.thisToOther_t[i] = (float)t[i];
+    float tR[9];
+    for (int i = 0; i < 9; i++) tR[i] = (float)R[i] * (float)s;       // thisToOther_R
+    for (int i = 0; i < 3; i++) { rc.row0[i] = tR[i * 3 + 0]; rc.row1[i] = tR[i * 3 + 1]; rc.row2[i] = tR[i * 3 + 2]; }
+}
+
+// Device-side tail of SE3Tracker::trackFrame (SE3Tracker.cpp:473-485) + head of DepthMap::updateKeyframe
+// (DepthMap.cpp:1079-1105) for the frame that was just tracked on the active keyframe: turns the tracker's
+// device-resident result into the observe parameters, so that the mapping kernels can be enqueued behind the
+// tracking kernel without a host round trip.  Runs on the last thread of k_track_persistent.
+struct PrepareConsts {
+    float K[9];
+    int frameId, reactivated, kfNumTracked, kfNumMapped, W1, H1;
+    const float* image;
+    const uint8_t* goodMask;
+};
+__device__ __forceinline__ void devicePrepareObserve(const lsd::SE3<float>& T, int diverged, float lastResidual, float pointUsage,
+                                                     float goodCount, float badCount, const PrepareConsts& c,
+                                                     ObserveParams* __restrict__ OP, int* __restrict__ skip)
+{
+    *skip = diverged;
+    if (diverged) return;
+    const lsd::SE3<double> f2r = lsd::se3Cast<double>(lsd::se3Inverse(T));        // SE3Tracker.cpp:483-485
+    RefConst& rc = OP->refs[0];
+    prepareStereoConsts(c.K, f2r.q, f2r.t, 1.0, rc);
+    rc.initialTrackedResidual = lastResidual / pointUsage;                       // :482
+    rc.id = c.frameId;
+    rc.trackedOnActive = 1;
+    rc.image = c.image;
+    rc.goodMask = c.goodMask;
+    const bool trackingWasGood = goodCount / (c.W1 * c.H1) > 0.04f && goodCount / (goodCount + badCount) > 0.5f;   // :475-477
+    OP->nRefs = 1;
+    OP->byIdOffset = c.frameId; OP->byIdSize = 1; OP->byId[0] = 0;
+    OP->oldestIdx = 0; OP->newestIdx = 0;
+    OP->reactivated = c.reactivated;
+    OP->kfNumTracked = c.kfNumTracked + (trackingWasGood ? 1 : 0);               // :479-480
+    OP->kfNumMapped = c.kfNumMapped;
+}
+

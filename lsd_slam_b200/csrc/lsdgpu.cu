@@ -880,71 +880,9 @@ extern "C" int lsdgpu_depth_download_integral(lsdgpu_ctx* ctx, int32_t* out)
     return 0;
 }
 
-// Frame::prepareForStereoWith, DataStructures/Frame.cpp:295-317 (double -> float like the reference).  Host and
-// device: the same IEEE operations, so k_prepare_observe produces bit-identical constants on the GPU.
-LSD_HD void prepareStereoConsts(const float K[9], const double q[4], const double t[3], const double s, RefConst& rc)
-{
-    double qi[4] = { -q[0], -q[1], -q[2], q[3] };
-    const double si = 1.0 / s;
-    double nt[3] = { t[0] * -1.0, t[1] * -1.0, t[2] * -1.0 }, rt[3];
-    lsd::quatRotate(qi, nt, rt);
-    const double oTt[3] = { si * rt[0], si * rt[1], si * rt[2] };      // otherToThis.translation()
-    double Ri[9], R[9];
-    lsd::quatToMatrix(qi, Ri);
-    lsd::quatToMatrix(q, R);
-    float Rif[9];
-    for (int i = 0; i < 9; i++) Rif[i] = (float)Ri[i];
-    for (int i = 0; i < 3; i++)
-        for (int j = 0; j < 3; j++) {
-            float kr = (K[i * 3 + 0] * Rif[0 * 3 + j] + K[i * 3 + 1] * Rif[1 * 3 + j]) + K[i * 3 + 2] * Rif[2 * 3 + j];
-            rc.K_otherToThis_R[i * 3 + j] = kr * (float)si;
-        }
-    for (int i = 0; i < 3; i++) rc.otherToThis_t[i] = (float)oTt[i];
-    for (int i = 0; i < 3; i++)
-        rc.K_otherToThis_t[i] = (K[i * 3 + 0] * rc.otherToThis_t[0] + K[i * 3 + 1] * rc.otherToThis_t[1]) + K[i * 3 + 2] * rc.otherToThis_t[2];
-    for (int i = 0; i < 3; i++) rc.thisToOther_t[i] = (float)t[i];
-    float tR[9];
-    for (int i = 0; i < 9; i++) tR[i] = (float)R[i] * (float)s;       // thisToOther_R
-    for (int i = 0; i < 3; i++) { rc.row0[i] = tR[i * 3 + 0]; rc.row1[i] = tR[i * 3 + 1]; rc.row2[i] = tR[i * 3 + 2]; }
-}
 static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, RefConst& rc)
 {
     prepareStereoConsts(ctx->cam[0].K, fr->thisToParent, fr->thisToParent + 4, fr->thisToParent[7], rc);
-}
-
-// Device-side tail of SE3Tracker::trackFrame (SE3Tracker.cpp:473-485) + head of DepthMap::updateKeyframe
-// (DepthMap.cpp:1079-1105) for the frame that was just tracked on the active keyframe: turns the tracker's
-// device-resident result into the observe parameters, so that the mapping kernels can be enqueued behind the
-// tracking kernel without a host round trip.  One thread.
-struct PrepareConsts {
-    float K[9];
-    int frameId, reactivated, kfNumTracked, kfNumMapped, W1, H1;
-    const float* image;
-    const uint8_t* goodMask;
-};
-__global__ void k_prepare_observe(const TrackState* __restrict__ ts, PrepareConsts c, ObserveParams* __restrict__ OP, int* __restrict__ skip)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    *skip = ts->diverged;
-    if (ts->diverged) return;
-    lsd::SE3<float> T;
-    for (int i = 0; i < 4; i++) T.q[i] = ts->refToFrame[i];
-    for (int i = 0; i < 3; i++) T.t[i] = ts->refToFrame[4 + i];
-    const lsd::SE3<double> f2r = lsd::se3Cast<double>(lsd::se3Inverse(T));        // SE3Tracker.cpp:483-485
-    RefConst& rc = OP->refs[0];
-    prepareStereoConsts(c.K, f2r.q, f2r.t, 1.0, rc);
-    rc.initialTrackedResidual = ts->lastResidual / ts->pointUsage;               // :482
-    rc.id = c.frameId;
-    rc.trackedOnActive = 1;
-    rc.image = c.image;
-    rc.goodMask = c.goodMask;
-    const bool trackingWasGood = ts->goodCount / (c.W1 * c.H1) > 0.04f && ts->goodCount / (ts->goodCount + ts->badCount) > 0.5f;   // :475-477
-    OP->nRefs = 1;
-    OP->byIdOffset = c.frameId; OP->byIdSize = 1; OP->byId[0] = 0;
-    OP->oldestIdx = 0; OP->newestIdx = 0;
-    OP->reactivated = c.reactivated;
-    OP->kfNumTracked = c.kfNumTracked + (trackingWasGood ? 1 : 0);               // :479-480
-    OP->kfNumMapped = c.kfNumMapped;
 }
 
 static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
@@ -1137,9 +1075,10 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
     if (kf->depthHasBeenUpdatedFlag) { r = lsdgpu_ref_import(ctx, kf_id); if (r) return r; }     // SlamSystem.cpp:907-912
     FrameSlot* fr = findSlot(ctx, frame_id);
-    // Measured on B200 (A/B on one box, 640x480): the single-sync path is ~5 us per frame SLOWER than syncing after
-    // the tracking kernel and preparing the stereo constants on the host (the one-thread double-precision
-    // k_prepare_observe costs more than the host round trip it removes), so it is opt-in.
+    // LSDGPU_SINGLE_SYNC=1 (opt-in): the whole frame is enqueued back to back and the host synchronises once; the stereo
+    // constants of prepareForStereoWith are then computed by the tracking kernel's last thread.  Measured on B200 (A/B on
+    // one box, 640x480): 202.6 us per step against 202.0 us for the default (poll the tracking result, constants on the
+    // host) -- the 2.2 us of one-thread double-precision work at the kernel's tail cost what the round trip saves.
     const bool singleSync = getenv("LSDGPU_SINGLE_SYNC") && atoi(getenv("LSDGPU_SINGLE_SYNC")) == 1;
     if (singleSync && mode == 1 && !keyframe_change && ctx->activeKf == kf_id && fr) {
         // Whole frame enqueued back to back: tracking kernel, device-side prepareForStereoWith, observe, fill holes,
@@ -1149,16 +1088,14 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
         if (!s) { lsdgpu_default_track_settings(&ds); ds.maxItsPerLvl[4] = 0; s = &ds; }
         r = ensureIdepthPyramid(ctx, kf);
         if (r) return r;
-        r = trackPersistentEnqueue(ctx, kf, fr, init_qt, s);
-        if (r) return r;
         PrepareConsts pc;
         memcpy(pc.K, ctx->cam[0].K, 36);
         pc.frameId = frame_id; pc.reactivated = ctx->activeKfReactivated ? 1 : 0;
         pc.kfNumTracked = kf->numFramesTrackedOnThis; pc.kfNumMapped = kf->numMappedOnThis;
         pc.W1 = ctx->w >> SE3TRACKING_MIN_LEVEL; pc.H1 = ctx->h >> SE3TRACKING_MIN_LEVEL;
         pc.image = fr->image[0]; pc.goodMask = fr->goodMask;
-        k_prepare_observe<<<1, 32, 0, ctx->stream>>>((const TrackState*)ctx->dTrackState, pc, ctx->dObs, ctx->dSkipFlag);
-        LAUNCH(ctx);
+        r = trackPersistentEnqueue(ctx, kf, fr, init_qt, s, &pc);         // the kernel's last thread also writes ctx->dObs / dSkipFlag
+        if (r) return r;
         r = runObserve(ctx, &frame_id, 1, true, ctx->dSkipFlag);          // DepthMap.cpp:1127
         if (r) return r;
         const bool didSetDepth = !kf->depthHasBeenUpdatedFlag;            // :1150-1157

@@ -55,6 +55,10 @@ struct alignas(64) TrackParams {
     int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
     int clusterLocalMaxPixels;       // levels up to this size are evaluated per cluster (0: never; needs a cluster launch)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
+    int doPrepare;                   // 1: the last thread also turns the result into the observe parameters of the same frame
+    PrepareConsts prep;              //    (Frame::prepareForStereoWith + head of DepthMap::updateKeyframe), no host round trip
+    ObserveParams* obsOut;
+    int* skipOut;
 };
 
 // what the kernel hands back (block 0 writes it)
@@ -699,6 +703,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         for (int i = 0; i < 7; i++) outDev->refToFrame[i] = out->refToFrame[i];
         outDev->pointUsage = ev.pointUsage; outDev->goodCount = ev.goodCount; outDev->badCount = ev.badCount;
         outDev->lastResidual = lm.last_residual; outDev->diverged = lm.diverged;
+        if (p.doPrepare)
+            devicePrepareObserve(lm.refToFrame, lm.diverged, lm.last_residual, ev.pointUsage, ev.goodCount, ev.badCount, p.prep, p.obsOut, p.skipOut);
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
@@ -772,7 +778,7 @@ static void flushTrackProfile(lsdgpu_ctx* ctx)
 
 // enqueue the tracking kernel of one frame on the context's stream (no host synchronisation)
 static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const double init_qt[7],
-                                  const lsdgpu_track_settings* st)
+                                  const lsdgpu_track_settings* st, const PrepareConsts* prep = nullptr)
 {
     flushTrackProfile(ctx);
     TrackParams P;
@@ -803,6 +809,7 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     P.partials = ctx->evPartials;
     P.barrier = ctx->evCounter;
     { const char* bm = getenv("LSDGPU_BARRIER_MODE"); P.barrierMode = bm ? atoi(bm) : 1; }
+    if (prep) { P.doPrepare = 1; P.prep = *prep; P.obsOut = ctx->dObs; P.skipOut = ctx->dSkipFlag; }
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* dOutDev = (TrackState*)ctx->dTrackState;
 
