@@ -1231,4 +1231,5 @@ int lsdo_trackFrameOnPermaref(int w0, int h0, const float* permaPos, const float
 }
 
 #include "lsd_oracle_sim3.inc"
+#include "lsd_oracle_undistort.inc"
 #include "lsd_oracle_depth.inc"
