@@ -1,0 +1,323 @@
+"""A SECOND, independent restatement of parts of the reference in vectorised numpy (fp32 element ops are IEEE, no FMA),
+written from the reference text and not from oracle/*.c, to cross-check the C oracle where the reference itself cannot
+be run (parity is unpinned):
+
+  * regularizeDepthMapRow<occl>         DepthEstimation/DepthMap.cpp:758-848    -> bit-exact against the oracle
+  * regularizeDepthMapFillHolesRow      DepthEstimation/DepthMap.cpp:656-701    -> bit-exact
+  * buildRegIntegralBuffer              DepthEstimation/DepthMap.cpp:724-756    -> exact (integers)
+  * SE3Tracker one evaluation           Tracking/SE3Tracker.cpp:885-1029, 749-790, 1258-1299 + LGS6 -> sums to fp32 summation-order accuracy
+  * Sim3Tracker one evaluation          Tracking/Sim3Tracker.cpp:414-607, 748-856, 992-1047 + LGS4/6/7 -> same
+  * TrackingReference::makePointCloud   Tracking/TrackingReference.cpp:96-147   -> through the two evaluations
+"""
+import numpy as np
+import pytest
+
+from lsd_slam_b200 import synth
+
+F = np.float32
+
+
+def unzero(v):
+    """UNZERO, util/settings.h:34: double literals, result stored to float"""
+    d = v.astype(np.float64)
+    out = np.where(d < 0, np.where(d > -1e-10, -1e-10, d), np.where(d < 1e-10, 1e-10, d))
+    return out.astype(F)
+
+
+def _pad(a, r, fill=0):
+    return np.pad(a, r, constant_values=fill)
+
+
+def np_integral(hyp):
+    v = np.where(hyp["isValid"] > 0, hyp["validity_counter"], 0).astype(np.int32)
+    return np.cumsum(np.cumsum(v, axis=1, dtype=np.int32), axis=0, dtype=np.int32)
+
+
+def np_fill_holes(hyp, maxgrad, min_use_grad=5.0):
+    H, W = hyp.shape
+    out = hyp.copy()
+    valid = hyp["isValid"] > 0
+    val = np.where(valid, hyp["validity_counter"], 0).astype(np.int32)
+    pv, pvalid = _pad(val, 2), _pad(valid, 2, False)
+    pid, pvar = _pad(hyp["idepth"], 2), _pad(np.where(valid, hyp["idepth_var"], F(1)), 2, F(1))
+    vsum = np.zeros((H, W), np.int32)
+    sumId = np.zeros((H, W), F)
+    sumIv = np.zeros((H, W), F)
+    for dy in range(-2, 3):              # rows outer, columns inner: the order of the source loops (:679-688)
+        for dx in range(-2, 3):
+            sl = (slice(2 + dy, 2 + dy + H), slice(2 + dx, 2 + dx + W))
+            vsum += pv[sl]
+            m = pvalid[sl]
+            sumId = np.where(m, sumId + pid[sl] / pvar[sl], sumId)
+            sumIv = np.where(m, sumIv + F(1) / pvar[sl], sumIv)
+    yy, xx = np.mgrid[0:H, 0:W]
+    region = (xx >= 3) & (xx < W - 2) & (yy >= 3) & (yy < H - 2)
+    cand = region & ~valid & ~(maxgrad < F(min_use_grad))
+    create = cand & (((hyp["blacklisted"] >= -1) & (vsum > 30)) | (vsum > 100))        # MIN_BLACKLIST, VAL_SUM_MIN_FOR_CREATE / _UNBLACKLIST
+    with np.errstate(all="ignore"):
+        obs = unzero(sumId / sumIv)
+    out["isValid"][create] = 1
+    out["blacklisted"][create] = 0
+    out["validity_counter"][create] = 0
+    out["nextStereoFrameMinID"][create] = 0
+    out["idepth"][create] = obs[create]
+    out["idepth_var"][create] = F(0.5) * (F(0.5) * F(0.5))                             # VAR_RANDOM_INIT_INITIAL = 0.5f*MAX_VAR
+    out["idepth_smoothed"][create] = -1
+    out["idepth_var_smoothed"][create] = -1
+    return out, create
+
+
+def np_regularize(hyp, remove_occlusions, validity_th, depth_smoothing_factor=1.0):
+    H, W = hyp.shape
+    out = hyp.copy()
+    valid = hyp["isValid"] > 0
+    reg_dist_var = F(0.075) * F(0.075) * F(depth_smoothing_factor) * F(depth_smoothing_factor)
+    pvalid = _pad(valid, 2, False)
+    pid, pvar, pvc = _pad(hyp["idepth"], 2), _pad(hyp["idepth_var"], 2), _pad(hyp["validity_counter"], 2)
+    cid, cvar = hyp["idepth"], hyp["idepth_var"]
+    s = np.zeros((H, W), F); val_sum = np.zeros((H, W), F); s_ivar = np.zeros((H, W), F)
+    n_occ = np.zeros((H, W), np.int32); n_not = np.zeros((H, W), np.int32)
+    with np.errstate(all="ignore"):
+        for dx in range(-2, 3):          # dx outer, dy inner (:782-783)
+            for dy in range(-2, 3):
+                sl = (slice(2 + dy, 2 + dy + H), slice(2 + dx, 2 + dx + W))
+                sv, sid, svar = pvalid[sl], pid[sl], pvar[sl]
+                diff = sid - cid
+                far = (F(1.0) * F(1.0)) * diff * diff > svar + cvar
+                n_occ += (sv & far & (sid > cid)).astype(np.int32)
+                use = sv & ~far
+                val_sum = np.where(use, val_sum + pvc[sl].astype(F), val_sum)
+                n_not += use.astype(np.int32)
+                dist_fac = F(dx * dx + dy * dy) * reg_dist_var
+                ivar = F(1.0) / (svar + dist_fac)
+                s = np.where(use, s + sid * ivar, s)
+                s_ivar = np.where(use, s_ivar + ivar, s_ivar)
+        yy, xx = np.mgrid[0:H, 0:W]
+        centre = valid & (xx >= 2) & (xx < W - 2) & (yy >= 2) & (yy < H - 2)
+        fail = centre & (val_sum < F(validity_th))
+        occl = centre & ~fail & bool(remove_occlusions) & (n_occ > n_not)
+        ok = centre & ~fail & ~occl
+        out["isValid"][fail | occl] = 0
+        out["blacklisted"][fail] -= 1
+        out["idepth_smoothed"][ok] = unzero(s / s_ivar)[ok]
+        out["idepth_var_smoothed"][ok] = (F(1.0) / s_ivar)[ok]
+    return out
+
+
+def _mapped(oracle, seq, frames, n_updates=2):
+    kf = oracle.Frame(0, frames[0][0], seq.K)
+    dm = oracle.DepthMap(seq.w, seq.h, seq.K)
+    dm.initializeRandomly(kf)
+    keep = [kf]
+    for k in (4, 6)[:n_updates]:
+        f = oracle.Frame(k, frames[k][0], seq.K)
+        f.set_thisToParent(np.concatenate([seq.frame_to_ref_qt(k), [1.0]]), kf)
+        keep.append(f)
+        dm.updateKeyframe([f])
+    return kf, dm, keep
+
+
+def _same(a, b, fields=("isValid", "blacklisted", "validity_counter", "idepth", "idepth_var", "idepth_smoothed", "idepth_var_smoothed")):
+    va = a["isValid"] > 0
+    assert np.array_equal(va, b["isValid"] > 0)
+    assert np.array_equal(a["blacklisted"], b["blacklisted"])
+    for f in fields[2:]:
+        x, y = a[f][va], b[f][va]
+        assert x.tobytes() == y.tobytes(), f
+
+
+@pytest.mark.parametrize("occl,th", [(False, 24), (True, 24), (False, 100)])
+def test_regularize_bit_exact_against_second_restatement(oracle, seq_small, frames_small, occl, th):
+    kf, dm, keep = _mapped(oracle, seq_small, frames_small)
+    before = dm.current().copy()
+    assert (before["isValid"] > 0).sum() > 3000 and (before["blacklisted"] < 0).any()
+    dm.regularize(occl, th)
+    _same(np_regularize(before, occl, th), dm.current().copy())
+
+
+def test_fill_holes_and_integral_against_second_restatement(oracle, seq_small, frames_small):
+    kf, dm, keep = _mapped(oracle, seq_small, frames_small)
+    before = dm.current().copy()
+    # punch holes: drop a third of the hypotheses, blacklist some of them so that both creation thresholds are exercised
+    rng = np.random.default_rng(11)
+    drop = (before["isValid"] > 0) & (rng.random(before.shape) < 0.33)
+    before["isValid"][drop] = 0
+    before["blacklisted"][drop & (rng.random(before.shape) < 0.3)] = -3
+    dm.set_current(before)
+    want, created = np_fill_holes(before, kf.maxGradients(0))
+    dm.regularizeFillHoles()
+    assert np.array_equal(np.array(dm.integral()).reshape(before.shape), np_integral(before))
+    _same(want, dm.current().copy())
+    assert created.sum() > 500 and (created & (before["blacklisted"] < -1)).sum() > 5
+
+
+# ---- one tracker evaluation, SE3 and Sim3 ---------------------------------------------------------------------------
+def quat_R(q):
+    x, y, z, w = [np.float64(v) for v in q]
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def np_point_cloud(kf, level):
+    """makePointCloud: x outer, y inner; skips var <= 0 or idepth == 0 and the 1-px border"""
+    K, Ki = kf.K(level)
+    Ki = Ki.reshape(3, 3)
+    w, h = kf.size(level)
+    idepth, var, img, grad = kf.idepth(level), kf.idepthVar(level), kf.image(level), kf.gradients(level)
+    xs, ys = np.meshgrid(np.arange(1, w - 1), np.arange(1, h - 1), indexing="ij")      # x-outer order
+    xs, ys = xs.ravel(), ys.ravel()
+    keep = ~((var[ys, xs] <= 0) | (idepth[ys, xs] == 0))
+    xs, ys = xs[keep], ys[keep]
+    s = F(1.0) / idepth[ys, xs]
+    pos = np.stack([s * (Ki[0, 0] * xs.astype(F) + Ki[0, 2]), s * (Ki[1, 1] * ys.astype(F) + Ki[1, 2]), s * F(1)], 1).astype(F)
+    return pos, grad[ys, xs, :2].astype(F), img[ys, xs].astype(F), var[ys, xs].astype(F)
+
+
+def interp43(g, x, y):
+    ix, iy = x.astype(np.int32), y.astype(np.int32)
+    dx, dy = x - ix.astype(F), y - iy.astype(F)
+    dxdy = dx * dy
+    br, bl, tr, tl = g[iy + 1, ix + 1], g[iy + 1, ix], g[iy, ix + 1], g[iy, ix]
+    return (dxdy[:, None] * br + (dy - dxdy)[:, None] * bl + (dx - dxdy)[:, None] * tr + (F(1) - dx - dy + dxdy)[:, None] * tl).astype(F)
+
+
+def _warp(kf, frame, level, R, t):
+    pos, rgrad, col, var = np_point_cloud(kf, level)
+    K = frame.K(level)[0].reshape(3, 3)
+    w, h = frame.size(level)
+    W = ((R[None, :, 0] * pos[:, :1] + R[None, :, 1] * pos[:, 1:2]) + R[None, :, 2] * pos[:, 2:3]) + t[None, :]
+    with np.errstate(all="ignore"):
+        u = (W[:, 0] / W[:, 2]) * K[0, 0] + K[0, 2]
+        v = (W[:, 1] / W[:, 2]) * K[1, 1] + K[1, 2]
+    ok = (u > 1) & (v > 1) & (u < w - 2) & (v < h - 2)
+    return pos, rgrad, col, var, W, u, v, ok, K
+
+
+def seqsum(x):
+    """fp32 running sum in index order, as the reference's scalar loops accumulate"""
+    return np.cumsum(x.astype(F), dtype=F)[-1] if len(x) else F(0)
+
+
+def test_se3_evaluation_against_second_restatement(oracle, seq_small, frames_small):
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    fr = oracle.Frame(3, frames_small[3][0], seq_small.K)
+    lvl = 2
+    qt = seq_small.frame_to_ref_qt(3, 0)
+    r2f = np.zeros(7)
+    oracle.lib().lsdo_se3d_inverse(oracle._dp(qt), oracle._dp(r2f))
+    r2f32 = r2f.astype(F)
+    want = oracle.se3_eval(kf, fr, lvl, r2f32, 0.97, 1.5)
+
+    q = r2f32[:4] / np.sqrt((r2f32[:4].astype(np.float64) ** 2).sum()).astype(F)
+    R = quat_R(q).astype(F)
+    t = r2f32[4:].astype(F)
+    pos, rgrad, col, var, W, u, v, ok, K = _warp(kf, fr, lvl, R, t)
+    g = interp43(fr.gradients(lvl)[..., :3], u[ok], v[ok])
+    Wk, posk, vark = W[ok], pos[ok], var[ok]
+    c1 = F(0.97) * col[ok] + F(1.5)
+    res = c1 - g[:, 2]
+    good = res * res / (F(40 * 40) + F(0.25) * (g[:, 0] * g[:, 0] + g[:, 1] * g[:, 1])) < 1
+    assert want.warpedSize == ok.sum() and want.goodCount == good.sum() and want.badCount == (~good).sum()
+    usage = np.minimum(posk[:, 2] / Wk[:, 2], F(1))
+    assert abs(want.pointUsage - seqsum(usage) / F(len(pos))) <= 2e-6 * want.pointUsage
+    # weights (:749-790, cameraPixelNoise2 = 16, var_weight = 1, huber_d = 3)
+    px, py, pz = Wk.T
+    d = F(1) / posk[:, 2]
+    gx, gy = K[0, 0] * g[:, 0], K[1, 1] * g[:, 1]
+    g0 = (t[0] * pz - t[2] * px) / (pz * pz * d)
+    g1 = (t[1] * pz - t[2] * py) / (pz * pz * d)
+    drpdd = gx * g0 + gy * g1
+    w_p = F(1) / (F(16) + vark * drpdd * drpdd)
+    wr = np.abs(res * np.sqrt(w_p))
+    wh = np.abs(np.where(wr < F(1.5), F(1), F(1.5) / wr)).astype(F)
+    assert abs(want.meanWeightedRes - seqsum(wh * w_p * res * res) / F(ok.sum())) <= 1e-5 * want.meanWeightedRes
+    # Jacobian rows (:1276-1291) and LGS6 (A += J J^T w, b -= J r w, finish divides by N)
+    z, z2 = F(1) / pz, F(1) / (pz * pz)
+    J = np.stack([z * gx, z * gy, (-px * z2) * gx + (-py * z2) * gy,
+                  ((-px * py * z2) * gx).astype(np.float64) + (-(1.0 + (py * py * z2).astype(np.float64))) * gy,
+                  (1.0 + (px * px * z2).astype(np.float64)) * gx + ((px * py * z2) * gy).astype(np.float64),
+                  (-py * z) * gx + (px * z) * gy], 1).astype(F)
+    wgt = wh * w_p
+    A = np.array([[seqsum(J[:, i] * J[:, j] * wgt) for j in range(6)] for i in range(6)], F) / F(ok.sum())
+    b = -np.array([seqsum(J[:, i] * (res * wgt)) for i in range(6)], F) / F(ok.sum())
+    Aw, bw = np.array(want.A).reshape(6, 6), np.array(want.b)
+    assert np.abs(A - Aw).max() <= 2e-5 * np.abs(Aw).max()
+    assert np.abs(b - bw).max() <= 2e-5 * np.abs(bw).max() + 1e-4
+
+
+def test_sim3_evaluation_against_second_restatement(oracle, seq_small, frames_small):
+    kfs = {}
+    for k in (0, 4):
+        f = oracle.Frame(k, frames_small[k][0], seq_small.K)
+        f.setDepthFromGroundTruth(frames_small[k][1])
+        kfs[k] = f
+    lvl = 1
+    f2r = np.concatenate([seq_small.frame_to_ref_qt(4, 0), [1.03]])
+    r2f = np.zeros(8)
+    oracle.lib().lsdo_sim3d_inverse(oracle._dp(f2r), oracle._dp(r2f))
+    want = oracle.sim3_eval(kfs[0], kfs[4], lvl, r2f, 1.0, 0.0)
+
+    Ru = quat_R(r2f[:4])
+    R = (r2f[7] * Ru).astype(F)
+    t = r2f[4:7].astype(F)
+    pos, rgrad, col, var, W, u, v, ok, K = _warp(kfs[0], kfs[4], lvl, R, t)
+    g = interp43(kfs[4].gradients(lvl)[..., :3], u[ok], v[ok])
+    # roll of the unscaled rotation about the optical axis (:451-460): shortest rotation taking R*(0,0,-1) back to (0,0,-1)
+    fwd = np.array([0, 0, -1.0])
+    rf = Ru @ fwd
+    axis = np.cross(rf, fwd)
+    ang = np.arctan2(np.linalg.norm(axis), rf @ fwd)
+    if np.linalg.norm(axis) > 1e-12:
+        k = axis / np.linalg.norm(axis)
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        back = np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+    else:
+        back = np.eye(3)
+    roll = (back @ Ru).astype(F)
+    Wk, posk, vark, rg = W[ok], pos[ok], var[ok], rgrad[ok]
+    px, py, pz = Wk.T
+    gx = K[0, 0] * F(0.5) * (g[:, 0] + (roll[0, 0] * rg[:, 0] + roll[0, 1] * rg[:, 1]))
+    gy = K[1, 1] * F(0.5) * (g[:, 1] + (roll[1, 0] * rg[:, 0] + roll[1, 1] * rg[:, 1]))
+    rp = (F(1.0) * col[ok] + F(0.0)) - g[:, 2]
+    w, h = kfs[4].size(lvl)
+    idx_r = (u[ok] + F(0.5)).astype(np.int32), (v[ok] + F(0.5)).astype(np.int32)
+    fvar = kfs[4].idepthVar(lvl)[idx_r[1], idx_r[0]]
+    has_d = fvar > 0
+    rd = np.where(has_d, F(1) / pz - kfs[4].idepth(lvl)[idx_r[1], idx_r[0]], F(-1)).astype(F)
+    sv = np.where(has_d, fvar, F(-1)).astype(F)
+    assert want.warpedSize == ok.sum() and want.numTermsP == ok.sum() and want.numTermsD == has_d.sum()
+    d = F(1) / posk[:, 2]
+    with np.errstate(all="ignore"):
+        g0 = (t[0] * pz - t[2] * px) / (pz * pz * d)
+        g1 = (t[1] * pz - t[2] * py) / (pz * pz * d)
+        g2 = (pz - t[2]) / (pz * pz * d)
+        drpdd = gx * g0 + gy * g1
+        w_p = F(1) / (F(16) + vark * drpdd * drpdd)
+        w_d = F(1) / (sv + g2 * g2 * vark)
+        wrd, wrp = np.abs(rd * np.sqrt(w_d)), np.abs(rp * np.sqrt(w_p))
+        tot = np.where(has_d, wrd + wrp, wrp)
+        wh = np.abs(np.where(tot < F(3), F(1), F(3) / tot)).astype(F)
+    sumD, sumP = seqsum((wh * w_d * rd * rd)[has_d]), seqsum(wh * w_p * rp * rp)
+    assert abs(want.sumResD - sumD) <= 2e-5 * want.sumResD and abs(want.sumResP - sumP) <= 2e-5 * want.sumResP
+    assert abs(want.mean - (sumD + sumP) / F(has_d.sum() + ok.sum())) <= 2e-5 * want.mean
+    wp, wd = wh * w_p, np.where(has_d, wh * w_d, F(0)).astype(F)
+    z, z2 = F(1) / pz, F(1) / (pz * pz)
+    v6 = np.stack([z * gx, z * gy, (-px * z2) * gx + (-py * z2) * gy,
+                   ((-px * py * z2) * gx).astype(np.float64) + (-(1.0 + (py * py * z2).astype(np.float64))) * gy,
+                   (1.0 + (px * px * z2).astype(np.float64)) * gx + ((px * py * z2) * gy).astype(np.float64),
+                   (-py * z) * gx + (px * z) * gy], 1).astype(F)
+    v4 = np.stack([z2, z2 * py, -z2 * px, z], 1).astype(F)
+    A7 = np.zeros((7, 7), F); b7 = np.zeros(7, F)
+    A7[:6, :6] = [[seqsum(v6[:, i] * v6[:, j] * wp) for j in range(6)] for i in range(6)]
+    b7[:6] = [-seqsum(v6[:, i] * (rp * wp)) for i in range(6)]
+    remap = [2, 3, 4, 6]
+    for i in range(4):
+        b7[remap[i]] += -seqsum(v4[:, i] * (rd * wd))
+        for j in range(4):
+            A7[remap[i], remap[j]] += seqsum(v4[:, i] * v4[:, j] * wd)
+    Aw, bw = np.array(want.A).reshape(7, 7), np.array(want.b)
+    assert np.abs(A7 - Aw).max() <= 5e-5 * np.abs(Aw).max()
+    assert np.abs(b7 - bw).max() <= 5e-5 * np.abs(bw).max() + 1e-3 * np.sqrt(np.abs(Aw).max())
+    assert want.num_constraints == 2 * ok.sum()
