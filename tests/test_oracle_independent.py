@@ -8,6 +8,8 @@ be run (parity is unpinned):
   * SE3Tracker one evaluation           Tracking/SE3Tracker.cpp:885-1029, 749-790, 1258-1299 + LGS6 -> sums to fp32 summation-order accuracy
   * Sim3Tracker one evaluation          Tracking/Sim3Tracker.cpp:414-607, 748-856, 992-1047 + LGS4/6/7 -> same
   * TrackingReference::makePointCloud   Tracking/TrackingReference.cpp:96-147   -> through the two evaluations
+  * observeDepthRow / Create / Update, makeAndCheckEPL, doLineStereo, prepareForStereoWith (tests/restate_stereo.py,
+    pure Python with fp32 scalars, sampled pixels)                              -> bit-exact
 """
 import numpy as np
 import pytest
@@ -321,3 +323,60 @@ def test_sim3_evaluation_against_second_restatement(oracle, seq_small, frames_sm
     assert np.abs(A7 - Aw).max() <= 5e-5 * np.abs(Aw).max()
     assert np.abs(b7 - bw).max() <= 5e-5 * np.abs(bw).max() + 1e-3 * np.sqrt(np.abs(Aw).max())
     assert want.num_constraints == 2 * ok.sum()
+
+
+# ---- per-pixel stereo: observeDepthCreate / observeDepthUpdate / doLineStereo ------------------------------------------
+def _hyp_dict(h):
+    return {k: (h[k].item() if k in ("isValid", "blacklisted", "validity_counter") else F(h[k])) for k in h.dtype.names}
+
+
+def _cam(kf):
+    K, Ki = kf.K(0)
+    K, Ki = K.reshape(3, 3), Ki.reshape(3, 3)
+    return dict(fx=K[0, 0], fy=K[1, 1], cx=K[0, 2], cy=K[1, 2], fxi=Ki[0, 0], fyi=Ki[1, 1], cxi=Ki[0, 2], cyi=Ki[1, 2])
+
+
+@pytest.mark.parametrize("init", ["empty", "gt", "random"])
+def test_observe_depth_pixels_against_second_restatement(oracle, seq_small, frames_small, init):
+    """observeDepthRow on sampled pixels, pure-Python fp32 restatement vs the C oracle: every field bit for bit"""
+    from tests import restate_stereo as rs
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    dm = oracle.DepthMap(seq_small.w, seq_small.h, seq_small.K)
+    if init == "gt":
+        kf.setDepthFromGroundTruth(frames_small[0][1])
+        dm.initializeFromGTDepth(kf)
+        dm.regularize(False, 24)                    # gives idepth_smoothed / var_smoothed their filtered values
+    else:
+        dm.initializeRandomly(kf)
+        if init == "empty":
+            cur = dm.current().copy()
+            cur["isValid"] = 0
+            dm.set_current(cur)
+    k = 5
+    fr = oracle.Frame(k, frames_small[k][0], seq_small.K)
+    qts = np.concatenate([seq_small.frame_to_ref_qt(k), [1.0]])
+    fr.set_thisToParent(qts, kf)
+    before = dm.current().copy()
+    dm.observeDepth([fr])
+    after = dm.current().copy()
+
+    G = dict(minUseGrad=F(5.0), cameraPixelNoise2=F(16.0), useSubpixelStereo=True, allowNegativeIdepths=True)
+    ref = rs.Ref(seq_small.K, qts, fr.image(0), k, initial_tracked_residual=0.0, good_mask=None)
+    refs = dict(oldest=ref, newest=ref, by_id=[ref], offset=k)
+    state = dict(reactivated=False, numTracked=0, numMapped=0)
+    cam = _cam(kf)
+    img, grad, mg = kf.image(0), kf.gradients(0), kf.maxGradients(0)
+    rng = np.random.default_rng(5)
+    ys, xs = np.nonzero(mg[3:-3, 3:-3] >= 5.0)
+    pick = rng.choice(len(xs), 350, replace=False)
+    changed = 0
+    for x, y in zip(xs[pick] + 3, ys[pick] + 3):
+        got = rs.observe_pixel(cam, G, img, grad, mg, _hyp_dict(before[y, x]), int(x), int(y), refs, state)
+        want = after[y, x]
+        assert int(got["isValid"]) == int(want["isValid"]) and int(got["blacklisted"]) == int(want["blacklisted"]), (x, y)
+        if want["isValid"]:
+            assert int(got["validity_counter"]) == int(want["validity_counter"]), (x, y)
+            for f in ("idepth", "idepth_var", "idepth_smoothed", "idepth_var_smoothed", "nextStereoFrameMinID"):
+                assert F(got[f]).tobytes() == F(want[f]).tobytes(), (x, y, f, got[f], want[f])
+        changed += int(before[y, x].tobytes() != want.tobytes())
+    assert changed > 60
