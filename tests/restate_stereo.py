@@ -412,3 +412,71 @@ def observe_pixel(cam, G, kf_image, kf_grad, kf_maxgrad, hyp, x, y, refs, state)
             inc = F(inc * F(3))
         h["nextStereoFrameMinID"] = F(F(ref.id) + inc)
     return h
+
+
+def propagate_depth(cam, kf_image, new_image, new_maxgrad, hyp, new_to_old_qts, good_mask, min_use_grad=F(5.0)):
+    """DepthMap::propagateDepth, DepthEstimation/DepthMap.cpp:475-653 (before the std::swap): -> the new map as a structured
+    array.  new_to_old_qts = new_keyframe->pose->thisToParent_raw; good_mask = refPixelWasGoodNoCreate() or None."""
+    H, W = hyp.shape
+    out = hyp.copy()
+    out["isValid"] = 0
+    out["blacklisted"] = 0
+    fx, fy, cx, cy = cam["fx"], cam["fy"], cam["cx"], cam["cy"]
+    fxi, fyi, cxi, cyi = cam["fxi"], cam["fyi"], cam["cxi"], cam["cyi"]
+    # se3FromSim3 (util/SophusUtil.h:60-63: SE3(quaternion, translation), the constructor normalises) and .inverse() in double
+    q = np.asarray(new_to_old_qts[:4], D)
+    q = q / np.sqrt((q * q).sum())
+    R = quat_R64(q).T
+    t = -(R @ np.asarray(new_to_old_qts[4:7], D))
+    Rf = R.astype(F)
+    tf = np.array([F(v) for v in t], F)
+    flat_old = kf_image.reshape(-1)
+    ys, xs = np.nonzero(hyp["isValid"] > 0)
+    with np.errstate(all="ignore"):
+        for y, x in zip(ys.tolist(), xs.tolist()):
+            src = hyp[y, x]
+            ids = F(src["idepth_smoothed"])
+            p = [F(F(F(x) * fxi) + cxi), F(F(F(y) * fyi) + cyi), F(1.0)]
+            pn = [F(F(F(F(F(Rf[i, 0] * p[0]) + F(Rf[i, 1] * p[1])) + F(Rf[i, 2] * p[2])) / ids) + tf[i]) for i in range(3)]
+            nid = F(F(1.0) / pn[2])
+            u = F(F(F(pn[0] * nid) * fx) + cx)
+            v = F(F(F(pn[1] * nid) * fy) + cy)
+            if not (u > F(2.1) and v > F(2.1) and u < F(F(W) - F(3.1)) and v < F(F(H) - F(3.1))):
+                continue
+            nx, ny = int(F(u + F(0.5))), int(F(v + F(0.5)))
+            dgrad = new_maxgrad[ny, nx]
+            if good_mask is not None:
+                if not good_mask[y >> 1, x >> 1] or dgrad < min_use_grad:
+                    continue
+            else:
+                res = F(interp(new_image, u, v) - flat_old[x + y * W])
+                if F(F(res * res) / F(F(40.0) * F(40.0) + F(F(F(0.5) * F(0.5)) * dgrad) * dgrad)) > F(1.0) or dgrad < min_use_grad:
+                    continue
+            tgt = out[ny, nx]
+            r4 = F(nid / ids)
+            r4 = F(r4 * r4)
+            r4 = F(r4 * r4)
+            nvar = F(r4 * F(src["idepth_var"]))
+            valid = bool(tgt["isValid"])
+            if valid:
+                diff = F(F(tgt["idepth"]) - nid)
+                if F(F(F(1.0) * F(1.0)) * diff * diff) > F(nvar + F(tgt["idepth_var"])):
+                    if nid < F(tgt["idepth"]):
+                        continue
+                    valid = False
+            if not valid:
+                new = (nid, nvar, int(src["validity_counter"]))
+            else:
+                w = F(nvar / F(F(tgt["idepth_var"]) + nvar))
+                merged = F(F(w * F(tgt["idepth"])) + F(F(F(1.0) - w) * nid))
+                mv = int(src["validity_counter"]) + int(tgt["validity_counter"])
+                if mv > F(5.0) + F(250.0):
+                    mv = int(F(5.0) + F(250.0))
+                new = (merged, F(F(1.0) / F(F(F(1.0) / F(tgt["idepth_var"])) + F(F(1.0) / nvar))), mv)
+            out[ny, nx]["isValid"] = 1
+            out[ny, nx]["blacklisted"] = 0
+            out[ny, nx]["nextStereoFrameMinID"] = 0
+            out[ny, nx]["validity_counter"] = new[2]
+            out[ny, nx]["idepth"], out[ny, nx]["idepth_var"] = new[0], new[1]
+            out[ny, nx]["idepth_smoothed"], out[ny, nx]["idepth_var_smoothed"] = -1, -1
+    return out

@@ -380,3 +380,37 @@ def test_observe_depth_pixels_against_second_restatement(oracle, seq_small, fram
                 assert F(got[f]).tobytes() == F(want[f]).tobytes(), (x, y, f, got[f], want[f])
         changed += int(before[y, x].tobytes() != want.tobytes())
     assert changed > 60
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_propagate_depth_against_second_restatement(oracle, seq_small, frames_small, with_mask):
+    """DepthMap::propagateDepth (order-dependent raster scan with merge / occlusion handling), both admission tests:
+    the tracker's refPixelWasGood mask and the colour test for untracked frames"""
+    from tests import restate_stereo as rs
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    dm = oracle.DepthMap(seq_small.w, seq_small.h, seq_small.K)
+    dm.initializeFromGTDepth(kf)
+    dm.regularize(False, 24)
+    k = 9
+    nf = oracle.Frame(k, frames_small[k][0], seq_small.K)
+    if with_mask:
+        r = oracle.se3_track(kf, nf, np.array([0, 0, 0, 1, 0, 0, 0], np.float64))
+        assert not r.diverged
+        qts = nf.thisToParent()
+        mask = nf.refPixelWasGood().copy().astype(bool)
+        assert (~mask).sum() > 50                       # the mask really rejects some pixels
+    else:
+        qts = np.concatenate([seq_small.frame_to_ref_qt(k), [1.0]])
+        nf.set_thisToParent(qts, kf)
+        mask = None
+    before = dm.current().copy()
+    dm.propagateDepth(nf)
+    after = dm.current().copy()
+    want = rs.propagate_depth(_cam(kf), kf.image(0), nf.image(0), nf.maxGradients(0), before, qts, mask)
+    va = after["isValid"] > 0
+    assert np.array_equal(va, want["isValid"] > 0)
+    assert va.sum() > 5000
+    assert np.array_equal(after["blacklisted"], want["blacklisted"])
+    for f in ("validity_counter", "idepth", "idepth_var", "idepth_smoothed", "idepth_var_smoothed", "nextStereoFrameMinID"):
+        assert after[f][va].tobytes() == want[f][va].tobytes(), f
