@@ -10,6 +10,8 @@ be run (parity is unpinned):
   * TrackingReference::makePointCloud   Tracking/TrackingReference.cpp:96-147   -> through the two evaluations
   * observeDepthRow / Create / Update, makeAndCheckEPL, doLineStereo, prepareForStereoWith (tests/restate_stereo.py,
     pure Python with fp32 scalars, sampled pixels)                              -> bit-exact
+  * propagateDepth (tests/restate_stereo.py, all pixels, both admission tests)   DepthMap.cpp:475-653  -> bit-exact
+  * Frame::buildMaxGradients, setDepth, buildIDepthAndIDepthVar                  Frame.cpp:690-767, 199-243, 775-877 -> bit-exact
 """
 import numpy as np
 import pytest
@@ -414,3 +416,59 @@ def test_propagate_depth_against_second_restatement(oracle, seq_small, frames_sm
     assert np.array_equal(after["blacklisted"], want["blacklisted"])
     for f in ("validity_counter", "idepth", "idepth_var", "idepth_smoothed", "idepth_var_smoothed", "nextStereoFrameMinID"):
         assert after[f][va].tobytes() == want[f][va].tobytes(), f
+
+
+# ---- Frame builders ------------------------------------------------------------------------------------------------
+def np_max_gradients(grad, min_create=F(5.0)):
+    """Frame::buildMaxGradients, DataStructures/Frame.cpp:690-767: three LINEAR-index sweeps (x wraps across rows);
+    never-written cells are zero (pool buffers defined zero-filled)"""
+    h, w = grad.shape[:2]
+    n = w * h
+    g = grad.reshape(n, 4)
+    a = np.zeros(n, F)
+    a[w:n - w] = np.sqrt(g[w:n - w, 0] * g[w:n - w, 0] + g[w:n - w, 1] * g[w:n - w, 1])
+    t = np.zeros(n, F)
+    i = np.arange(w + 1, n - w - 1)
+    t[i] = np.maximum(np.maximum(a[i - w], a[i]), a[i + w])
+    out = a.copy()
+    out[i] = np.maximum(np.maximum(t[i - 1], t[i]), t[i + 1])
+    return out.reshape(h, w), int((out[i] >= min_create).sum())
+
+
+def np_idepth_level(idepth, var):
+    """Frame::buildIDepthAndIDepthVar for one level, DataStructures/Frame.cpp:775-877 (source order: tl, tr, bl, br)"""
+    h, w = idepth.shape[0] // 2, idepth.shape[1] // 2
+    isum = np.zeros((h, w), F); dsum = np.zeros((h, w), F); num = np.zeros((h, w), np.int32)
+    with np.errstate(all="ignore"):
+        for oy, ox in ((0, 0), (0, 1), (1, 0), (1, 1)):
+            v, d = var[oy::2, ox::2][:h, :w], idepth[oy::2, ox::2][:h, :w]
+            m = v > 0
+            ivar = F(1.0) / v
+            isum = np.where(m, isum + ivar, isum)
+            dsum = np.where(m, dsum + ivar * d, dsum)
+            num += m
+        depth = isum / dsum
+        oid = np.where(num > 0, F(1.0) / depth, F(-1)).astype(F)
+        ovar = np.where(num > 0, num.astype(F) / isum, F(-1)).astype(F)
+    return oid, ovar
+
+
+def test_frame_builders_against_second_restatement(oracle, seq_small, frames_small):
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    mg, mappable = np_max_gradients(kf.gradients(0))
+    assert kf.maxGradients(0).tobytes() == mg.tobytes()
+    assert oracle.lib().lsdo_frame_numMappablePixels(kf.ptr) == mappable
+    dm = oracle.DepthMap(seq_small.w, seq_small.h, seq_small.K)
+    dm.initializeRandomly(kf)                       # ends with Frame::setDepth(currentDepthMap)
+    cur = dm.current().copy()
+    ok = (cur["isValid"] > 0) & (cur["idepth_smoothed"].astype(np.float64) >= -0.05)
+    assert np.array_equal(kf.idepth(0), np.where(ok, cur["idepth_smoothed"], F(-1)))
+    assert np.array_equal(kf.idepthVar(0), np.where(ok, cur["idepth_var_smoothed"], F(-1)))
+    assert oracle.lib().lsdo_frame_numPoints(kf.ptr) == ok.sum()
+    mean = seqsum(cur["idepth_smoothed"][ok]) / F(ok.sum())               # row-major fp32 running sum, Frame.cpp:217-234
+    assert abs(oracle.lib().lsdo_frame_meanIdepth(kf.ptr) - mean) <= 1e-6 * mean
+    idl, vl = kf.idepth(0).copy(), kf.idepthVar(0).copy()
+    for lvl in range(1, 5):
+        idl, vl = np_idepth_level(idl, vl)
+        assert kf.idepth(lvl).tobytes() == idl.tobytes(), lvl
+        assert kf.idepthVar(lvl).tobytes() == vl.tobytes(), lvl
