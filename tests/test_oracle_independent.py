@@ -12,6 +12,8 @@ be run (parity is unpinned):
     pure Python with fp32 scalars, sampled pixels)                              -> bit-exact
   * propagateDepth (tests/restate_stereo.py, all pixels, both admission tests)   DepthMap.cpp:475-653  -> bit-exact
   * Frame::buildMaxGradients, setDepth, buildIDepthAndIDepthVar                  Frame.cpp:690-767, 199-243, 775-877 -> bit-exact
+  * the LM loops of SE3Tracker::trackFrame (:280-486) and Sim3Tracker::trackFrameSim3 (:149-382), driven from Python over
+    the oracle's single evaluations: identical accept / reject / lambda schedules and call counts, identical poses
 """
 import numpy as np
 import pytest
@@ -472,3 +474,165 @@ def test_frame_builders_against_second_restatement(oracle, seq_small, frames_sma
         idl, vl = np_idepth_level(idl, vl)
         assert kf.idepth(lvl).tobytes() == idl.tobytes(), lvl
         assert kf.idepthVar(lvl).tobytes() == vl.tobytes(), lvl
+
+
+# ---- LM control flow of the two trackers (second restatement of the LOOP; evaluations and small solves are the oracle's) ----
+def _se3f(oracle, name, *arrs):
+    out = np.zeros(7, F)
+    getattr(oracle.lib(), name)(*[oracle._fp(np.ascontiguousarray(a, F)) for a in arrs], oracle._fp(out))
+    return out
+
+
+def py_track_frame(oracle, kf, fr, init_f2r, settings, use_affine=True):
+    """SE3Tracker::trackFrame, Tracking/SE3Tracker.cpp:280-486: level schedule, LM damping, accept / reject / convergence"""
+    L = oracle.lib()
+    inv = np.zeros(7)
+    L.lsdo_se3d_inverse(oracle._dp(np.ascontiguousarray(init_f2r, np.float64)), oracle._dp(inv))
+    r2f = inv.astype(F)
+    r2f[:4] = r2f[:4] / np.sqrt(F(F(F(r2f[0] * r2f[0]) + F(r2f[1] * r2f[1])) + F(r2f[2] * r2f[2])) + F(r2f[3] * r2f[3]))   # cast<float>() normalises
+    a, b = F(1), F(0)
+    n_res, n_upd = [0] * 5, [0] * 5
+    last_residual = F(0)
+    W, H = kf.w, kf.h
+    for lvl in range(4, 0, -1):
+        ev = oracle.se3_eval(kf, fr, lvl, r2f, a, b, settings, lvl == 1)
+        if ev.warpedSize < F(0.01) * (W >> lvl) * (H >> lvl):
+            return None, n_res, n_upd
+        if use_affine:
+            a, b = F(ev.affine_a_lastIt), F(ev.affine_b_lastIt)
+        last_err = F(ev.meanWeightedRes)
+        ls = ev
+        n_res[lvl] += 1
+        lam = F(settings.lambdaInitial[lvl])
+        it = 0
+        while it < settings.maxItsPerLvl[lvl]:
+            n_upd[lvl] += 1
+            inc_try = 0
+            while True:
+                A = np.array(ls.A, F).reshape(6, 6).copy()
+                for i in range(6):
+                    A[i, i] = F(A[i, i] * F(1 + lam))
+                rhs = (-np.array(ls.b, F)).astype(F)
+                inc = np.zeros(6, F)
+                L.lsdo_ldlt6_solve(oracle._fp(np.ascontiguousarray(A.reshape(36))), oracle._fp(rhs), oracle._fp(inc))
+                inc_try += 1
+                new = _se3f(oracle, "lsdo_se3f_mul", _se3f(oracle, "lsdo_se3f_exp", inc), r2f)
+                ev = oracle.se3_eval(kf, fr, lvl, new, a, b, settings, lvl == 1)
+                if ev.warpedSize < F(0.01) * (W >> lvl) * (H >> lvl):
+                    return None, n_res, n_upd
+                err = F(ev.meanWeightedRes)
+                n_res[lvl] += 1
+                if err < last_err:
+                    r2f = new
+                    if use_affine:
+                        a, b = F(ev.affine_a_lastIt), F(ev.affine_b_lastIt)
+                    if F(err / last_err) > F(settings.convergenceEps[lvl]):
+                        it = settings.maxItsPerLvl[lvl]
+                    last_residual = last_err = err
+                    ls = ev
+                    lam = F(0) if np.float64(lam) <= 0.2 else F(lam * F(settings.lambdaSuccessFac))   # float compared with the double literal 0.2
+                    break
+                dot = F(0)
+                for i in range(6):
+                    dot = F(dot + F(inc[i] * inc[i]))
+                if not (dot > F(settings.stepSizeMin[lvl])):
+                    it = settings.maxItsPerLvl[lvl]
+                    break
+                lam = F(0.2) if lam == 0 else F(np.float64(lam) * np.float64(F(settings.lambdaFailFac)) ** inc_try)
+            it += 1
+    f2r = _se3f(oracle, "lsdo_se3f_inverse", r2f)
+    return f2r, n_res, n_upd
+
+
+@pytest.mark.parametrize("k", [2, 7])
+def test_track_frame_control_flow_against_second_restatement(oracle, seq_small, frames_small, k):
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    s = oracle.default_track_settings()
+    fa, fb = oracle.Frame(k, frames_small[k][0], seq_small.K), oracle.Frame(k, frames_small[k][0], seq_small.K)
+    want = oracle.se3_track(kf, fa, ident, s)
+    got, n_res, n_upd = py_track_frame(oracle, kf, fb, ident, s)
+    assert n_res == list(want.numCalcResidualCalls) and n_upd == list(want.numCalcWarpUpdateCalls)
+    assert sum(n_res) > sum(n_upd) + 4 > 8                      # the schedule really contains rejected tries
+    q = np.array(want.frameToRef_qt)
+    assert np.abs(got.astype(np.float64)[4:] - q[4:]).max() == 0 and np.abs(got.astype(np.float64)[:4] - q[:4]).max() < 1e-7
+    assert np.array_equal(fa.refPixelWasGood(), fb.refPixelWasGood())
+
+
+def test_track_frame_sim3_control_flow_against_second_restatement(oracle, seq_small, frames_small):
+    """Sim3Tracker::trackFrameSim3, Tracking/Sim3Tracker.cpp:149-382, driven from Python over lsdo_sim3_eval"""
+    L = oracle.lib()
+    kfs = {}
+    for k in (0, 4):
+        f = oracle.Frame(k, frames_small[k][0], seq_small.K)
+        f.setDepthFromGroundTruth(frames_small[k][1])
+        kfs[k] = f
+    init = np.concatenate([seq_small.frame_to_ref_qt(4, 0), [1.02]])
+    init[4:7] += [0.01, -0.005, 0.004]
+    s = oracle.default_track_settings(main_tracker=False)
+    want = oracle.sim3_track(kfs[0], kfs[4], init, 4, 1, s)
+
+    def qts(fn, *a):
+        out = np.zeros(8)
+        getattr(L, fn)(*[oracle._dp(np.ascontiguousarray(x, np.float64)) for x in a], oracle._dp(out))
+        return out
+    r2f = qts("lsdo_sim3d_inverse", init)
+    a, b = 1.0, 0.0
+    n_res, n_upd = [0] * 5, [0] * 5
+    W, H = kfs[0].w, kfs[0].h
+    up_to_date, final = False, None
+    for lvl in range(4, 0, -1):
+        if s.maxItsPerLvl[lvl] == 0:
+            continue
+        ev = oracle.sim3_eval(kfs[0], kfs[4], lvl, r2f, a, b, s)
+        assert not (ev.warpedSize < 0.5 * F(0.01) * (W >> lvl) * (H >> lvl) or ev.warpedSize < 10)
+        last = ev
+        n_res[lvl] += 1
+        a, b = ev.affine_a_lastIt, ev.affine_b_lastIt
+        lam = F(s.lambdaInitial[lvl])
+        up_to_date = False
+        ls = ev
+        it = 0
+        while it < s.maxItsPerLvl[lvl]:
+            up_to_date = True
+            n_upd[lvl] += 1
+            inc_try = 0
+            while True:
+                nc = F(ls.num_constraints)
+                A = (np.array(ls.A, F) / nc).astype(F).reshape(7, 7)
+                for i in range(7):
+                    A[i, i] = F(A[i, i] * F(1 + lam))
+                rhs = (-np.array(ls.b, F) / nc).astype(F)
+                inc = np.zeros(7, F)
+                L.lsdo_ldlt7_solve(oracle._fp(np.ascontiguousarray(A.reshape(49))), oracle._fp(rhs), oracle._fp(inc))
+                inc_try += 1
+                abs_inc = F(0)
+                for i in range(7):
+                    abs_inc = F(abs_inc + F(inc[i] * inc[i]))
+                assert abs_inc >= 0 and abs_inc < 1
+                new = qts("lsdo_sim3d_mul", qts("lsdo_sim3d_exp", inc.astype(np.float64)), r2f)
+                ev = oracle.sim3_eval(kfs[0], kfs[4], lvl, new, a, b, s)
+                n_res[lvl] += 1
+                if ev.mean < last.mean:
+                    r2f = new
+                    up_to_date = False
+                    a, b = ev.affine_a_lastIt, ev.affine_b_lastIt
+                    if F(F(ev.mean) / F(last.mean)) > F(s.convergenceEps[lvl]):
+                        it = s.maxItsPerLvl[lvl]
+                    final = last = ev
+                    ls = ev
+                    lam = F(0) if np.float64(lam) <= 0.2 else F(lam * F(s.lambdaSuccessFac))
+                    break
+                if not (abs_inc > F(s.stepSizeMin[lvl])):
+                    it = s.maxItsPerLvl[lvl]
+                    break
+                lam = F(0.2) if lam == 0 else F(np.float64(lam) * np.float64(F(s.lambdaFailFac)) ** inc_try)
+            it += 1
+    if not up_to_date:
+        final = ls = oracle.sim3_eval(kfs[0], kfs[4], 1, r2f, a, b, s)
+    assert n_res == list(want.numCalcResidualCalls) and n_upd == list(want.numCalcWarpUpdateCalls)
+    got = qts("lsdo_sim3d_inverse", r2f)
+    assert np.abs(got - np.array(want.frameToRef_qts)).max() < 1e-6
+    assert abs(final.mean - want.lastResidual) <= 1e-5 * want.lastResidual
+    assert np.abs(np.array(ls.A) - np.array(want.lastSim3Hessian)).max() <= 1e-4 * np.abs(np.array(want.lastSim3Hessian)).max()
