@@ -12,6 +12,7 @@ be run (parity is unpinned):
     pure Python with fp32 scalars, sampled pixels)                              -> bit-exact
   * propagateDepth (tests/restate_stereo.py, all pixels, both admission tests)   DepthMap.cpp:475-653  -> bit-exact
   * Frame::buildMaxGradients, setDepth, buildIDepthAndIDepthVar                  Frame.cpp:690-767, 199-243, 775-877 -> bit-exact
+  * DepthMap::createKeyFrame (:1222-1327) composed from the pieces above, rescale included        -> bit-exact
   * the LM loops of SE3Tracker::trackFrame (:280-486) and Sim3Tracker::trackFrameSim3 (:149-382), driven from Python over
     the oracle's single evaluations: identical accept / reject / lambda schedules and call counts, identical poses
 """
@@ -636,3 +637,42 @@ def test_track_frame_sim3_control_flow_against_second_restatement(oracle, seq_sm
     assert np.abs(got - np.array(want.frameToRef_qts)).max() < 1e-6
     assert abs(final.mean - want.lastResidual) <= 1e-5 * want.lastResidual
     assert np.abs(np.array(ls.A) - np.array(want.lastSim3Hessian)).max() <= 1e-4 * np.abs(np.array(want.lastSim3Hessian)).max()
+
+
+def test_create_keyframe_against_second_restatement(oracle, seq_small, frames_small):
+    """DepthMap::createKeyFrame, DepthEstimation/DepthMap.cpp:1222-1327, composed from the second restatements:
+    propagateDepth -> regularize<true>(KEEP) -> fillHoles -> regularize<false>(KEEP) -> rescale to mean idepth 1 -> setDepth"""
+    from tests import restate_stereo as rs
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    dm = oracle.DepthMap(seq_small.w, seq_small.h, seq_small.K)
+    dm.initializeFromGTDepth(kf)
+    dm.regularize(False, 24)
+    k = 8
+    nf = oracle.Frame(k, frames_small[k][0], seq_small.K)
+    r = oracle.se3_track(kf, nf, np.array([0, 0, 0, 1, 0, 0, 0], np.float64))
+    qts = nf.thisToParent().copy()
+    mask = nf.refPixelWasGood().copy().astype(bool)
+    before = dm.current().copy()
+    dm.createKeyFrame(nf)
+    after = dm.current().copy()
+
+    cur = rs.propagate_depth(_cam(kf), kf.image(0), nf.image(0), nf.maxGradients(0), before, qts, mask)
+    cur = np_regularize(cur, True, 24)
+    cur, _ = np_fill_holes(cur, nf.maxGradients(0))
+    cur = np_regularize(cur, False, 24)
+    va = cur["isValid"] > 0
+    s = seqsum(cur["idepth_smoothed"][va])                    # row-major fp32 running sum, :1286-1293
+    f = F(F(va.sum()) / s)
+    f2 = F(f * f)
+    for name, fac in (("idepth", f), ("idepth_smoothed", f), ("idepth_var", f2), ("idepth_var_smoothed", f2)):
+        cur[name][va] = (cur[name][va] * fac).astype(F)
+    assert np.array_equal(va, after["isValid"] > 0) and va.sum() > 5000
+    assert np.array_equal(cur["blacklisted"], after["blacklisted"])
+    for name in ("validity_counter", "idepth", "idepth_var", "idepth_smoothed", "idepth_var_smoothed"):
+        assert cur[name][va].tobytes() == after[name][va].tobytes(), name
+    new_pose = nf.thisToParent()
+    assert abs(new_pose[7] - np.float64(f)) == 0                 # sim3FromSE3(oldToNew.inverse(), rescaleFactor), :1305
+    assert np.abs(new_pose[4:7] - qts[4:7]).max() < 1e-12 and abs(abs(np.dot(new_pose[:4], qts[:4])) - 1) < 1e-12
+    ok = va & (cur["idepth_smoothed"].astype(np.float64) >= -0.05)
+    assert np.array_equal(nf.idepth(0), np.where(ok, cur["idepth_smoothed"], F(-1)))
