@@ -676,3 +676,35 @@ def test_create_keyframe_against_second_restatement(oracle, seq_small, frames_sm
     assert np.abs(new_pose[4:7] - qts[4:7]).max() < 1e-12 and abs(abs(np.dot(new_pose[:4], qts[:4])) - 1) < 1e-12
     ok = va & (cur["idepth_smoothed"].astype(np.float64) >= -0.05)
     assert np.array_equal(nf.idepth(0), np.where(ok, cur["idepth_smoothed"], F(-1)))
+
+
+def test_perma_ref_overlap_against_second_restatement(oracle, seq_small, frames_small):
+    """SE3Tracker::checkPermaRefOverlap, Tracking/SE3Tracker.cpp:121-157 over the Frame::setPermaRef snapshot (level 4)"""
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    pr = oracle.PermaRef(kf)
+    pos, _, col, var = np_point_cloud(kf, 4)
+    assert pr.n == len(pos) and np.array_equal(pr.pos[:pr.n], pos) and np.array_equal(pr.colvar[:pr.n, 0], col) and np.array_equal(pr.colvar[:pr.n, 1], var)
+    K4 = kf.K(4)[0].reshape(3, 3)
+    w2, h2 = kf.size(4)[0] - 1, kf.size(4)[1] - 1
+    rng = np.random.default_rng(2)
+    for _ in range(6):
+        a = rng.normal(0, [0.2, 0.2, 0.3, 0.05, 0.05, 0.05])
+        qt = np.zeros(7)
+        oracle.lib().lsdo_se3d_exp(oracle._dp(a), oracle._dp(qt))
+        q32 = qt.astype(F)
+        q32[:4] = q32[:4] / np.sqrt(F(F(F(q32[0] * q32[0]) + F(q32[1] * q32[1])) + F(q32[2] * q32[2])) + F(q32[3] * q32[3]))
+        R, t = quat_R(q32[:4]).astype(F), q32[4:]
+        # the float rotation matrix of a float quaternion: redo in fp32 to match Eigen's toRotationMatrix on SE3f
+        x, y, z, w = q32[:4]
+        tx, ty, tz = F(2) * x, F(2) * y, F(2) * z
+        R = np.array([[F(1) - (ty * y + tz * z), ty * x - tz * w, tz * x + ty * w],
+                      [ty * x + tz * w, F(1) - (tx * x + tz * z), tz * y - tx * w],
+                      [tz * x - ty * w, tz * y + tx * w, F(1) - (tx * x + ty * y)]], F)
+        W = ((R[None, :, 0] * pos[:, :1] + R[None, :, 1] * pos[:, 1:2]) + R[None, :, 2] * pos[:, 2:3]) + t[None, :]
+        with np.errstate(all="ignore"):
+            u = (W[:, 0] / W[:, 2]) * K4[0, 0] + K4[0, 2]
+            v = (W[:, 1] / W[:, 2]) * K4[1, 1] + K4[1, 2]
+            inside = (u > 0) & (v > 0) & (u < w2) & (v < h2)
+            usage = seqsum(np.minimum(pos[inside, 2] / W[inside, 2], F(1))) / F(len(pos))
+        assert abs(pr.overlap(qt) - usage) <= 2e-6 * max(usage, 1e-3)
