@@ -329,7 +329,6 @@ extern "C" int lsdgpu_frame_from_stage(lsdgpu_ctx* ctx, int frame_id, int index)
 static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc, bool remap)
 {
     const int w = ctx->w, h = ctx->h;
-    const size_t n0 = (size_t)w * h;
     PyrPtrs pp;
     for (int l = 0; l < LSD_LEVELS; l++) pp.l[l] = s->image[l];
     if (remap) k_image_pyramid<true><<<dim3(w / 16, h / 16), 256, 0, ctx->stream>>>(dsrc, pp, w, h, ctx->dRemapX, ctx->dRemapY, ctx->rawW, nullptr);

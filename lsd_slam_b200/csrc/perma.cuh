@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(PERMA_THREADS) k_perma_track(const __grid_cons
                                                                PermaResult* __restrict__ results)
 {
     __shared__ LMShared sh;
-    __shared__ LMState lm;
+    __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
+    LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
     __shared__ float sm[PERMA_THREADS / 32][EV_NCH];
     const PermaItem it = items[blockIdx.x];
     const TrackLevelParams& L = p.lvl[QUICK_KF_CHECK_LVL];

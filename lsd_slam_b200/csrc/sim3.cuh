@@ -463,7 +463,8 @@ __global__ void __launch_bounds__(S3_THREADS) k_sim3_track(const __grid_constant
     cg::cluster_group cluster = cg::this_cluster();
     const int csize = (int)cluster.num_blocks(), crank = (int)cluster.block_rank();
     const int prob = blockIdx.x / csize;
-    __shared__ Sim3LM lm;
+    __shared__ alignas(Sim3LM) unsigned char lmStorage[sizeof(Sim3LM)];     // every field is written before use; no constructor in shared memory
+    Sim3LM& lm = *reinterpret_cast<Sim3LM*>(lmStorage);
     __shared__ Sim3Shared sh;
     __shared__ float warpRows[S3_THREADS / 32][S3_NCH];
     __shared__ float xrow[2][S3_NCH];          // this CTA's partial sums, double-buffered by evaluation parity

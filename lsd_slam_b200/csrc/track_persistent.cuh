@@ -627,7 +627,8 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
 __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out, TrackState* __restrict__ outDev)
 {
     __shared__ LMShared sh;
-    __shared__ LMState lm;
+    __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
+    LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
     __shared__ float sm[TP_THREADS / 32][EV_NCH];
     static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
     extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
