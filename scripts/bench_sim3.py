@@ -53,13 +53,16 @@ for n in (1, 2, 6, 18, 36, 148, 296):
             ctx.timer_end(2)
             out[n][f"ms_cluster{cs}"] = ctx.timer_ms(2) / reps
         del os.environ["LSDGPU_SIM3_CLUSTER"]
-# CPU: scalar parity flavour and -O3 flavour (the Sim3 loops of the oracle are scalar in both; the reference has SSE
-# variants of calcSim3WeightsAndResidual / calcSim3LGS, Sim3Tracker.cpp:611-745, 860-990, not restated)
+# CPU, one thread (the constraint-search thread of the reference runs trackFrameSim3 single-threaded): strict-IEEE scalar
+# flavour, -O3 scalar, and -O3 with the reference's SSE variants of calcSim3WeightsAndResidual / calcSim3LGS
+# (Sim3Tracker.cpp:611-736, 860-973; calcSim3Buffers is scalar in the reference as well) = the reference's default build
 cpu = {}
-for name, d in (("parity", of), ("O3", off)):
+for name, d, fast, sse in (("parity_scalar", of, False, 0), ("O3_scalar", off, True, 0), ("O3_sse", off, True, 1)):
+    po.set_globals(fast=fast, useSSE=sse)
     t0 = time.perf_counter(); m = 0
-    while time.perf_counter() - t0 < 4.0:
+    while time.perf_counter() - t0 < 3.0:
         for ref, fr in pairs:
             po.sim3_track(d[ref], d[fr], init(ref, fr), 4, 1); m += 1
     cpu[name] = (time.perf_counter() - t0) / m * 1e3
+    po.set_globals(fast=fast)
 print(json.dumps({"gpu": out, "cpu_oracle_ms_per_tracking_1thread": cpu}))

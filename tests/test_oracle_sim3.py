@@ -163,3 +163,22 @@ def test_sim3_eval_consistency(oracle):
     assert e.num_constraints == 2 * e.warpedSize and e.numTermsP == e.warpedSize and 0 < e.numTermsD <= e.numTermsP
     assert A7[6, 6] > 0 and A7[6, 0] == 0 and A7[6, 1] == 0 and A7[6, 5] == 0      # sigma only couples with rows 2,3,4
     assert abs(e.mean - (e.sumResD + e.sumResP) / (e.numTermsD + e.numTermsP)) < 1e-6 * e.mean
+
+
+def test_sse_flavour_agrees_with_scalar(oracle, seq_small, frames_small):
+    """the reference's SSE variants of the weights / LGS loops (rcp approximations, N mod 4 tail dropped) give the same
+    tracking up to their approximation error"""
+    seq, A, B = _keyframes(oracle)
+    init = np.concatenate([seq.frame_to_ref_qt(6, 0), [1.02]])
+    init[4:7] += [0.01, -0.005, 0.004]
+    ref = oracle.sim3_track(A, B, init, 4, 1)
+    oracle.set_globals(useSSE=1)
+    try:
+        sse = oracle.sim3_track(A, B, init, 4, 1)
+    finally:
+        oracle.set_globals()
+    a, b = np.array(ref.frameToRef_qts), np.array(sse.frameToRef_qts)
+    assert np.abs(a - b).max() < 2e-4 and not sse.diverged
+    assert abs(sse.lastResidual - ref.lastResidual) < 5e-3 * ref.lastResidual
+    Hs, Hr = np.array(sse.lastSim3Hessian), np.array(ref.lastSim3Hessian)
+    assert np.abs(Hs - Hr).max() < 5e-3 * np.abs(Hr).max()
