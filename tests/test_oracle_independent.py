@@ -484,18 +484,22 @@ def _se3f(oracle, name, *arrs):
     return out
 
 
-def py_track_frame(oracle, kf, fr, init_f2r, settings, use_affine=True):
-    """SE3Tracker::trackFrame, Tracking/SE3Tracker.cpp:280-486: level schedule, LM damping, accept / reject / convergence"""
+def py_track_frame(oracle, kf, fr, init_f2r, settings, use_affine=True, levels=(4, 3, 2, 1), init_is_ref_to_frame=False):
+    """SE3Tracker::trackFrame, Tracking/SE3Tracker.cpp:280-486: level schedule, LM damping, accept / reject / convergence.
+    levels=(4,), init_is_ref_to_frame=True: the loop of trackFrameOnPermaref (:162-272), which returns referenceToFrame."""
     L = oracle.lib()
     inv = np.zeros(7)
-    L.lsdo_se3d_inverse(oracle._dp(np.ascontiguousarray(init_f2r, np.float64)), oracle._dp(inv))
+    if init_is_ref_to_frame:
+        inv[:] = init_f2r
+    else:
+        L.lsdo_se3d_inverse(oracle._dp(np.ascontiguousarray(init_f2r, np.float64)), oracle._dp(inv))
     r2f = inv.astype(F)
     r2f[:4] = r2f[:4] / np.sqrt(F(F(F(r2f[0] * r2f[0]) + F(r2f[1] * r2f[1])) + F(r2f[2] * r2f[2])) + F(r2f[3] * r2f[3]))   # cast<float>() normalises
     a, b = F(1), F(0)
     n_res, n_upd = [0] * 5, [0] * 5
     last_residual = F(0)
     W, H = kf.w, kf.h
-    for lvl in range(4, 0, -1):
+    for lvl in levels:
         ev = oracle.se3_eval(kf, fr, lvl, r2f, a, b, settings, lvl == 1)
         if ev.warpedSize < F(0.01) * (W >> lvl) * (H >> lvl):
             return None, n_res, n_upd
@@ -541,6 +545,8 @@ def py_track_frame(oracle, kf, fr, init_f2r, settings, use_affine=True):
                     break
                 lam = F(0.2) if lam == 0 else F(np.float64(lam) * np.float64(F(settings.lambdaFailFac)) ** inc_try)
             it += 1
+    if init_is_ref_to_frame:
+        return r2f, n_res, n_upd
     f2r = _se3f(oracle, "lsdo_se3f_inverse", r2f)
     return f2r, n_res, n_upd
 
@@ -708,3 +714,21 @@ def test_perma_ref_overlap_against_second_restatement(oracle, seq_small, frames_
             inside = (u > 0) & (v > 0) & (u < w2) & (v < h2)
             usage = seqsum(np.minimum(pos[inside, 2] / W[inside, 2], F(1))) / F(len(pos))
         assert abs(pr.overlap(qt) - usage) <= 2e-6 * max(usage, 1e-3)
+
+
+def test_track_frame_on_permaref_control_flow_against_second_restatement(oracle, seq_small, frames_small):
+    """SE3Tracker::trackFrameOnPermaref, Tracking/SE3Tracker.cpp:162-272: the level-4 loop with the TestTrack settings
+    (util/settings.h:379-382), re-driven over single evaluations of the same level-4 cloud"""
+    kf = oracle.Frame(0, frames_small[0][0], seq_small.K)
+    kf.setDepthFromGroundTruth(frames_small[0][1])
+    pr = oracle.PermaRef(kf)
+    fr = oracle.Frame(6, frames_small[6][0], seq_small.K)
+    s = oracle.default_track_settings(main_tracker=False)
+    s.lambdaInitial[4], s.stepSizeMin[4], s.convergenceEps[4], s.maxItsPerLvl[4] = 0, 1e-3, 0.98, 5
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    want = pr.track(fr, ident)
+    got, n_res, n_upd = py_track_frame(oracle, kf, fr, ident, s, levels=(4,), init_is_ref_to_frame=True)
+    assert not want.diverged
+    assert n_res[4] == want.numCalcResidualCalls[4] and n_upd[4] == want.numCalcWarpUpdateCalls[4] and n_res[4] >= 3
+    q = np.array(want.frameToRef_qt)                  # holds referenceToFrame for this call (:271)
+    assert np.abs(got.astype(np.float64)[4:] - q[4:]).max() == 0 and np.abs(got.astype(np.float64)[:4] - q[:4]).max() < 1e-7
