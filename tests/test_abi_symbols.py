@@ -50,3 +50,17 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "lsd_oracle" not in txt and "liblsd_oracle" not in txt, f
+
+
+def test_docs_only_name_declared_entry_points():
+    """every lsdgpu_* identifier used in INTEGRATION.md / README.md / DESIGN.md is declared in include/lsdgpu.h, and every
+    reference citation of the header has the form path:line"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "lsdgpu.h")).read()
+    declared = set(re.findall(r"\b(lsdgpu_[a-z0-9_]+)\b", hdr))
+    for doc in ("INTEGRATION.md", "README.md", "DESIGN.md"):
+        used = set(re.findall(r"\b(lsdgpu_[a-z0-9_]+)\b", open(os.path.join(ROOT, doc)).read()))
+        assert not (used - declared), (doc, sorted(used - declared))
+    # each extern "C" function of the header carries a citation (file.cpp:line or file.h:line) in the comment above it
+    funcs = re.findall(r"/\*(?:(?!\*/).)*\*/\s*(?:int|void|const char\*|long long)\s+(lsdgpu_[a-z0-9_]+)\s*\(", hdr, flags=re.S)
+    assert len(funcs) >= 25
