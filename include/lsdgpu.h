@@ -183,8 +183,13 @@ int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t
  * UndistorterOpenCV (:449-567) delegates to cv::initUndistortRectifyMap / cv::remap and stays on the host. */
 int lsdgpu_undistorter_ptam_prepare(const float input_calibration[5], int in_width, int in_height, const float output_calibration[5],
                                     int out_width, int out_height, float* remapX, float* remapY, float K_out[9]);
+/* host-only check of a pair of remap tables: every entry is either "no source" (x < 0, as Undistorter.cpp:312-316 writes it)
+ * or a position whose four bilinear taps lie inside the in_width x in_height image (0 <= x < in_width-1, 0 <= y < in_height-1).
+ * Returns 0 if valid, otherwise 1 + the index of the first offending entry (-2 for bad arguments). */
+int lsdgpu_undistorter_validate_tables(int in_width, int in_height, int out_width, int out_height, const float* remapX, const float* remapY);
 /* install remap tables (host pointers, w*h floats each; w, h = the context's size) for raw images of in_width x in_height;
- * NULL tables = pass-through (then in_width/in_height must equal the context's size) */
+ * NULL tables = pass-through (then in_width/in_height must equal the context's size).  Tables that fail
+ * lsdgpu_undistorter_validate_tables are rejected (the gather kernel does no bounds checks of its own). */
 int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const float* remapX, const float* remapY);
 /* UndistorterPTAM::undistort, util/Undistorter.cpp:355-411: raw (in_width*in_height) -> out (w*h), 8 bit */
 int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t* out);

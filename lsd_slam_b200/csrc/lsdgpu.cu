@@ -1508,6 +1508,18 @@ extern "C" int lsdgpu_undistorter_ptam_prepare(const float ic[5], int iw, int ih
     return (ih == oh && iw == ow && ic[4] == 0) ? 1 : 0;
 }
 
+extern "C" int lsdgpu_undistorter_validate_tables(int in_width, int in_height, int out_width, int out_height, const float* remapX, const float* remapY)
+{
+    if (!remapX || !remapY || in_width < 2 || in_height < 2 || out_width <= 0 || out_height <= 0) return -2;
+    const long long n = (long long)out_width * out_height;
+    for (long long i = 0; i < n; i++) {
+        const float x = remapX[i], y = remapY[i];
+        if (x < 0) continue;                                               // undistort() writes 0 (Undistorter.cpp:389-390)
+        if (!(x >= 0 && y >= 0 && x < in_width - 1 && y < in_height - 1)) return (int)(1 + (i < 0x7ffffffeLL ? i : 0x7ffffffeLL));   // also NaN
+    }
+    return 0;
+}
+
 extern "C" int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const float* remapX, const float* remapY)
 {
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -1522,6 +1534,8 @@ extern "C" int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_heig
     if (!remapX || !remapY) {
         if (in_width != ctx->w || in_height != ctx->h) return lsd_fail(ctx, "pass-through undistorter needs input size == context size");
     } else {
+        if (lsdgpu_undistorter_validate_tables(in_width, in_height, ctx->w, ctx->h, remapX, remapY) != 0)
+            return lsd_fail(ctx, "remap table entry outside the input image (lsdgpu_undistorter_validate_tables)");
         LSD_CHECK(ctx, cudaMalloc((void**)&ctx->dRemapX, n * 4));
         LSD_CHECK(ctx, cudaMalloc((void**)&ctx->dRemapY, n * 4));
         LSD_CHECK(ctx, cudaMemcpy(ctx->dRemapX, remapX, n * 4, cudaMemcpyHostToDevice));

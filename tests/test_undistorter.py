@@ -46,6 +46,24 @@ def test_tables_are_sane(oracle):
     assert set(np.unique(out)) <= {0, 76, 77}
 
 
+def test_table_validation(oracle):
+    """host-only guard of lsdgpu_set_undistorter: the prepared tables pass, corrupted ones are rejected"""
+    import ctypes as C
+    L = abi.load()
+    fp = C.POINTER(C.c_float)
+    for case in CASES:
+        u = oracle.UndistorterPTAM(*case)
+        (iw, ih), (ow, oh) = case[1], case[3]
+        assert L.lsdgpu_undistorter_validate_tables(iw, ih, ow, oh, u.remapX.ctypes.data_as(fp), u.remapY.ctypes.data_as(fp)) == 0
+    u = oracle.UndistorterPTAM(*CASES[0])
+    (iw, ih), (ow, oh) = CASES[0][1], CASES[0][3]
+    for bad_x, bad_y in ((iw - 1.0, 5.0), (5.0, ih - 1.0), (float("nan"), 5.0), (5.0, -0.5), (1e9, 1e9)):
+        x, y = u.remapX.copy(), u.remapY.copy()
+        x[7, 9], y[7, 9] = bad_x, bad_y
+        assert L.lsdgpu_undistorter_validate_tables(iw, ih, ow, oh, x.ctypes.data_as(fp), y.ctypes.data_as(fp)) == 1 + 7 * ow + 9
+    assert L.lsdgpu_undistorter_validate_tables(iw, ih, ow, oh, None, None) == -2
+
+
 def _raw(seq_w, seq_h, seed=3):
     rng = np.random.default_rng(seed)
     base = rng.integers(0, 256, (seq_h // 8 + 2, seq_w // 8 + 2)).astype(np.float32)
