@@ -90,6 +90,9 @@ def render_frames(w, h, seed, n):
     from lsd_slam_b200 import synth
     seq = synth.Sequence(w, h, seed=seed)
     frames = [seq.render(k) for k in range(n)]
+    seq.density = synth.semi_dense_fraction(frames[0][0])          # report it, refuse unrepresentative streams
+    if not 0.30 <= seq.density <= 0.50:
+        raise SystemExit(f"synthetic stream: maxGrad >= 5 on {100 * seq.density:.1f} % of the pixels (expected 30-50 %)")
     return seq, frames
 
 
@@ -245,6 +248,7 @@ def main():
             return
         n_frames = args.warmup + args.steps + 1
         seq, frames = render_frames(args.width, args.height, 1234, n_frames)
+        config["semi_dense_fraction"] = round(seq.density, 4)
         fps, ms, n, threads = cpu_loop(seq, frames, args.steps, args.warmup, time_budget_s=120.0)
         line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -257,6 +261,7 @@ def main():
         return
 
     seq, frames, res = gpu_run(args, rank, world, local_rank)
+    config["semi_dense_fraction"] = round(seq.density, 4)          # maxGrad >= 5 fraction of this rank's frame 0
     if world > 1:
         import torch.distributed as dist
         if dist.is_initialized():

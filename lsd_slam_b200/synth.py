@@ -79,6 +79,27 @@ def _height(X, Y):
     return 2.0 + 0.5 * np.sin(1.5 * X) * np.cos(1.2 * Y)
 
 
+def semi_dense_fraction(image_u8: np.ndarray, min_use_grad: float = 5.0) -> float:
+    """Fraction of pixels with maxGradients >= minUseGrad, with the reference's definitions: central-difference gradient
+    (Frame.cpp:658-677) and the 3x1 / 1x3 maximum filters over LINEAR index ranges (Frame.cpp:708-759).  SURVEY 8d asks the
+    generator to report this and to refuse streams outside 30-50 % (a texture that is dense everywhere is unrepresentative)."""
+    img = image_u8.astype(np.float32)
+    h, w = img.shape
+    n = w * h
+    f = img.reshape(n)
+    a = np.zeros(n, np.float32)
+    i = np.arange(w, n - w)
+    gx = np.float32(0.5) * (f[i + 1] - f[i - 1])
+    gy = np.float32(0.5) * (f[i + w] - f[i - w])
+    a[i] = np.sqrt(gx * gx + gy * gy)
+    j = np.arange(w + 1, n - w - 1)
+    t = np.zeros(n, np.float32)
+    t[j] = np.maximum(np.maximum(a[j - w], a[j]), a[j + w])
+    m = a.copy()
+    m[j] = np.maximum(np.maximum(t[j - 1], t[j]), t[j + 1])
+    return float((m >= np.float32(min_use_grad)).mean())
+
+
 class Sequence:
     """A synthetic stream: ``frame(k)`` -> uint8 image, ``pose(k)`` -> camera-k-from-world (R, t)."""
 
@@ -92,6 +113,13 @@ class Sequence:
         f, cx, cy = float(self.K[0, 0]), float(self.K[0, 2]), float(self.K[1, 2])
         u, v = np.meshgrid(np.arange(w, dtype=np.float64), np.arange(h, dtype=np.float64))
         self._rays = np.stack([(u - cx) / f, (v - cy) / f, np.ones_like(u)], axis=-1)
+
+    def check_density(self, lo: float = 0.30, hi: float = 0.50) -> float:
+        """semi-dense density of frame 0; raises outside [lo, hi]"""
+        frac = semi_dense_fraction(self.frame(0))
+        if not lo <= frac <= hi:
+            raise ValueError(f"synthetic stream has maxGrad >= 5 on {100 * frac:.1f} % of the pixels, outside {100 * lo:.0f}-{100 * hi:.0f} %")
+        return frac
 
     def pose(self, k: int):
         return se3_exp(k * self.xi)

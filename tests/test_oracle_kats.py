@@ -32,10 +32,15 @@ def test_frame_pyramid_exact(oracle, seq_small, frames_small):
 
 
 def test_semi_dense_density(oracle, seq_small, frames_small):
+    from lsd_slam_b200 import synth
     img0, _ = frames_small[0]
     f = oracle.Frame(0, img0, seq_small.K)
     frac = float((f.maxGradients(0) >= 5).mean())
     assert 0.30 <= frac <= 0.55, frac          # realistic semi-dense density
+    assert synth.semi_dense_fraction(img0) == frac          # the generator's own report uses the reference's definition
+    assert seq_small.check_density(0.30, 0.55) == frac
+    with pytest.raises(ValueError):
+        seq_small.check_density(0.60, 0.70)
 
 
 def test_zero_motion_tracks_to_identity(oracle, seq_small, frames_small):
