@@ -99,11 +99,12 @@ def render_frames(w, h, seed, n):
 # ------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference's algorithm (oracle, timing flavour: SSE tracker loops + 4 mapping threads)
 # ------------------------------------------------------------------------------------------------------------
-def cpu_loop(seq, frames, n_steps, warmup, time_budget_s=25.0):
-    """Returns (fps, ms_per_step, frames_timed, threads).  Same loop as lsd_slam_b200/stream.py."""
+def cpu_loop(seq, frames, n_steps, warmup, time_budget_s=25.0, multi_threading=1):
+    """Returns (fps, ms_per_step, frames_timed, threads).  Same loop as lsd_slam_b200/stream.py.
+    multi_threading=0: the reference's single-threaded fallback (IndexThreadReduce.h:72-77), i.e. one busy core."""
     from oracle import pyoracle as po
     po.build()
-    po.set_globals(fast=True, useSSE=1, multiThreading=1)
+    po.set_globals(fast=True, useSSE=1, multiThreading=multi_threading)
     L = po.lib(fast=True)
     ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
     img0, d0 = frames[0]
@@ -143,7 +144,7 @@ def cpu_loop(seq, frames, n_steps, warmup, time_budget_s=25.0):
         if len(times) >= n_steps or (time.perf_counter() - t_begin) > time_budget_s:
             break
     total = float(np.sum(times))
-    return len(times) / total, 1e3 * total / len(times), len(times), 1 + 4
+    return len(times) / total, 1e3 * total / len(times), len(times), (1 + 4) if multi_threading else 1
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -250,12 +251,14 @@ def main():
         seq, frames = render_frames(args.width, args.height, 1234, n_frames)
         config["semi_dense_fraction"] = round(seq.density, 4)
         fps, ms, n, threads = cpu_loop(seq, frames, args.steps, args.warmup, time_budget_s=120.0)
+        fps1, _, n1, _ = cpu_loop(seq, frames, min(args.steps, 30), args.warmup, time_budget_s=30.0, multi_threading=0)
         line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
                 "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                                  "sample": f"{n} frames of the same stream; oracle -O3 x86-64-v3, SSE tracker loops, 4 mapping threads + 1 tracking thread (reference threading)",
-                                 "host_cores": os.cpu_count()},
+                                 "host_cores": os.cpu_count(),
+                                 "single_core": {"value": fps1, "unit": "frames/s", "sample": f"{n1} frames, multiThreading = false"}},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -306,9 +309,11 @@ def main():
     if not args.no_cpu_baseline and world == 1:
         n_cpu = min(len(frames) - 1 - args.warmup, args.steps)
         cfps, cms, n, threads = cpu_loop(seq, frames, n_cpu, args.warmup, time_budget_s=25.0)
+        cfps1, _, n1, _ = cpu_loop(seq, frames, min(n_cpu, 30), args.warmup, time_budget_s=20.0, multi_threading=0)
         line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port", "ms_per_step": cms,
                                 "sample": f"{n} frames of the same stream; oracle -O3 x86-64-v3, SSE tracker loops, 4 mapping threads + 1 tracking thread",
-                                "host_cores": os.cpu_count()}
+                                "host_cores": os.cpu_count(),
+                                "single_core": {"value": cfps1, "unit": "frames/s", "sample": f"{n1} frames, multiThreading = false"}}
     print(json.dumps(line))
 
 
