@@ -732,3 +732,47 @@ def test_track_frame_on_permaref_control_flow_against_second_restatement(oracle,
     assert n_res[4] == want.numCalcResidualCalls[4] and n_upd[4] == want.numCalcWarpUpdateCalls[4] and n_res[4] >= 3
     q = np.array(want.frameToRef_qt)                  # holds referenceToFrame for this call (:271)
     assert np.abs(got.astype(np.float64)[4:] - q[4:]).max() == 0 and np.abs(got.astype(np.float64)[:4] - q[:4]).max() < 1e-7
+
+
+def test_initialisers_against_second_restatement(oracle, seq_small, frames_small):
+    """Frame::setDepthFromGroundTruth (Frame.cpp:245-293), DepthMap::initializeFromGTDepth (DepthMap.cpp:965-1018) and
+    initializeRandomly (:883-918, glibc rand() re-seeded to its default state for both sides)"""
+    import ctypes
+    img, depth = frames_small[0]
+    kf = oracle.Frame(0, img, seq_small.K)
+    mg = kf.maxGradients(0)
+    H, W = mg.shape
+    depth = depth.copy()
+    depth[50:60, 70:90] = np.nan
+    depth[100:105, 10:40] = -1.0
+    kf.setDepthFromGroundTruth(depth, 2.0)
+    yy, xx = np.mgrid[0:H, 0:W]
+    with np.errstate(all="ignore"):
+        ok = (xx > 0) & (xx < W - 1) & (yy > 0) & (yy < H - 1) & (mg >= F(5.0)) & ~np.isnan(depth) & (depth > 0)
+        want_id = np.where(ok, F(1.0) / depth, F(-1)).astype(F)
+    want_var = np.where(ok, F(F(0.01) * F(0.01)) * F(2.0), F(-1)).astype(F)       # VAR_GT_INIT_INITIAL * cov_scale
+    assert kf.idepth(0).tobytes() == want_id.tobytes() and kf.idepthVar(0).tobytes() == want_var.tobytes()
+
+    dm = oracle.DepthMap(W, H, seq_small.K)
+    dm.initializeFromGTDepth(kf)
+    cur = dm.current().copy()
+    v = ~np.isnan(want_id) & (want_id > 0)
+    assert np.array_equal(cur["isValid"] > 0, v)
+    assert np.array_equal(cur["idepth"][v], want_id[v]) and np.array_equal(cur["idepth_smoothed"][v], want_id[v])
+    assert (cur["idepth_var"][v] == F(0.01) * F(0.01)).all() and (cur["validity_counter"][v] == 20).all() and not cur["blacklisted"].any()
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    kf2 = oracle.Frame(1, img, seq_small.K)
+    dm2 = oracle.DepthMap(W, H, seq_small.K)
+    dm2.initializeRandomly(kf2)
+    got = dm2.current().copy()
+    libc.srand(1)
+    sel = (mg > F(5.0))[1:H - 1, 1:W - 1]
+    n = int(sel.sum())
+    r = np.array([libc.rand() for _ in range(n)], np.int64)                   # row-major order of the reference's loops
+    idepth = (F(0.5) + F(1.0) * ((r % 100001).astype(F) / F(100000.0))).astype(F)
+    inner = got[1:H - 1, 1:W - 1]
+    assert np.array_equal(inner["isValid"] > 0, sel)
+    assert inner["idepth"][sel].tobytes() == idepth.tobytes() and inner["idepth_smoothed"][sel].tobytes() == idepth.tobytes()
+    assert (inner["idepth_var"][sel] == F(0.5) * (F(0.5) * F(0.5))).all() and (inner["validity_counter"][sel] == 20).all()
