@@ -42,7 +42,8 @@ template <typename T> struct SE3 {
 
 template <typename T> LSD_HD void quatNormalize(T q[4])
 {
-    T len = MathFn<T>::sqrt_(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    // coeffs().norm(): Eigen's unrolled reduction tree over 4 coefficients, (x^2 + y^2) + (z^2 + w^2)
+    T len = MathFn<T>::sqrt_((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
     q[0] /= len; q[1] /= len; q[2] /= len; q[3] /= len;
 }
 
@@ -103,7 +104,7 @@ template <typename T> LSD_HD SE3<T> se3Exp(const T a[6])
 {
     typedef MathFn<T> M;
     const T* om = a + 3;
-    T theta_sq = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    T theta_sq = om[0] * om[0] + (om[1] * om[1] + om[2] * om[2]);   // omega.squaredNorm(): 1 + 2 reduction tree
     T theta = M::sqrt_(theta_sq);
     T half_theta = (T)0.5 * theta;
     T imag, real;
@@ -127,8 +128,9 @@ template <typename T> LSD_HD SE3<T> se3Exp(const T a[6])
     if (theta < M::eps()) {
         quatToMatrix(r.q, V);
     } else {
-        T c1 = ((T)1 - M::cos_(theta)) / theta_sq;
-        T c2 = (theta - M::sin_(theta)) / (theta_sq * theta);
+        T tsq = theta * theta;                                      // se3.hpp:419 recomputes theta_sq from theta
+        T c1 = ((T)1 - M::cos_(theta)) / tsq;
+        T c2 = (theta - M::sin_(theta)) / (tsq * theta);
         for (int i = 0; i < 9; i++) V[i] = (((i % 4) == 0 ? (T)1 : (T)0) + c1 * Om[i]) + c2 * Om2[i];
     }
     for (int i = 0; i < 3; i++) r.t[i] = (V[i * 3 + 0] * a[0] + V[i * 3 + 1] * a[1]) + V[i * 3 + 2] * a[2];
@@ -162,11 +164,23 @@ LSD_HD void mat3Inverse(const float m[9], float r[9])
     r[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
 }
 
-// x = A^-1 b for a symmetric NxN via LDL^T with largest-diagonal pivoting (float)
+// Eigen's unrolled reduction tree (Redux.h): sum(first n/2) + sum(rest)
+LSD_HD float treeSumF(const float* v, int n)
+{
+    if (n == 1) return v[0];
+    if (n == 2) return v[0] + v[1];
+    if (n == 3) return v[0] + (v[1] + v[2]);
+    const int h = n / 2;
+    return treeSumF(v, h) + treeSumF(v + h, n - h);
+}
+
+// x = A^-1 b for a symmetric NxN via LDL^T with largest-diagonal pivoting (float): Eigen's LDLT (unblocked lower
+// factorisation; solve = P, unrolled unit-lower solve with tree sums, pseudo-inverse of D, unrolled upper solve, P^T)
 template <int N> LSD_HD void ldltSolve(const float* Ain, const float* bin, float* x)
 {
     float A[N][N];
     int tr[N];
+    float cutoff = 0;
     for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++) A[i][j] = Ain[i * N + j];
     for (int k = 0; k < N; k++) {
@@ -174,7 +188,9 @@ template <int N> LSD_HD void ldltSolve(const float* Ain, const float* bin, float
         float big = fabsf(A[k][k]);
         for (int i = k + 1; i < N; i++)
             if (fabsf(A[i][i]) > big) { big = fabsf(A[i][i]); p = i; }
+        if (k == 0) cutoff = fabsf(1.1920929e-07f * big);
         tr[k] = p;
+        if (big < cutoff) { for (int i = k; i < N; i++) tr[i] = i; break; }
         if (p != k) {
             for (int j = 0; j < k; j++) { float t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
             for (int i = p + 1; i < N; i++) { float t = A[i][k]; A[i][k] = A[i][p]; A[i][p] = t; }
@@ -194,16 +210,29 @@ template <int N> LSD_HD void ldltSolve(const float* Ain, const float* bin, float
             }
         }
         float d = A[k][k];
-        if (fabsf(d) > 0)
+        if (fabsf(d) > cutoff)
             for (int i = k + 1; i < N; i++) A[i][k] /= d;
     }
     float y[N];
     for (int i = 0; i < N; i++) y[i] = bin[i];
     for (int k = 0; k < N; k++)
         if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int i = 0; i < N; i++) { float s = y[i]; for (int j = 0; j < i; j++) s -= A[i][j] * y[j]; y[i] = s; }
-    for (int i = 0; i < N; i++) { float d = A[i][i]; y[i] = (fabsf(d) > 1.17549435e-38f) ? y[i] / d : 0.0f; }
-    for (int i = N - 1; i >= 0; i--) { float s = y[i]; for (int j = i + 1; j < N; j++) s -= A[j][i] * y[j]; y[i] = s; }
+    for (int i = 1; i < N; i++) {
+        float pr[N];
+        for (int j = 0; j < i; j++) pr[j] = A[i][j] * y[j];
+        y[i] -= treeSumF(pr, i);
+    }
+    float dmax = 0;
+    for (int i = 0; i < N; i++) if (fabsf(A[i][i]) > dmax) dmax = fabsf(A[i][i]);
+    float tol = dmax * 1.1920929e-07f;
+    if (tol < 1.0f / 3.40282347e+38f) tol = 1.0f / 3.40282347e+38f;
+    for (int i = 0; i < N; i++) { float d = A[i][i]; y[i] = (fabsf(d) > tol) ? y[i] / d : 0.0f; }
+    for (int i = N - 2; i >= 0; i--) {
+        float pr[N];
+        const int n = N - 1 - i;
+        for (int j = 0; j < n; j++) pr[j] = A[i + 1 + j][i] * y[i + 1 + j];
+        y[i] -= treeSumF(pr, n);
+    }
     for (int k = N - 1; k >= 0; k--)
         if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
     for (int i = 0; i < N; i++) x[i] = y[i];

@@ -110,15 +110,25 @@ void lsdo_mat3_inverse(const float m[9], float r[9])
 #undef M
 }
 
+/* redux_novec_unroller<Func, Derived, Start, Length> (Eigen/src/Core/Redux.h): sum(first Length/2) + sum(rest) */
+static float tree_sum_f(const float* v, int n)
+{
+    if (n == 1) return v[0];
+    int h = n/2;
+    return tree_sum_f(v, h) + tree_sum_f(v+h, n-h);
+}
+
 /* Eigen LDLT (Cholesky/LDLT.h, unblocked lower, largest-|diagonal| pivoting) + solve, float; N <= 8 */
 static int ldlt_solve_n(int N, const float* Ain, const float* bin, float* x)
 {
-    float A[8][8]; int tr[8];
+    float A[8][8]; int tr[8]; float cutoff = 0;
     for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) A[i][j] = Ain[i*N+j];
     for (int k = 0; k < N; k++) {
         int p = k; float big = fabsf(A[k][k]);
         for (int i = k+1; i < N; i++) if (fabsf(A[i][i]) > big) { big = fabsf(A[i][i]); p = i; }
+        if (k == 0) cutoff = fabsf(1.1920929e-07f * big);
         tr[k] = p;
+        if (big < cutoff) { for (int i = k; i < N; i++) tr[i] = i; break; }     /* not full rank: LDLT.h stops here */
         if (p != k) {   /* symmetric swap of rows/cols k,p in the lower triangle */
             for (int j = 0; j < k; j++) { float t = A[k][j]; A[k][j] = A[p][j]; A[p][j] = t; }
             for (int i = p+1; i < N; i++) { float t = A[i][k]; A[i][k] = A[i][p]; A[i][p] = t; }
@@ -137,14 +147,20 @@ static int ldlt_solve_n(int N, const float* Ain, const float* bin, float* x)
             }
         }
         float d = A[k][k];
-        if (fabsf(d) > 0) for (int i = k+1; i < N; i++) A[i][k] /= d;
+        if (fabsf(d) > cutoff) for (int i = k+1; i < N; i++) A[i][k] /= d;
     }
+    /* LDLT::solve (LDLT.h): dst = P b; L^-1; D^+ (pseudo-inverse, tolerance max|D| eps); L^-T; P^T.  The right-hand side is a
+     * fixed-size vector of <= 8 coefficients, so both triangular solves are Eigen's completely unrolled
+     * triangular_solver_unroller: rhs(I) -= (lhs.row(I).segment(S, n) .* rhs.segment(S, n)).sum(), the sum being the binary
+     * tree of redux_novec_unroller (split n/2 | n - n/2).  oracle/ref_shim/Eigen/Core implements the same statement. */
     float y[8];
     for (int i = 0; i < N; i++) y[i] = bin[i];
     for (int k = 0; k < N; k++) if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
-    for (int i = 0; i < N; i++) { float s = y[i]; for (int j = 0; j < i; j++) s -= A[i][j]*y[j]; y[i] = s; }
-    for (int i = 0; i < N; i++) { float d = A[i][i]; y[i] = (fabsf(d) > 1.17549435e-38f) ? y[i]/d : 0.0f; }
-    for (int i = N-1; i >= 0; i--) { float s = y[i]; for (int j = i+1; j < N; j++) s -= A[j][i]*y[j]; y[i] = s; }
+    for (int i = 1; i < N; i++) { float pr[8]; for (int j = 0; j < i; j++) pr[j] = A[i][j]*y[j]; y[i] -= tree_sum_f(pr, i); }
+    float dmax = 0; for (int i = 0; i < N; i++) if (fabsf(A[i][i]) > dmax) dmax = fabsf(A[i][i]);
+    float tol = dmax * 1.1920929e-07f; if (tol < 1.0f/3.40282347e+38f) tol = 1.0f/3.40282347e+38f;
+    for (int i = 0; i < N; i++) { float d = A[i][i]; y[i] = (fabsf(d) > tol) ? y[i]/d : 0.0f; }
+    for (int i = N-2; i >= 0; i--) { float pr[8]; int n = N-1-i; for (int j = 0; j < n; j++) pr[j] = A[i+1+j][i]*y[i+1+j]; y[i] -= tree_sum_f(pr, n); }
     for (int k = N-1; k >= 0; k--) if (tr[k] != k) { float t = y[k]; y[k] = y[tr[k]]; y[tr[k]] = t; }
     for (int i = 0; i < N; i++) x[i] = y[i];
     return 0;
@@ -166,7 +182,8 @@ static void quat_mul_##SUF(const T a[4], const T b[4], T o[4])                  
 }                                                                                                   \
 static void quat_normalize_##SUF(T q[4])                                                            \
 {   /* so3.hpp:196-202 */                                                                           \
-    T len = SQRT(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3]);                                     \
+    /* coeffs().norm(): redux tree over 4 coefficients (Redux.h): (x^2 + y^2) + (z^2 + w^2) */      \
+    T len = SQRT((q[0]*q[0] + q[1]*q[1]) + (q[2]*q[2] + q[3]*q[3]));                                 \
     q[0] /= len; q[1] /= len; q[2] /= len; q[3] /= len;                                             \
 }                                                                                                   \
 static void quat_rot_##SUF(const T q[4], const T v[3], T o[3])                                      \
@@ -209,7 +226,7 @@ void lsdo_se3##SUF##_inverse(const T a[7], T out[7])                            
 void lsdo_se3##SUF##_exp(const T a[6], T out[7])                                                    \
 {   /* se3.hpp:406-428 with so3.hpp:342-369 (expAndTheta); tangent = [upsilon, omega] */            \
     const T* om = a + 3;                                                                            \
-    T theta_sq = om[0]*om[0] + om[1]*om[1] + om[2]*om[2];                                           \
+    T theta_sq = om[0]*om[0] + (om[1]*om[1] + om[2]*om[2]);     /* omega.squaredNorm(): 1 + 2 tree */  \
     T theta = SQRT(theta_sq);                                                                       \
     T half_theta = (T)0.5*theta;                                                                    \
     T imag_factor, real_factor;                                                                     \
@@ -233,8 +250,9 @@ void lsdo_se3##SUF##_exp(const T a[6], T out[7])                                
     if (theta < (T)EPS) {                                                                           \
         quat_to_R_##SUF(q, V);                                                                      \
     } else {                                                                                        \
-        T c1 = ((T)1 - COS(theta))/theta_sq;                                                        \
-        T c2 = (theta - SIN(theta))/(theta_sq*theta);                                               \
+        T tsq = theta*theta;            /* se3.hpp:419 recomputes theta_sq from theta */             \
+        T c1 = ((T)1 - COS(theta))/tsq;                                                             \
+        T c2 = (theta - SIN(theta))/(tsq*theta);                                                    \
         for (int i = 0; i < 9; i++) V[i] = (((i%4)==0 ? (T)1 : (T)0) + c1*Om[i]) + c2*Om2[i];       \
     }                                                                                               \
     out[0] = q[0]; out[1] = q[1]; out[2] = q[2]; out[3] = q[3];                                     \
@@ -668,6 +686,24 @@ static void frame_prepareForStereoWith(lsdo_frame* f, lsdo_frame* other, const d
     f->distSquared = (float)(oTt_t[0]*oTt_t[0] + oTt_t[1]*oTt_t[1] + oTt_t[2]*oTt_t[2]);
     f->referenceID = other->id;
     f->referenceLevel = 0;
+}
+
+/* test hooks shared with oracle/ref_driver.cpp (the reference-compiled twin exports the same names) */
+void lsdo_frame_set_initialTrackedResidual(lsdo_frame* f, float v) { f->initialTrackedResidual = v; }
+void lsdo_ref_prepareForStereoWith(lsdo_frame* frame, lsdo_frame* kf, const double thisToOther_qts[8], const float K[9], float out[30])
+{
+    frame_prepareForStereoWith(frame, kf, thisToOther_qts, thisToOther_qts + 4, thisToOther_qts[7], K);
+    int k = 0;
+    for (int i = 0; i < 9; i++) out[k++] = frame->K_otherToThis_R[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->K_otherToThis_t[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->otherToThis_t[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->thisToOther_t[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->otherToThis_R_row0[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->otherToThis_R_row1[i];
+    for (int i = 0; i < 3; i++) out[k++] = frame->otherToThis_R_row2[i];
+    out[k++] = frame->distSquared;
+    out[k++] = (float)frame->referenceID;
+    out[k++] = (float)frame->referenceLevel;
 }
 
 /* ------------------------------------------------------------------------------------------

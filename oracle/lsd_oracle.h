@@ -172,6 +172,7 @@ int   lsdo_frame_numPoints(const lsdo_frame* f);
 int   lsdo_frame_depthHasBeenUpdatedFlag(const lsdo_frame* f);
 void  lsdo_frame_set_depthHasBeenUpdatedFlag(lsdo_frame* f, int v);
 float lsdo_frame_initialTrackedResidual(const lsdo_frame* f);
+void  lsdo_frame_set_initialTrackedResidual(lsdo_frame* f, float v);   /* test hook: a frame tracked elsewhere */
 void  lsdo_frame_get_thisToParent(const lsdo_frame* f, double qts[8]);  /* Sim3: q(4) t(3) s */
 void  lsdo_frame_set_thisToParent(lsdo_frame* f, const double qts[8], lsdo_frame* parent);
 int   lsdo_frame_numFramesTrackedOnThis(const lsdo_frame* f);
@@ -234,6 +235,9 @@ void lsdo_depthmap_observeDepth(lsdo_depthmap* d, lsdo_frame** refs, int n_refs)
 void lsdo_depthmap_regularizeFillHoles(lsdo_depthmap* d);
 void lsdo_depthmap_regularize(lsdo_depthmap* d, int removeOcclusions, int validityTH);
 void lsdo_depthmap_propagateDepth(lsdo_depthmap* d, lsdo_frame* new_kf);
+/* the stereo constants Frame::prepareForStereoWith leaves in `frame` (Frame.cpp:295-317): K_otherToThis_R[9], K_otherToThis_t,
+ * otherToThis_t, thisToOther_t, otherToThis_R_row0..2, distSquared, referenceID, referenceLevel */
+void lsdo_ref_prepareForStereoWith(lsdo_frame* frame, lsdo_frame* kf, const double thisToOther_qts[8], const float K[9], float out[30]);
 /* per-stage EMA timers of the reference (DepthMap.cpp:1126-1162), ms of the last call */
 void lsdo_depthmap_last_timings(const lsdo_depthmap* d, float out_ms[8]);
 

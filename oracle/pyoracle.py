@@ -1,6 +1,11 @@
 """ctypes binding of the CPU ORACLE (oracle/lsd_oracle.c).  TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / ``--impl reference`` legs import this.
+
+Flavours (the ``fast`` argument everywhere): False = strict-IEEE C restatement (parity), True = its -O3 timing build,
+"ref" = oracle/_ref/liblsd_ref.so and "ref_sse" = oracle/_ref/liblsd_ref_sse.so -- the reference's own sources compiled
+unmodified (oracle/ref_build.py, oracle/ref_driver.cpp) behind the same C names; entry points the reference-compiled
+library does not export are simply absent there.
 """
 from __future__ import annotations
 
@@ -85,21 +90,40 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", _HERE] + (["-B"] if force else []), check=True, capture_output=True)
 
 
+def ref_available() -> bool:
+    """oracle/_ref present (prebuilt, or buildable because /root/reference is here)?"""
+    from oracle import ref_build
+    return ref_build.built() or ref_build.available()
+
+
 _libs: dict = {}
+_REF_NAMES = {"ref": "liblsd_ref.so", "ref_sse": "liblsd_ref_sse.so", "ref_legacy_math": "liblsd_ref_legacy_math.so"}
 
 
-def lib(fast: bool = False):
-    name = "liblsd_oracle_fast.so" if fast else "liblsd_oracle.so"
+def lib(fast=False):
+    if isinstance(fast, str):
+        name = os.path.join("_ref", _REF_NAMES[fast])
+    else:
+        name = "liblsd_oracle_fast.so" if fast else "liblsd_oracle.so"
     if name in _libs:
         return _libs[name]
     path = os.path.join(_HERE, name)
-    if not os.path.exists(path):
+    if isinstance(fast, str):
+        from oracle import ref_build
+        if not ref_build.build():
+            raise RuntimeError("oracle/_ref is not built and /root/reference is not available to build it")
+    elif not os.path.exists(path):
         build()
     L = C.CDLL(path)
     fp, dp, ip, u8p, vp = C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_uint8), C.c_void_p
 
     def sig(name, res, *args):
-        f = getattr(L, name)
+        try:
+            f = getattr(L, name)
+        except AttributeError:
+            if isinstance(fast, str) or name.startswith("lsdo_ref_"):
+                return                      # not exported by the reference-compiled library / only exported by it
+            raise
         f.restype = res
         f.argtypes = list(args)
 
@@ -134,6 +158,7 @@ def lib(fast: bool = False):
     sig("lsdo_frame_depthHasBeenUpdatedFlag", C.c_int, vp)
     sig("lsdo_frame_set_depthHasBeenUpdatedFlag", None, vp, C.c_int)
     sig("lsdo_frame_initialTrackedResidual", C.c_float, vp)
+    sig("lsdo_frame_set_initialTrackedResidual", None, vp, C.c_float)
     sig("lsdo_frame_get_thisToParent", None, vp, dp)
     sig("lsdo_frame_set_thisToParent", None, vp, dp, vp)
     sig("lsdo_frame_numFramesTrackedOnThis", C.c_int, vp)
@@ -176,6 +201,7 @@ def lib(fast: bool = False):
     sig("lsdo_depthmap_regularize", None, vp, C.c_int, C.c_int)
     sig("lsdo_depthmap_propagateDepth", None, vp, vp)
     sig("lsdo_depthmap_last_timings", None, vp, fp)
+    sig("lsdo_ref_prepareForStereoWith", None, vp, vp, dp, fp, fp)
     _libs[name] = L
     return L
 
@@ -188,7 +214,7 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def default_track_settings(fast: bool = False, main_tracker: bool = True) -> TrackSettings:
+def default_track_settings(fast=False, main_tracker: bool = True) -> TrackSettings:
     s = TrackSettings()
     lib(fast).lsdo_default_track_settings(C.byref(s))
     if main_tracker:                       # SlamSystem.cpp:80-81
@@ -197,7 +223,7 @@ def default_track_settings(fast: bool = False, main_tracker: bool = True) -> Tra
     return s
 
 
-def set_globals(fast: bool = False, **kw) -> Globals:
+def set_globals(fast=False, **kw) -> Globals:
     g = Globals()
     lib(fast).lsdo_default_globals(C.byref(g))
     for k, v in kw.items():
@@ -209,7 +235,7 @@ def set_globals(fast: bool = False, **kw) -> Globals:
 class Frame:
     """Mirror of lsd_slam::Frame for the oracle (DataStructures/Frame.h)."""
 
-    def __init__(self, fid: int, image_u8: np.ndarray, K: np.ndarray, fast: bool = False):
+    def __init__(self, fid: int, image_u8: np.ndarray, K: np.ndarray, fast=False):
         self.L = lib(fast)
         self.h, self.w = image_u8.shape
         img = np.ascontiguousarray(image_u8, np.uint8)
@@ -395,7 +421,7 @@ def se3_eval(kf: Frame, frame: Frame, level: int, refToFrame_qt, a=1.0, b=0.0, s
 class DepthMap:
     """Mirror of lsd_slam::DepthMap for the oracle (DepthEstimation/DepthMap.h)."""
 
-    def __init__(self, w, h, K, fast: bool = False):
+    def __init__(self, w, h, K, fast=False):
         self.L = lib(fast)
         self.w, self.h = w, h
         Kf = np.ascontiguousarray(K, np.float32).reshape(9)

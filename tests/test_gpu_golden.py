@@ -1,5 +1,6 @@
-"""The CUDA path against the COMMITTED golden fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py from the
-oracle): bit-exact for the integer / per-pixel outputs, north_star tolerances for the tracked poses and the map that follows
+"""The CUDA path against the COMMITTED golden fixtures (tests/golden/*.npz, produced by tests/golden/make_golden.py:
+reference_320x240.npz and the Sim3 entries are outputs of the reference's own sources compiled unmodified -- oracle/_ref --,
+the keyframe-output and undistorter entries come from the C oracle): bit-exact for the integer / per-pixel outputs, north_star tolerances for the tracked poses and the map that follows
 from them.  Complements the live oracle comparisons of the other -m gpu tests."""
 import os
 import zlib
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def test_hot_path_against_golden(gpu_ctx_small, seq_small, frames_small):
-    gold = np.load(os.path.join(HERE, "golden", "oracle_320x240.npz"))
+    gold = np.load(os.path.join(HERE, "golden", "reference_320x240.npz"))
     ctx = gpu_ctx_small
     ctx.upload(0, frames_small[0][0])
     ctx.set_depth_gt(0, frames_small[0][1])
