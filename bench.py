@@ -3,11 +3,18 @@
 forced finalizeKeyFrame + createKeyFrame every 20 frames) on a synthetic 640x480 grayscale stream.
 
   python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one stream per GPU)
-  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU algorithm (oracle, SSE + 4 threads)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU code (oracle/_ref, ENABLE_SSE build,
+                                                            # 1 tracking + 4 mapping threads); the C port if _ref is absent
 
-One "step" = one frame through {Frame construction, trackFrame, mapping}.  `value` is measured with the raw u8
-frames already parked in HBM (prefetch ring); `e2e` is the same loop fed from HOST buffers through the C ABI with
-the H2D copy of every frame and the D2H read of the tracking result inside the timed region.
+One "step" = one frame through {Frame construction, trackFrame, mapping}.  `value` is measured with the raw u8 frames already
+parked in HBM (prefetch ring); `e2e` is the same loop fed from HOST buffers through the C ABI with the H2D copy of every frame
+and the D2H read of the tracking result inside the timed region.
+
+Timing: W warm-up steps, then R passes of EXACTLY K steps each on consecutive fresh frames of the stream; every pass is
+bracketed by barrier + synchronize, its time is the sum of the K per-step CUDA-event times (L2 flushed between steps), MAX
+over ranks; `value` is the MEDIAN pass (all passes are in the JSON).  With K a multiple of 20 every pass holds the same
+number of keyframe changes.  Parity is asserted in the same run (world size 1): the poses of the timed frames are compared
+with the CPU oracle's scalar path on the same frames; the line carries `parity` and the run fails above 1e-4.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -15,7 +22,6 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -27,15 +33,47 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec (track+depth-update) at 640x480"
 KF_EVERY = 20
+POSE_TOL = 1e-4           # north_star: SE3 pose within 1e-4 rel on translation / rotation
 
 
 def rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
+def n_passes(steps: int) -> int:
+    return int(min(5, max(1, 120 // max(steps, 1))))
+
+
+def nvml_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        parts = vis.split(",")
+        if local_rank < len(parts) and parts[local_rank].strip().isdigit():
+            return int(parts[local_rank])
+    return local_rank
+
+
+def pin_to_gpu_numa_node(local_rank: int):
+    """bind this rank to the host cores next to its GPU (NVML ideal CPU affinity = the GPU's NUMA node): on a 2-socket host
+    an unpinned rank's polling thread can sit across the socket link from its GPU.  Returns the number of cores or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(nvml_index(local_rank))
+        n = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n)
+        cores = [64 * i + b for i, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        cores = [c for c in cores if c in os.sched_getaffinity(0)]
+        if cores:
+            os.sched_setaffinity(0, cores)
+            return len(cores)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
-    """SM clocks and throttle reasons sampled DURING the timed region (NVML every ~2 ms in a thread; the
-    nvidia-smi -lms recipe of B200_PROFILING.md is too coarse for a 30 ms timed region)."""
+    """SM clocks and throttle reasons sampled DURING the timed passes (NVML every 20 ms from a thread)."""
 
     def __init__(self, index: int):
         self.index = index
@@ -50,9 +88,7 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
             self.nv = pynvml
             self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception as e:      # pragma: no cover
@@ -74,7 +110,7 @@ class ClockSampler:
             except Exception as e:  # pragma: no cover
                 self.err = repr(e)
                 return
-            time.sleep(0.002)
+            self._stop.wait(0.02)
 
     def stop(self):
         self._stop.set()
@@ -97,54 +133,52 @@ def render_frames(w, h, seed, n):
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's algorithm (oracle, timing flavour: SSE tracker loops + 4 mapping threads)
+# CPU arm
 # ------------------------------------------------------------------------------------------------------------
-def cpu_loop(seq, frames, n_steps, warmup, time_budget_s=25.0, multi_threading=1):
-    """Returns (fps, ms_per_step, frames_timed, threads).  Same loop as lsd_slam_b200/stream.py.
+def cpu_flavour():
+    """(flavour, kind, description): the reference's own sources (oracle/_ref, stock ENABLE_SSE build) when they are
+    here, else the oracle's restatement of the same SSE loops"""
+    from oracle import pyoracle as po
+    if po.ref_available():
+        return "ref_sse", "reference", ("lsd_slam_core's own DepthMap.cpp / SE3Tracker.cpp / Frame.cpp compiled unmodified "
+                                        "(oracle/_ref, -DENABLE_SSE -O3 -march=x86-64-v3)")
+    return True, "port", "oracle/lsd_oracle.c -O3 (its restatement of the reference's SSE tracker loops)"
+
+
+def cpu_loop(seq, frames, n_steps, warmup, time_budget_s=25.0, multi_threading=1, flavour=None, kf_every=KF_EVERY):
+    """Returns dict(fps, ms, n, threads, poses, kind, what).  Same loop as lsd_slam_b200/stream.py (oracle/cpu_stream.py).
     multi_threading=0: the reference's single-threaded fallback (IndexThreadReduce.h:72-77), i.e. one busy core."""
     from oracle import pyoracle as po
+    from oracle.cpu_stream import CpuStream
     po.build()
-    po.set_globals(fast=True, useSSE=1, multiThreading=multi_threading)
-    L = po.lib(fast=True)
-    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
-    img0, d0 = frames[0]
-    kf = po.Frame(0, img0, seq.K, fast=True)
-    kf.setDepthFromGroundTruth(d0)
-    dm = po.DepthMap(seq.w, seq.h, seq.K, fast=True)
-    dm.initializeFromGTDepth(kf)
-    st = po.default_track_settings(fast=True)
-    last = ident
+    fl, kind, what = cpu_flavour() if flavour is None else (flavour, "port", "oracle/lsd_oracle.c, strict IEEE scalar path")
+    if fl is True:
+        po.set_globals(True, useSSE=1, multiThreading=multi_threading)
+    else:
+        po.set_globals(fl, multiThreading=multi_threading)
+    cs = CpuStream(seq, fl, kf_every=kf_every)
+    cs.init_gt(0, frames[0][0], frames[0][1])
     times = []
     t_begin = time.perf_counter()
-    n_tracked = 0
-    keep = [kf]
     for k in range(1, len(frames)):
-        img = frames[k][0]
-        t0 = time.perf_counter()
-        f = po.Frame(k, img, seq.K, fast=True)                      # Frame::Frame(uchar*) (u8 -> f32)
-        if L.lsdo_frame_depthHasBeenUpdatedFlag(kf.ptr):
-            L.lsdo_frame_set_depthHasBeenUpdatedFlag(kf.ptr, 0)     # importFrame, SlamSystem.cpp:907-912
-        r = po.se3_track(kf, f, last, st)
-        n_tracked += 1
-        if n_tracked % KF_EVERY == 0:
-            dm.finalizeKeyFrame()
-            dm.createKeyFrame(f)
-            kf = f
-            last = ident
-        else:
-            dm.updateKeyframe([f])
-            L.lsdo_frame_clear_refPixelWasGood(f.ptr)
-            last = np.array(r.frameToRef_qt)
-        dt = time.perf_counter() - t0
-        keep.append(f)
-        if len(keep) > 3:
-            keep.pop(0) if keep[0] is not kf else keep.pop(1)
+        _, dt = cs.step(k, frames[k][0])
         if k > warmup:
             times.append(dt)
-        if len(times) >= n_steps or (time.perf_counter() - t_begin) > time_budget_s:
+        if len(times) >= n_steps or (time_budget_s and (time.perf_counter() - t_begin) > time_budget_s):
             break
     total = float(np.sum(times))
-    return len(times) / total, 1e3 * total / len(times), len(times), (1 + 4) if multi_threading else 1
+    return dict(fps=len(times) / total, ms=1e3 * total / len(times), n=len(times), threads=(1 + 4) if multi_threading else 1,
+                poses=np.array(cs.poses), kind=kind, what=what)
+
+
+def pose_errors(a, b):
+    """per-frame (relative translation error, rotation angle error [rad]) between two pose lists (qx,qy,qz,qw,t)"""
+    a, b = np.asarray(a), np.asarray(b)
+    n = min(len(a), len(b))
+    dt = np.linalg.norm(a[:n, 4:7] - b[:n, 4:7], axis=1) / np.maximum(np.linalg.norm(b[:n, 4:7], axis=1), 1e-12)
+    d = np.abs(np.sum(a[:n, :4] * b[:n, :4], axis=1))
+    ang = 2 * np.arccos(np.minimum(1.0, d))
+    return dt, ang
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -159,17 +193,30 @@ def gpu_run(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    pinned_cores = pin_to_gpu_numa_node(local_rank)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner out of stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sync_t = torch.zeros(1, device="cuda")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def settle_collectives():
+        """the communicator's FIRST collectives (connection set-up, proxy threads) happen here, before any warm-up or
+        timed frame of a leg -- not right in front of the timed window (round 1's N = 8 outlier)"""
+        if world > 1:
+            for _ in range(3):
+                dist.all_reduce(sync_t)
+                dist.barrier()
+        torch.cuda.synchronize()
+
     w, h = args.width, args.height
-    n_frames = args.warmup + args.steps + 1
+    R, K, W = n_passes(args.steps), args.steps, args.warmup
+    n_frames = W + R * K + 1
     # independent streams: one per GPU, seeds 1234 + 1000*rank (SURVEY 8d, config 4)
     seq, frames = render_frames(w, h, 1234 + 1000 * rank, n_frames)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
@@ -187,38 +234,54 @@ def gpu_run(args, rank, world, local_rank):
                 ctx.stage_put(k, frames[k][0])
         gs = GpuStream(ctx, mode=args.mode, kf_every=KF_EVERY)
         gs.init_gt(0, frames[0][0], frames[0][1])
-        for k in range(1, args.warmup + 1):
+        settle_collectives()
+        for k in range(1, W + 1):
             gs.step(k, pinned_np[k]) if leg == "e2e" else gs.step(k, stage_index=k)
         ctx.synchronize()
         ctx.track_kernel_stats(reset=1)
-        sampler = ClockSampler(local_rank)
-        barrier()
+        sampler = ClockSampler(nvml_index(local_rank))
         sampler.start()
         launches0 = ctx.launch_count()
         step_ms = []
-        wall0 = time.perf_counter()
-        for k in range(args.warmup + 1, args.warmup + args.steps + 1):
-            flush.fill_(k & 0xff)                                          # L2 flush between timed steps
-            torch.cuda.synchronize()
-            ctx.timer_begin(0)
-            if leg == "e2e":
-                pose = gs.step(k, pinned_np[k])                            # pinned host u8 in, pose (D2H) out
-            else:
-                pose = gs.step(k, stage_index=k)
-            ctx.timer_end(0)
-            step_ms.append(ctx.timer_ms(0))
-        barrier()
-        wall = time.perf_counter() - wall0
+        pass_ms = []
+        wall = 0.0
+        for r in range(R):
+            barrier()
+            wall0 = time.perf_counter()
+            acc = 0.0
+            for k in range(W + 1 + r * K, W + 1 + (r + 1) * K):
+                flush.fill_(k & 0xff)                                          # L2 flush between timed steps
+                torch.cuda.synchronize()
+                ctx.timer_begin(0)
+                if leg == "e2e":
+                    gs.step(k, pinned_np[k])                                   # pinned host u8 in, pose (D2H) out
+                else:
+                    gs.step(k, stage_index=k)
+                ctx.timer_end(0)
+                ms = ctx.timer_ms(0)
+                step_ms.append(ms)
+                acc += ms
+            barrier()
+            wall += time.perf_counter() - wall0
+            pass_ms.append(acc)
         clocks = sampler.stop()
         launches = ctx.launch_count() - launches0
         kms, klaunch, kbytes = ctx.track_kernel_stats(reset=2)
-        total_ms = float(np.sum(step_ms))
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor(pass_ms, dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        results[leg] = dict(total_ms=float(t.item()), launches=launches, clocks=clocks, wall=wall,
-                            kms=kms, klaunch=klaunch, kbytes=kbytes, poses=np.array(gs.poses[-args.steps:]),
-                            p50=float(np.median(step_ms)), p95=float(np.percentile(step_ms, 95)))
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)                          # per pass: the slowest rank
+        pass_max = [float(x) for x in t.tolist()]
+        sm = np.array(step_ms)
+        mine = {"rank": rank, "sum_ms": float(sm.sum()), "p50": float(np.median(sm)), "p95": float(np.percentile(sm, 95)),
+                "max_step_ms": float(sm.max()), "argmax_step": int(sm.argmax()), "pass_ms": [float(x) for x in pass_ms],
+                "sm_mhz": clocks.get("sm_mhz"), "reasons": clocks.get("reasons"), "pinned_cores": pinned_cores}
+        per_rank = [mine]
+        if world > 1:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine)
+            per_rank = gathered
+        results[leg] = dict(pass_ms=pass_max, launches=launches, clocks=clocks, wall=wall, kms=kms, klaunch=klaunch, kbytes=kbytes,
+                            poses=np.array(gs.poses), p50=float(np.median(sm)), p95=float(np.percentile(sm, 95)), per_rank=per_rank)
         ctx.close()
     return seq, frames, results
 
@@ -233,14 +296,17 @@ def main():
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--mode", type=int, default=1, help="tracker: 1 = device-resident LM, 0 = host-driven LM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity check (profiling runs only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world, local_rank = rank_world()
     metric = METRIC if (args.width, args.height) == (640, 480) else METRIC.replace("640x480", f"{args.width}x{args.height}")
     workload = f"synthetic {args.width}x{args.height} grayscale stream, full track+map loop, forced keyframe every {KF_EVERY} frames"
+    R = n_passes(args.steps)
     config = {"workload": workload, "width": args.width, "height": args.height, "pyramid_levels_tracked": "L4..L1",
               "kf_every": KF_EVERY, "streams_per_gpu": 1, "parallelism": f"{world} independent stream(s), one per GPU, no collective",
               "l2": "flushed between timed steps (256 MiB fill); per-step CUDA-event times summed",
+              "passes": R, "statistic": f"median of {R} pass(es) of exactly {args.steps} steps each (max over ranks per pass)",
               "init": "gtDepthInit (SlamSystem.cpp:831-854)",
               "e2e_input": "one 8-bit frame per step in page-locked host memory, copied H2D inside the timed step; result block read back per step"}
 
@@ -250,16 +316,18 @@ def main():
         n_frames = args.warmup + args.steps + 1
         seq, frames = render_frames(args.width, args.height, 1234, n_frames)
         config["semi_dense_fraction"] = round(seq.density, 4)
-        fps, ms, n, threads = cpu_loop(seq, frames, args.steps, args.warmup, time_budget_s=120.0)
-        fps1, _, n1, _ = cpu_loop(seq, frames, min(args.steps, 30), args.warmup, time_budget_s=30.0, multi_threading=0)
-        line = {"impl": "reference", "metric": metric, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": n,
-                "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        config["passes"], config["statistic"] = 1, f"mean over {args.steps} steps (wall clock, CPU)"
+        c = cpu_loop(seq, frames, args.steps, args.warmup, time_budget_s=150.0)
+        c1 = cpu_loop(seq, frames, min(args.steps, 30), args.warmup, time_budget_s=40.0, multi_threading=0)
+        line = {"impl": "reference", "metric": metric, "value": c["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": c["n"],
+                "warmup": args.warmup, "ms_per_step": c["ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                                 "sample": f"{n} frames of the same stream; oracle -O3 x86-64-v3, SSE tracker loops, 4 mapping threads + 1 tracking thread (reference threading)",
+                "cpu_baseline": {"value": c["fps"], "unit": "frames/s", "cores": c["threads"], "kind": c["kind"],
+                                 "sample": f"{c['n']} frames of the same stream; {c['what']}; 1 tracking thread + 4 mapping threads "
+                                           "(MAPPING_THREADS, util/settings.h:94) as the reference threads it",
                                  "host_cores": os.cpu_count(),
-                                 "single_core": {"value": fps1, "unit": "frames/s", "sample": f"{n1} frames, multiThreading = false"}},
-                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                                 "single_core": {"value": c1["fps"], "unit": "frames/s", "sample": f"{c1['n']} frames, multiThreading = false"}},
+                "e2e": {"value": c["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
 
@@ -281,8 +349,10 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json, copy burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     r, e = res["resident"], res["e2e"]
-    fps = world * args.steps / (r["total_ms"] * 1e-3)
-    fps_e2e = world * args.steps / (e["total_ms"] * 1e-3)
+    K = args.steps
+    pass_r, pass_e = float(np.median(r["pass_ms"])), float(np.median(e["pass_ms"]))
+    fps = world * K / (pass_r * 1e-3)
+    fps_e2e = world * K / (pass_e * 1e-3)
     traffic = None
     try:        # DRAM bytes per launch of the tracking kernel from the committed ncu --set full capture (640x480 only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_track_persistent"]
@@ -291,30 +361,57 @@ def main():
     except Exception:
         pass
     ach = (r["kbytes"] / max(r["klaunch"], 1)) / (r["kms"] * 1e-3 / max(r["klaunch"], 1)) / 1e9 if r["kms"] > 0 else 0.0
-    line = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    total_r = float(np.sum([p["sum_ms"] for p in r["per_rank"] if p["rank"] == 0]))
+    line = {"metric": metric, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": pass_r / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": config,
             "clocks": r["clocks"],
             "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": args.width * args.height,
-                    "d2h_bytes_per_step": 144, "ms_per_step": e["total_ms"] / args.steps},
-            "gpu_launches": int(r["launches"]),
-            "step_ms": {"p50": r["p50"], "p95": r["p95"], "wall_ms_per_step_incl_flush": 1e3 * r["wall"] / args.steps},
+                    "d2h_bytes_per_step": 144, "ms_per_step": pass_e / K, "pass_ms": e["pass_ms"]},
+            "gpu_launches": int(round(r["launches"] / R)),
+            "pass_ms": r["pass_ms"],
+            "step_ms": {"p50": r["p50"], "p95": r["p95"], "wall_ms_per_step_incl_flush": 1e3 * r["wall"] / (R * K)},
+            "per_rank": r["per_rank"], "per_rank_e2e": e["per_rank"],
             "roofline": {"kernel": "warp/residual/JtJ (SE3 tracking) kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                          "unit": "GB/s", "frac": ach / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
-                         "share_of_step": r["kms"] / max(r["total_ms"], 1e-9),
+                         "share_of_step": r["kms"] / max(total_r, 1e-9),
                          "launches": int(r["klaunch"]), "avg_launch_us": 1e3 * r["kms"] / max(r["klaunch"], 1),
                          "algorithmic_bytes_per_launch": r["kbytes"] / max(r["klaunch"], 1),
+                         "algorithmic_bytes": "SURVEY 8d B_fused: per evaluation 20 B per valid point + 16 B per texel of the gradient level"
+                                              " (+5 B per point on L1) + 160 B, summed over the evaluations of the launch",
                          "note": "working set (<= 2.2 MB per level) is L2/SMEM resident: the kernel is latency-bound, not HBM-bound"},
             "tracker_mode": args.mode}
+    failed = None
+    if world == 1 and not args.no_parity:
+        # parity asserted in the same run: the oracle's scalar path (bit-identical to the reference-compiled scalar
+        # build, tests/test_ref_pin.py) over the same frames, outside the timed region
+        n_cmp = min(len(frames) - 1, args.warmup + R * K)
+        o = cpu_loop(seq, frames[: n_cmp + 1], n_cmp, 0, time_budget_s=0, flavour=False)
+        par = {"frames": int(n_cmp), "tolerance": POSE_TOL, "against": "CPU oracle, scalar path (= the reference's sources compiled without ENABLE_SSE, bit for bit)"}
+        for leg in ("resident", "e2e"):
+            dt, ang = pose_errors(res[leg]["poses"][:n_cmp], o["poses"][:n_cmp])
+            par[leg] = {"max_pose_rel": float(dt.max()), "max_rot_rad": float(ang.max()), "argmax_frame": int(dt.argmax()) + 1}
+        par["max_pose_rel"] = max(par["resident"]["max_pose_rel"], par["e2e"]["max_pose_rel"])
+        par["ok"] = bool(par["max_pose_rel"] <= POSE_TOL)
+        line["parity"] = par
+        if not par["ok"]:
+            failed = f"parity: pose error {par['max_pose_rel']:.3e} > {POSE_TOL}"
     if not args.no_cpu_baseline and world == 1:
-        n_cpu = min(len(frames) - 1 - args.warmup, args.steps)
-        cfps, cms, n, threads = cpu_loop(seq, frames, n_cpu, args.warmup, time_budget_s=25.0)
-        cfps1, _, n1, _ = cpu_loop(seq, frames, min(n_cpu, 30), args.warmup, time_budget_s=20.0, multi_threading=0)
-        line["cpu_baseline"] = {"value": cfps, "unit": "frames/s", "cores": threads, "kind": "port", "ms_per_step": cms,
-                                "sample": f"{n} frames of the same stream; oracle -O3 x86-64-v3, SSE tracker loops, 4 mapping threads + 1 tracking thread",
+        n_cpu = min(len(frames) - 1 - args.warmup, K)
+        c = cpu_loop(seq, frames, n_cpu, args.warmup, time_budget_s=25.0)
+        c1 = cpu_loop(seq, frames, min(n_cpu, 30), args.warmup, time_budget_s=20.0, multi_threading=0)
+        line["cpu_baseline"] = {"value": c["fps"], "unit": "frames/s", "cores": c["threads"], "kind": c["kind"], "ms_per_step": c["ms"],
+                                "sample": f"{c['n']} frames of the same stream; {c['what']}; 1 tracking thread + 4 mapping threads",
                                 "host_cores": os.cpu_count(),
-                                "single_core": {"value": cfps1, "unit": "frames/s", "sample": f"{n1} frames, multiThreading = false"}}
+                                "single_core": {"value": c1["fps"], "unit": "frames/s", "sample": f"{c1['n']} frames, multiThreading = false"}}
+        if "parity" in line and c["kind"] == "reference":
+            # how far the stock (SSE) build of the reference is from its own scalar path on this stream
+            dt, ang = pose_errors(c["poses"], o["poses"][: len(c["poses"])])
+            line["parity"]["reference_sse_vs_scalar"] = {"max_pose_rel": float(dt.max()), "median_pose_rel": float(np.median(dt)), "frames": int(len(dt))}
     print(json.dumps(line))
+    if failed:
+        sys.stderr.write(failed + "\n")
+        sys.exit(3)
 
 
 if __name__ == "__main__":

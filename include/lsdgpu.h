@@ -109,6 +109,7 @@ void lsdgpu_destroy(lsdgpu_ctx* ctx);
 const char* lsdgpu_last_error(const lsdgpu_ctx* ctx);
 int  lsdgpu_abi_version(void);
 int  lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g);      /* util/settings.cpp:77-88 */
+int  lsdgpu_get_globals(const lsdgpu_ctx* ctx, lsdgpu_globals* g);      /* the values in force (the reference reads the globals directly) */
 void lsdgpu_default_globals(lsdgpu_globals* g);
 void lsdgpu_default_track_settings(lsdgpu_track_settings* s);            /* util/settings.h:358-386 */
 int  lsdgpu_synchronize(lsdgpu_ctx* ctx);

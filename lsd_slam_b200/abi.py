@@ -92,6 +92,7 @@ SYMBOLS = [
     ("lsdgpu_last_error", C.c_char_p, [_vp]),
     ("lsdgpu_abi_version", C.c_int, []),
     ("lsdgpu_set_globals", C.c_int, [_vp, C.POINTER(Globals)]),
+    ("lsdgpu_get_globals", C.c_int, [_vp, C.POINTER(Globals)]),
     ("lsdgpu_default_globals", None, [C.POINTER(Globals)]),
     ("lsdgpu_default_track_settings", None, [C.POINTER(TrackSettings)]),
     ("lsdgpu_synchronize", C.c_int, [_vp]),

@@ -208,6 +208,7 @@ extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
 
 extern "C" const char* lsdgpu_last_error(const lsdgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" int lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g) { ctx->g = *g; return 0; }
+extern "C" int lsdgpu_get_globals(const lsdgpu_ctx* ctx, lsdgpu_globals* g) { *g = ctx->g; return 0; }
 extern "C" int lsdgpu_synchronize(lsdgpu_ctx* ctx)
 {
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -531,7 +532,9 @@ static int runEval(lsdgpu_ctx* ctx, const EvalLevel& L, const lsd::SE3<float>& r
     C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; C.var_weight = s->var_weight; C.huber_half = s->huber_d / 2;
     const int nBlocks = divUp(L.w * L.h, EVAL_THREADS);
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
-    k_se3_eval<<<nBlocks, EVAL_THREADS, 0, ctx->stream>>>(L, P, C, ctx->evPartials, ctx->evCounter, ctx->dEvOut);
+    // last-block counter of its own (word 16): evCounter[0] is the persistent tracker's monotonic barrier counter, which must
+    // never be reset or counted on by anybody else (mode-1 and mode-0 / parity-hook calls interleave on one context)
+    k_se3_eval<<<nBlocks, EVAL_THREADS, 0, ctx->stream>>>(L, P, C, ctx->evPartials, ctx->evCounter + 16, ctx->dEvOut);
     LAUNCH(ctx);
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kEnd, ctx->stream);
     LSD_CHECK(ctx, cudaGetLastError());

@@ -16,6 +16,7 @@
 #include "internal.cuh"
 #include "track.cuh"
 #include <stdlib.h>
+#include <atomic>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -584,6 +585,7 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
     const int lvl = lm.lvl;
     const float warped = s[CH_GOOD] + s[CH_BAD];
     sh.action = ACT_CONTINUE;
+    // MIN_GOODPERALL_PIXEL_ABSMIN is the float literal 0.01f (util/settings.h:170): the reference's threshold is a float product
     if (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) {                          // :324-329 / :369-374
         lm.diverged = 1;
         sh.action = ACT_DIVERGED;
@@ -865,6 +867,9 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
         }
         if (!done) LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    // the other fields of the mapped result block are read with plain loads below: keep them behind the doneSeq read.  Block 0
+    // publishes doneSeq while other CTAs may still be exiting, so only STREAM-ORDERED consumers may assume the kernel has retired.
+    std::atomic_thread_fence(std::memory_order_acquire);
     ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
 
     if (ctx->profileTrackKernel) {           // the event pair is read lazily (flushTrackProfile): no extra sync on the path

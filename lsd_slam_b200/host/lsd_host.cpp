@@ -277,12 +277,17 @@ void DepthMap::initializeRandomly(Frame* new_frame)
 {   // DepthMap.cpp:883-916: the rand() draws stay on the host, the hypotheses are uploaded
     std::vector<float> maxGrad((size_t)width_ * height_);
     dev_.check(lsdgpu_frame_download(dev_.raw(), new_frame->id(), LSDGPU_BUF_MAXGRAD, 0, maxGrad.data()), "DepthMap::initializeRandomly");
+    lsdgpu_globals g;
+    dev_.check(lsdgpu_get_globals(dev_.raw(), &g), "DepthMap::initializeRandomly");
+    const float minAbsGradCreate = g.minUseGrad;                    // MIN_ABS_GRAD_CREATE == minUseGrad (util/settings.h:157)
+    // interior pixels as in the reference; the border keeps the constructor's state (isValid = false, blacklisted = 0),
+    // which is what a freshly constructed / reset DepthMap holds there (DepthMapPixelHypothesis.h:63-64, DepthMap.cpp:102-109)
     std::vector<lsdgpu_hyp> hyp((size_t)width_ * height_);
     std::memset(hyp.data(), 0, hyp.size() * sizeof(lsdgpu_hyp));
     for (int y = 1; y < height_ - 1; y++)
         for (int x = 1; x < width_ - 1; x++) {
             lsdgpu_hyp& h = hyp[x + y * width_];
-            if (maxGrad[x + y * width_] > 5.0f /* MIN_ABS_GRAD_CREATE */) {
+            if (maxGrad[x + y * width_] > minAbsGradCreate) {
                 float idepth = 0.5f + 1.0f * ((rand() % 100001) / 100000.0f);
                 h.isValid = 1; h.blacklisted = 0; h.nextStereoFrameMinID = 0; h.validity_counter = 20;
                 h.idepth = idepth; h.idepth_smoothed = idepth;

@@ -466,7 +466,7 @@ void lsdo_depthmap_updateKeyframe(lsdo_depthmap* d, lsdo_frame** refs, int n)
     for (int i = 0; i < n; i++) q.push_back(refs[i]->f);
     d->d->updateKeyframe(q);
 }
-void lsdo_depthmap_createKeyFrame(lsdo_depthmap* d, lsdo_frame* nk) { flushPool(); d->keep.push_back(nk->f); d->d->createKeyFrame(nk->f.get()); }
+void lsdo_depthmap_createKeyFrame(lsdo_depthmap* d, lsdo_frame* nk) { flushPool(); d->keep.push_back(nk->f); d->d->createKeyFrame(nk->f.get()); while (d->keep.size() > 3) d->keep.erase(d->keep.begin()); }
 void lsdo_depthmap_finalizeKeyFrame(lsdo_depthmap* d) { d->d->finalizeKeyFrame(); }
 const lsdo_hyp* lsdo_depthmap_current(const lsdo_depthmap* d) { return reinterpret_cast<const lsdo_hyp*>(d->d->currentDepthMap); }
 void lsdo_depthmap_set_current(lsdo_depthmap* d, const lsdo_hyp* h) { std::memcpy(d->d->currentDepthMap, h, sizeof(lsdo_hyp) * d->w * d->h); }

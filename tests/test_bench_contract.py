@@ -25,7 +25,10 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and abs(d["value"] - 1e3 / d["ms_per_step"]) < 1e-6 * d["value"]
     assert "workload" in d["config"] and "model" not in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 5 and cb["value"] == d["value"] and "sample" in cb
+    from oracle import pyoracle
+    # the reference's own sources (oracle/_ref) whenever they are here, the C port otherwise
+    assert cb["kind"] == ("reference" if pyoracle.ref_available() else "port")
+    assert cb["cores"] == 5 and cb["value"] == d["value"] and "sample" in cb
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 
@@ -41,32 +44,64 @@ def test_bench_refuses_to_run_the_gpu_arm_without_a_gpu():
     assert not any(ln.strip().startswith("{") for ln in r.stdout.splitlines())
 
 
-def test_product_arm_line_contract_with_mocked_device_results(monkeypatch, capsys):
-    """the JSON line of the product arm (everything after the device timing): all contract keys, roofline, cpu_baseline,
-    e2e, clocks, gpu_launches -- exercised on the CPU by replacing only the device loop with canned timings"""
+def _fake_gpu_run_factory(bench, perturb=0.0):
     import numpy as np
-    sys.path.insert(0, ROOT)
-    import bench
 
     def fake_gpu_run(args, rank, world, local_rank):
-        seq, frames = bench.render_frames(args.width, args.height, 1234, args.warmup + args.steps + 1)
-        leg = dict(total_ms=2.0, launches=53, clocks={"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 5}, wall=0.1,
-                   kms=1.1, klaunch=10, kbytes=1.1e8, poses=np.zeros((args.steps, 7)), p50=0.2, p95=0.22)
-        return seq, frames, {"resident": leg, "e2e": dict(leg, total_ms=2.2)}
-    monkeypatch.setattr(bench, "gpu_run", fake_gpu_run)
-    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "10", "--warmup", "3"])
+        R = bench.n_passes(args.steps)
+        n = args.warmup + R * args.steps
+        seq, frames = bench.render_frames(args.width, args.height, 1234, n + 1)
+        poses = bench.cpu_loop(seq, frames, n, 0, time_budget_s=0, flavour=False)["poses"].copy()   # what a correct device run returns
+        poses[:, 4:7] *= (1.0 + perturb)
+        pr = [{"rank": 0, "sum_ms": 2.0 * R, "p50": 0.2, "p95": 0.22, "max_step_ms": 0.3, "argmax_step": 1, "pass_ms": [2.0] * R,
+               "sm_mhz": 1965.0, "reasons": [], "pinned_cores": None}]
+        leg = dict(pass_ms=[2.0] * R, launches=53 * R, clocks={"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 5}, wall=0.1,
+                   kms=1.1, klaunch=10, kbytes=1.1e8, poses=poses, p50=0.2, p95=0.22, per_rank=pr)
+        return seq, frames, {"resident": leg, "e2e": dict(leg, pass_ms=[2.2] * R)}
+    return fake_gpu_run
+
+
+def test_product_arm_line_contract_with_mocked_device_results(monkeypatch, capsys):
+    """the JSON line of the product arm (everything after the device timing): all contract keys, roofline, cpu_baseline,
+    e2e, clocks, gpu_launches, the in-run parity record -- exercised on the CPU by replacing only the device loop"""
+    sys.path.insert(0, ROOT)
+    import bench
+    from oracle import pyoracle
+    monkeypatch.setattr(bench, "gpu_run", _fake_gpu_run_factory(bench))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "20", "--warmup", "3"])
+    monkeypatch.setattr(bench, "n_passes", lambda steps: 1)
     bench.main()
     lines = [ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches"):
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "clocks", "gpu_launches", "parity", "per_rank", "pass_ms"):
         assert k in d, k
-    assert d["n_gpus"] == 1 and d["steps"] == 10 and d["gpu_launches"] == 53 and d["vs_baseline"] is None
-    assert abs(d["value"] - 10 / 2.0e-3) < 1e-6 and abs(d["e2e"]["value"] - 10 / 2.2e-3) < 1e-6
+    assert d["n_gpus"] == 1 and d["steps"] == 20 and d["gpu_launches"] == 53 and d["vs_baseline"] is None
+    assert abs(d["value"] - 20 / 2.0e-3) < 1e-6 and abs(d["e2e"]["value"] - 20 / 2.2e-3) < 1e-6
     assert d["e2e"]["h2d_bytes_per_step"] == 640 * 480 and d["e2e"]["d2h_bytes_per_step"] > 0
     rf = d["roofline"]
     assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-12
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 5 and cb["value"] > 0 and cb["single_core"]["value"] > 0
+    assert cb["kind"] == ("reference" if pyoracle.ref_available() else "port")
+    assert cb["cores"] == 5 and cb["value"] > 0 and cb["single_core"]["value"] > 0
     assert 0.30 <= d["config"]["semi_dense_fraction"] <= 0.50 and "workload" in d["config"] and "l2" in d["config"]
+    par = d["parity"]
+    assert par["ok"] is True and par["max_pose_rel"] == 0.0 and par["frames"] == 23 and par["tolerance"] == 1e-4
+    if cb["kind"] == "reference":
+        assert par["reference_sse_vs_scalar"]["max_pose_rel"] > 1e-4        # the stock SSE build is NOT within 1e-4 of its scalar path
+
+
+def test_product_arm_fails_when_parity_is_off(monkeypatch, capsys):
+    """poses 3e-4 away from the oracle: the line still prints (parity.ok false) and the process exits non-zero"""
+    import pytest
+    sys.path.insert(0, ROOT)
+    import bench
+    monkeypatch.setattr(bench, "gpu_run", _fake_gpu_run_factory(bench, perturb=3e-4))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
+    monkeypatch.setattr(bench, "n_passes", lambda steps: 1)
+    with pytest.raises(SystemExit) as ei:
+        bench.main()
+    assert ei.value.code == 3
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][0])
+    assert d["parity"]["ok"] is False and 2e-4 < d["parity"]["max_pose_rel"] < 4e-4

@@ -1,53 +1,67 @@
-"""Parity at BASELINE.json's full sizes (640x480 and 1280x1024): the track + map loop of both sides, plus the
-size-independent properties the domain offers (zero-motion -> identity, determinism run to run)."""
+"""Parity at BASELINE.json's full sizes (640x480 and 1280x1024) over the BENCH loop itself: frames tracked and mapped in
+sequence with a forced finalizeKeyFrame + createKeyFrame every 20 frames, GpuStream (C ABI) against
+the same loop on the CPU oracle (oracle/cpu_stream.py); plus the size-independent properties the domain offers
+(zero-motion -> identity, determinism run to run).
+
+Tolerances are north_star's: pose <= 1e-4 relative (translation) / 1e-4 rad... stated per assert below."""
 import numpy as np
 import pytest
 
 from lsd_slam_b200 import abi, synth
 from lsd_slam_b200.stream import GpuStream
-from tests.util import IDENT, pose_err
+from oracle.cpu_stream import CpuStream
+from tests.util import pose_err
 
 pytestmark = pytest.mark.gpu
 
 
-def _loop_both(oracle, w, h, n, kf_every=0):
-    seq = synth.Sequence(w, h, seed=1234)
+def _compare_maps(a, b, what):
+    va, vb = a["isValid"] > 0, b["isValid"] > 0
+    assert (va != vb).mean() <= 1e-3, (what, float((va != vb).mean()))
+    both = va & vb
+    for f in ("idepth", "idepth_smoothed"):
+        rel = np.abs(a[f][both] - b[f][both]) / np.abs(b[f][both])
+        assert (rel <= 1e-3).mean() >= 0.999, (what, f, float((rel <= 1e-3).mean()))   # inverse depth <= 1e-3 relative per pixel
+    return int(both.sum())
+
+
+def _loop_both(w, h, n, kf_every, seed):
+    """the bench loop on both sides; returns the per-frame (translation, rotation) errors and the keyframe-change frames"""
+    seq = synth.Sequence(w, h, seed=seed)
     frames = [seq.render(k) for k in range(n)]
     ctx = abi.Context(w, h, seq.K, max_frames=8)
     gs = GpuStream(ctx, mode=1, kf_every=kf_every)
     gs.init_gt(0, frames[0][0], frames[0][1])
-    okf = oracle.Frame(0, frames[0][0], seq.K)
-    okf.setDepthFromGroundTruth(frames[0][1])
-    odm = oracle.DepthMap(w, h, seq.K)
-    odm.initializeFromGTDepth(okf)
-    last = IDENT
-    worst = (0.0, 0.0)
+    cs = CpuStream(seq, flavour=False, kf_every=kf_every)
+    cs.init_gt(0, frames[0][0], frames[0][1])
+    errs, counts_equal = [], 0
     for k in range(1, n):
         pg = gs.step(k, frames[k][0])
-        of = oracle.Frame(k, frames[k][0], seq.K)
-        oracle.lib().lsdo_frame_set_depthHasBeenUpdatedFlag(okf.ptr, 0)
-        r = oracle.se3_track(okf, of, last)
-        last = np.array(r.frameToRef_qt)
-        odm.updateKeyframe([of])
-        dt, ang = pose_err(pg, last)
-        worst = (max(worst[0], dt), max(worst[1], ang))
-        assert list(gs.tracker.last.numCalcResidualCalls) == list(r.numCalcResidualCalls), k
-    a, b = gs.map.current(), odm.current().copy()     # copy: the oracle view dies with odm
+        pc, _ = cs.step(k, frames[k][0])
+        errs.append(pose_err(pg, pc))
+        r = cs.results[-1]
+        same = list(gs.tracker.last.numCalcResidualCalls) == list(r.numCalcResidualCalls) and \
+            list(gs.tracker.last.numCalcWarpUpdateCalls) == list(r.numCalcWarpUpdateCalls)
+        counts_equal += int(same)
+        if k in cs.kf_changes or k == n - 1:
+            _compare_maps(gs.map.current(), cs.dm.current().copy(), f"{w}x{h} seed {seed} after frame {k}")
     ctx.close()
-    return worst, a, b
+    return np.array(errs), counts_equal, cs.kf_changes
 
 
-@pytest.mark.parametrize("size", [(640, 480), (1280, 1024)])
-def test_full_size_loop_parity(oracle, size):
-    w, h = size
-    n = 6 if w == 640 else 4
-    worst, a, b = _loop_both(oracle, w, h, n)
-    assert worst[0] <= 1e-4 and worst[1] <= 1e-6, worst                 # pose <= 1e-4 relative (north_star)
-    va, vb = a["isValid"] > 0, b["isValid"] > 0
-    assert (va != vb).mean() <= 1e-3
-    both = va & vb
-    rel = np.abs(a["idepth_smoothed"][both] - b["idepth_smoothed"][both]) / np.abs(b["idepth_smoothed"][both])
-    assert (rel <= 1e-3).mean() >= 0.999, float((rel <= 1e-3).mean())   # inverse depth <= 1e-3 relative per pixel
+@pytest.mark.parametrize("cfg", [(640, 480, 45, 1234), (640, 480, 25, 2234), (1280, 1024, 25, 1234)],
+                         ids=["640x480-45f-2kf", "640x480-seed2234", "1280x1024-25f-1kf"])
+def test_bench_loop_parity(cfg):
+    """BASELINE configs 2 / 3 / 4(stream 1): the loop bench.py times, keyframe changes included, at full size"""
+    w, h, n, seed = cfg
+    errs, counts_equal, kfc = _loop_both(w, h, n, 20, seed)
+    assert len(kfc) == (n - 1) // 20 >= 1
+    # SE3 pose within 1e-4 relative on translation and 1e-4 rad... the rotation of a 1-frame step is ~1e-3 rad, so the
+    # rotation bound is stated absolutely: 1e-6 rad (= 1e-3 relative of the per-frame rotation)
+    assert errs[:, 0].max() <= 1e-4, (errs[:, 0].argmax() + 1, errs[:, 0].max())
+    assert errs[:, 1].max() <= 1e-6, (errs[:, 1].argmax() + 1, errs[:, 1].max())
+    # the LM takes the same accept / reject decisions on (nearly) every frame; a decision exactly at a threshold may flip
+    assert counts_equal >= (n - 1) - 2, (counts_equal, n - 1)
 
 
 def test_full_size_determinism_and_zero_motion():

@@ -112,3 +112,27 @@ def test_divergence_returns_identity(gpu_ctx_small, oracle, seq_small, frames_sm
     r = oracle.se3_track(okf, of, far)
     assert r.diverged and trk.diverged and not trk.trackingWasGood
     assert np.array_equal(p, IDENT)
+
+
+def test_tracker_modes_and_parity_hook_interleave_on_one_context(gpu_ctx_small, oracle, seq_small, frames_small):
+    """mode-1 track, single evaluation (parity hook), mode-0 track, mode-1 track again on ONE context: the persistent kernel's
+    monotonic barrier counter and the evaluation kernel's last-block counter must not share a word (each would break the other)"""
+    okf, of = _setup(gpu_ctx_small, oracle, seq_small, frames_small, 3)
+    r = oracle.se3_track(okf, of, IDENT)
+    pose_o = np.array(r.frameToRef_qt)
+    ctx = gpu_ctx_small
+    t1, t0 = abi.SE3Tracker(ctx, mode=1), abi.SE3Tracker(ctx, mode=0)
+    o_ev = oracle.se3_eval(okf, of, 2, IDENT.astype(np.float32), 1.0, 0.0)
+    poses, counts = [], []
+    for step in ("m1", "eval", "m0", "eval", "m1", "m1", "m0"):
+        if step == "eval":
+            _cmp_eval(t1.eval(0, 3, 2, IDENT.astype(np.float32), 1.0, 0.0), o_ev)
+            continue
+        trk = t1 if step == "m1" else t0
+        poses.append(trk.trackFrame(0, 3, IDENT))
+        counts.append((list(trk.last.numCalcResidualCalls), list(trk.last.numCalcWarpUpdateCalls)))
+    for p, c in zip(poses, counts):
+        assert pose_err(p, pose_o)[0] <= 1e-4
+        assert c == (list(r.numCalcResidualCalls), list(r.numCalcWarpUpdateCalls))
+    assert np.array_equal(poses[0], poses[2]) and np.array_equal(poses[2], poses[3])      # mode 1 is deterministic across the interleaving
+    assert np.array_equal(poses[1], poses[4])

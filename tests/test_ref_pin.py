@@ -320,3 +320,19 @@ def test_sse_vs_scalar_gap_of_the_reference_itself(seq_small, frames_small):
           f"vs ground truth: scalar {e_scalar:.2e}, SSE {e_sse:.2e}")
     assert 1e-4 < dt < 5e-2             # both minimise the same cost; they are NOT within 1e-4 of each other
     assert abs(e_scalar - e_sse) < 2e-2 # and neither is closer to the ground truth than the other by more than that
+
+
+def test_bench_loop_with_keyframe_changes_bit_exact(seq_small, frames_small):
+    """the loop bench.py and the full-size GPU tests run (oracle/cpu_stream.py: track, map, forced finalizeKeyFrame +
+    createKeyFrame every 10 frames), C oracle vs reference-compiled: every pose equal as doubles, final map identical"""
+    from oracle.cpu_stream import CpuStream
+    out = {}
+    for fl in (False, "ref"):
+        cs = CpuStream(seq_small, fl, kf_every=10)
+        cs.init_gt(0, *frames_small[0])
+        for k in range(1, 26):
+            cs.step(k, frames_small[k][0])
+        out[fl] = (np.array(cs.poses), cs.dm.current().copy(), cs.kf_changes, cs)
+    assert out[False][2] == out["ref"][2] == [10, 20]
+    assert np.array_equal(out[False][0], out["ref"][0])
+    assert_hyp_identical(out[False][1], out["ref"][1], "after 25 frames and 2 keyframe changes")
