@@ -147,11 +147,18 @@ struct lsdgpu_ctx {
     int rawW = 0, rawH = 0;
     bool undistorterSet = false;
     uint32_t* dPacked = nullptr;         // keyframeMsg.pointcloud staging: w*h InputPointDense records (device)
-    int trackCluster = 1, trackGrid = 148;   // launch shape of the persistent tracker (set by trackPersistentSetup)
+    int trackGrid = 148;                 // launch shape of the persistent tracker (set by trackPersistentSetup): one CTA per SM
+    int trackG[LSD_LEVELS] = { 1, 1, 1, 1, 1 };          // CTAs taking part in the evaluations of each level
+    unsigned int* trkSync = nullptr;     // per-level barrier counters + level records of the persistent tracker (TP_SYNC_WORDS)
+    unsigned int trkBase[LSD_LEVELS] = { 0, 0, 0, 0, 0 };  // arrivals already counted on each level's counter (never reset)
+    unsigned int tmaTimeoutsSeen = 0;
+    // environment switches, read once at lsdgpu_create
+    int optTrackTma = 1, optSingleSync = 0;
+    bool optTrackDebug = false;
+    int optTrackWpc[LSD_LEVELS] = { 16, 16, 16, 16, 16 };
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
     unsigned int trackSeq = 0;           // sequence number of the last tracking launch (TrackState::doneSeq)
-    unsigned int barrierBase = 0;        // arrivals already counted on evCounter[0] by earlier launches
     uint8_t* stageRing = nullptr;        // device prefetch ring of raw u8 frames (separate allocation)
     int stageEntries = 0;
     uint8_t* hStage[2] = { nullptr, nullptr };   // double-buffered pinned staging for the u8 frame upload

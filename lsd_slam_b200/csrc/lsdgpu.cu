@@ -91,7 +91,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     const int maxBlocks = divUp((int)n0, EVAL_THREADS) + 8;
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
                      + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256) + 2 * alignUp(n0 * 4, 256) + alignUp(n0, 256)) * (size_t)max_frames + alignUp(n0 * 12, 256) + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024 + alignUp(S3_MAX_BATCH * sizeof(Sim3Item), 256) + alignUp(S3_MAX_BATCH * sizeof(Sim3Out), 256)
-                     + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192;
+                     + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192 + TP_SYNC_WORDS * 4;
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
     LSD_CHECK(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arenaBytes, ctx->stream));
@@ -140,6 +140,7 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     ctx->propVal = (float4*)take(n0 * 16);
     ctx->evPartials = (float*)take((size_t)maxBlocks * EV_NCH * 4 + 65536);   // also holds the 2 x 160 x 192 B exchange rows of mode 1
     ctx->evCounter = (unsigned int*)take(256);
+    ctx->trkSync = (unsigned int*)take(TP_SYNC_WORDS * 4);
     ctx->dEvOut = (float*)take(EV_NCH * 4);
     ctx->dStageU8[0] = (uint8_t*)take(n0);
     ctx->dStageU8[1] = (uint8_t*)take(n0);
@@ -1081,7 +1082,7 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
     // constants of prepareForStereoWith are then computed by the tracking kernel's last thread.  Measured on B200 (A/B on
     // one box, 640x480): 202.6 us per step against 202.0 us for the default (poll the tracking result, constants on the
     // host) -- the 2.2 us of one-thread double-precision work at the kernel's tail cost what the round trip saves.
-    const bool singleSync = getenv("LSDGPU_SINGLE_SYNC") && atoi(getenv("LSDGPU_SINGLE_SYNC")) == 1;
+    const bool singleSync = ctx->optSingleSync == 1;
     if (singleSync && mode == 1 && !keyframe_change && ctx->activeKf == kf_id && fr) {
         // Whole frame enqueued back to back: tracking kernel, device-side prepareForStereoWith, observe, fill holes,
         // regularise, setDepth -- ONE host synchronisation at the end (the mapping kernels read the pose from the

@@ -7,7 +7,7 @@
 // Callers in the reference evaluate MANY keyframe candidates against one frame, one call after the other
 // (Relocalizer.cpp:172,188; TrackableKeyFrameSearch.cpp:126,135; SlamSystem.cpp:1298,1304).  Here a whole candidate list
 // is one launch: one CTA per candidate runs the complete level-4 LM loop on its own (the problems are independent, so
-// there is no grid barrier and no exchange at all) with the same evalPoint() / lmAdvance() as the main tracker.
+// there is no grid barrier and no exchange at all) with the same evalPoint() / lmStep() as the main tracker.
 #pragma once
 #include "internal.cuh"
 #include "track.cuh"
@@ -64,7 +64,8 @@ __global__ void __launch_bounds__(128) k_perma_overlap(const PermaItem* __restri
 __global__ void __launch_bounds__(PERMA_THREADS) k_perma_track(const __grid_constant__ TrackParams p, const PermaItem* __restrict__ items,
                                                                PermaResult* __restrict__ results)
 {
-    __shared__ LMShared sh;
+    __shared__ alignas(LMShared) unsigned char shStorage[sizeof(LMShared)];   // raw storage: Proposal holds a type with a constructor
+    LMShared& sh = *reinterpret_cast<LMShared*>(shStorage);
     __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
     LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
     __shared__ float sm[PERMA_THREADS / 32][EV_NCH];
@@ -104,8 +105,7 @@ __global__ void __launch_bounds__(PERMA_THREADS) k_perma_track(const __grid_cons
             sh.sums[threadIdx.x] = s;
         }
         __syncthreads();
-        if (threadIdx.x == 0) lmAdvance(p, lm, sh);
-        __syncthreads();
+        lmStep(p, lm, sh, 0u);           // all threads: decision on thread 0, the two speculative solves on threads 32 and 64
         if (sh.action != ACT_CONTINUE) break;
     }
     if (threadIdx.x == 0) {

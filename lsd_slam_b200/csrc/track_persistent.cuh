@@ -21,11 +21,11 @@
 namespace cg = cooperative_groups;
 
 #define TP_THREADS 512
+#define TP_WARPS (TP_THREADS / 32)
+#define TP_MAXGRID 160               // combine code is unrolled for <= 160 CTAs (B200: 148 SMs)
 #define TP_MAXGRID_DBG 160
-#define TP_WIN_SMEM ((TP_THREADS / 32) * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
-#define EX_ROW 48                    // floats per exchange row (192 B): EV_NCH data + tag + pad
-#define TP_LOCAL_MAX_PIXELS 1024      // levels up to this many pixels are evaluated redundantly per CTA
-#define TP_CLUSTER_MAX_PIXELS 8192    // ... and up to this many redundantly per thread-block cluster (DSMEM exchange)
+#define TP_WIN_SMEM (TP_WARPS * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
+#define TP_SYNC_WORDS 1024           // ctx->trkSync: barrier counter of level l at word 32*l, level records from word 256 on
 
 struct TrackLevelParams {
     const float* kfIdepth;
@@ -34,6 +34,19 @@ struct TrackLevelParams {
     const float4* frameGrad;
     int w, h;
     float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
+    // Work split of the persistent tracker.  Only INTERIOR pixels can be points (TrackingReference.cpp:128-129 scans
+    // 1..w-2 x 1..h-2); they are numbered row by row, j = (x-1) + (y-1)*iw, and cut into chunks of 32 consecutive j.
+    // At 640x480 level 1 has 318*238 = 75 684 interior pixels = 2 366 chunks <= 148 CTAs x 16 warps: one chunk per warp.
+    int iw, nInt, nChunks;
+    int G;                           // CTAs 0..G-1 evaluate this level (chunk c -> CTA c % G, warp slot c / G); non-increasing in l
+};
+
+// what CTA 0 leaves in global memory when a level starts, for the CTAs that join the computation at that level
+struct alignas(128) LevelRecord {
+    float q[4], t[3], a, b;          // refToFrame and the affine estimate at the start of the level
+    int action;                      // ACT_CONTINUE, or a stop code if tracking ended before this level
+    unsigned int epochAll;           // evaluations done so far in this launch (parity of the exchange buffer)
+    unsigned int tag;                // == launchSeq once the record is complete (written last, release)
 };
 
 struct alignas(64) TrackParams {
@@ -48,13 +61,11 @@ struct alignas(64) TrackParams {
     EvalConsts C;
     int useAffine;
     float* partials;                 // [2][EV_NCH][gridDim]
-    unsigned int* barrier;           // [0] arrival counter (monotonic), [32] released-epoch flag
-    int barrierMode;
-    unsigned int barrierBase;        // arrivals counted by earlier launches (the counter is never reset)
+    unsigned int* sync;              // per-level arrival counters (monotonic) + level records, see TP_SYNC_WORDS
+    unsigned int barrierBase[LSD_LEVELS];   // arrivals counted on each level's counter by earlier launches (never reset)
     int debug;                       // 1: also write the per-CTA cycle table
     unsigned int launchSeq;          // value the kernel stores in TrackState::doneSeq when the result block is complete
     int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
-    int clusterLocalMaxPixels;       // levels up to this size are evaluated per cluster (0: never; needs a cluster launch)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
     int doPrepare;                   // 1: the last thread also turns the result into the observe parameters of the same frame
     PrepareConsts prep;              //    (Frame::prepareForStereoWith + head of DepthMap::updateKeyframe), no host round trip
@@ -70,6 +81,8 @@ struct TrackState {
     int diverged;
     int numCalcResidualCalls[LSD_LEVELS];
     int numCalcWarpUpdateCalls[LSD_LEVELS];
+    int evalsAtLevel[LSD_LEVELS];    // evaluations per level (advances the per-level barrier bases on the host)
+    float pointsAtLevel[LSD_LEVELS]; // numData[level]: valid points of the keyframe on each tracked level (CH_REFNUM)
     int totalEvals;
     volatile unsigned int doneSeq;   // written last (after a system-wide fence): the host polls it instead of a stream sync
     long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
@@ -108,54 +121,59 @@ __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int
                  ::"r"(smemU32(dst)), "l"(map), "r"(x), "r"(y), "r"(smemU32(bar)) : "memory");
 }
 
-// Grid-wide barrier.  Arrivals are counted on `counter[0]` (monotonic: epoch e completes at e * gridDim
-// arrivals); the LAST arriver publishes the epoch number in `counter[32]` (a different 128-byte line), which is
-// what everybody else polls -- the pollers never touch the line the atomics serialise on.  Thread 0 carries the
-// release / acquire for its CTA (the fences are cumulative over the preceding / following __syncthreads).
-__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int base, unsigned int epoch, int mode)
+__device__ __forceinline__ unsigned int ldAcquire(const unsigned int* p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stRelease(unsigned int* p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Barrier over the CTAs that evaluate one level.  Arrivals are counted on the level's own counter (monotonic: epoch e
+// of this launch completes at base + e * G arrivals, the counter is never reset): release-add, then acquire-poll of the
+// counter itself.  Thread 0 carries the release / acquire for its CTA (cumulative over the __syncthreads on both sides).
+// Measured alternatives (round 1, B200): a separate release flag written by the last arriver (+1 800 cycles), fire-and-
+// forget red.release + poll (no gain), tagged-row polling without a counter (148 x 148 polling loads saturate L2, +35 %).
+__device__ __forceinline__ void levelBarrier(unsigned int* counter, unsigned int target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int target = base + epoch * gridDim.x;     // wraps consistently (unsigned arithmetic)
-        if (mode == 0) {
-            // arrival counter + separate release flag (last arriver publishes the epoch)
-            __threadfence();
-            const unsigned int old = atomicAdd(counter, 1u);
-            volatile unsigned int* flag = counter + 32;
-            if (old == target - 1u) { __threadfence(); *flag = target; }
-            else { while ((int)(*flag - target) < 0) { } }
-            __threadfence();
-        } else if (mode == 1) {
-            // release-add, then acquire-poll the counter itself (one L2 hop less than mode 0)
-            unsigned int v;
-            asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
-            if (v != target - 1u) {
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-                } while ((int)(v - target) < 0);
-            } else {
-                asm volatile("fence.acq_rel.gpu;" ::: "memory");
-            }
+        unsigned int v;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
+        if (v != target - 1u) {
+            do { v = ldAcquire(counter); } while ((int)(v - target) < 0);
         } else {
-            // fire-and-forget release reduction + acquire poll
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-            unsigned int v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
-            } while ((int)(v - target) < 0);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
     }
     __syncthreads();
 }
+
+enum { ACT_CONTINUE = 0, ACT_LEVEL_DONE = 1, ACT_DIVERGED = 2 };
+enum { CHOICE_NONE = 0, CHOICE_ACCEPT = 1, CHOICE_REJECT = 2 };
+
+// next pose proposed by one of the two speculative lanes (see lmStep)
+struct Proposal {
+    float inc[6];
+    lsd::SE3<float> cand;
+    float R[9];
+    float lambda;
+};
 
 struct LMShared {
     float sums[EV_NCH];
     EvalPose pose;                   // pose being evaluated
     int action;
     int lvl;                         // level of the next evaluation
+    unsigned int epochAll;
+    // decision of thread 0 about the evaluation just summed (phase 1 of lmStep; applied in phase 2)
+    int dDiverged, dAccept, dInit, dConverged, dLeave, dChoice;
+    float dError, dA, dB;
+    Proposal propA, propR;
 };
-
-enum { ACT_CONTINUE = 0, ACT_LEVEL_DONE = 1, ACT_DIVERGED = 2, ACT_RETRY = 3, ACT_ACCEPTED = 4 };
 
 __device__ __forceinline__ void setEvalPose(EvalPose& P, const lsd::SE3<float>& T, float a, float b)
 {
@@ -210,12 +228,6 @@ __device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* sm
     if ((lane & 3) == 0) smRow[32 + warpReduceChannel<8>(lane)] = a8[0];
 }
 
-#define TP_WARPS (TP_THREADS / 32)
-#define TP_MAXGRID 160               // combine code is unrolled for <= 160 CTAs (B200: 148 SMs)
-
-// One evaluation.  Levels with few pixels (local == true) are evaluated REDUNDANTLY by every CTA over the whole
-// level -- no grid barrier, no exchange; big levels are split over the grid with one barrier.  On return
-// sh.sums holds the EV_NCH totals, bit-identical in every CTA.
 struct WarpWindow {
     const float4* win;               // this warp's TRK_WIN_H x TRK_WIN_W window in shared memory
     uint64_t* bar;
@@ -224,60 +236,52 @@ struct WarpWindow {
     int ox, oy;                      // window origin in level pixels
     bool valid;
     unsigned int hits;               // low 16 bits: taps served from the window, high 16: taps through L1/L2
-    // the thread's first pixel of the current level, reconstructed once (see gridEvaluate)
-    int pcLvl, pcMode;
+    // the thread's first pixel of the current level, reconstructed once (see levelEvaluate)
+    int pcLvl;
     bool pcIsPoint;
     float pcx, pcy, pcz, pcVar, pcColor;
 };
 
-enum { EVAL_GRID = 0, EVAL_CTA = 1, EVAL_CLUSTER = 2 };
-
-// evalMode: EVAL_GRID    the level is split over the whole grid (one grid barrier + L2 exchange),
-//           EVAL_CLUSTER every thread-block cluster evaluates the whole level redundantly (small levels: the CTAs of a
-//                        cluster exchange their 40 sums through distributed shared memory behind one hardware
-//                        cluster barrier, ~10x cheaper than the grid barrier and no L2 round trip),
-//           EVAL_CTA     every CTA evaluates the whole level redundantly (tiny levels, no exchange at all).
-__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int evalMode, LMShared& sh, float (*sm)[EV_NCH],
-                                             float (*xrow)[EV_NCH], unsigned int& xphase,
-                                             unsigned int& epoch, long long* cyc, WarpWindow& W)
+// One evaluation of level `lvl` by the CTAs 0..G-1 of that level: points, CTA reduction, one row per CTA through L2 behind
+// ONE barrier over the G CTAs, then every CTA sums the G rows in rank order.  On return sh.sums holds the EV_NCH totals,
+// bit-identical in every CTA.
+__device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCH],
+                                              unsigned int& epochAll, unsigned int& epochLvl, long long* cyc, WarpWindow& W)
 {
-    const bool local = evalMode != EVAL_GRID;
     long long t0 = clock64();
     const TrackLevelParams& L = p.lvl[lvl];
     const EvalPose P = sh.pose;
     PointAcc acc;
 #pragma unroll
     for (int c = 0; c < EV_NCH; c++) acc.v[c] = 0.f;
-    const int w = L.w, h = L.h, n = w * h;
+    const int w = L.w, h = L.h, iw = L.iw, nInt = L.nInt, G = L.G;
     const float4* fg = L.frameGrad;
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
-    // 32-pixel chunks are dealt round-robin to the CTAs (chunk c -> CTA c % G, warp (c / G) % TP_WARPS): the
-    // semi-dense density varies over the image, a contiguous split would leave CTAs unevenly loaded
-    cg::cluster_group cluster = cg::this_cluster();
-    const int crank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
-    int first, stride;
-    if (evalMode == EVAL_GRID) { first = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32 + (threadIdx.x & 31); stride = gridDim.x * TP_THREADS; }
-    else if (evalMode == EVAL_CLUSTER) { first = ((threadIdx.x >> 5) * csize + crank) * 32 + (threadIdx.x & 31); stride = csize * TP_THREADS; }
-    else { first = threadIdx.x; stride = TP_THREADS; }
-    // the loop bound is evaluated on the chunk base so that whole warps stay in the loop (the window set-up below
-    // uses full-warp ballots / shuffles); w*h need not be a multiple of 32 (e.g. 40x30 on level 4)
-    const int laneId = threadIdx.x & 31;
-    for (int base = first - laneId; base < n; base += stride) {
-        const int i = base + laneId;
-        const int x = i % w, y = i / w;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // chunks of this CTA: c = blockIdx.x + G * k, k = 0 .. nMine-1; warp `warp` takes k = warp, warp + 16, ...
+    const int nMine = ((int)blockIdx.x < L.nChunks) ? (L.nChunks - (int)blockIdx.x + G - 1) / G : 0;
+    const int activeWarps = nMine < TP_WARPS ? nMine : TP_WARPS;
+    for (int k = warp; k < nMine; k += TP_WARPS) {
+        const int j = (((int)blockIdx.x + G * k) << 5) + lane;        // interior pixel number
+        const bool firstChunk = (k == warp);
         bool isPoint = false;
         float px = 0.f, py = 0.f, pz = 0.f, var = 0.f, color = 0.f;
-        const bool firstChunk = (base == first - laneId);
-        if (firstChunk && W.pcLvl == lvl && W.pcMode == evalMode) {
+        int i = 0;
+        if (j < nInt) {
+            const int yy = j / iw;
+            i = (j - yy * iw + 1) + (yy + 1) * w;                      // x = 1 + j % iw, y = 1 + j / iw
+        }
+        if (firstChunk && W.pcLvl == lvl) {
             // the thread's first pixel of a level never changes between the evaluations of that level: keep the
             // reconstructed point in registers instead of re-reading the keyframe planes (an L2 round trip at the head
             // of every evaluation's dependency chain)
             isPoint = W.pcIsPoint; px = W.pcx; py = W.pcy; pz = W.pcz; var = W.pcVar; color = W.pcColor;
         } else {
-            if (i < n && x >= 1 && x < w - 1 && y >= 1 && y < h - 1) {
+            if (j < nInt) {
                 const float idepth = __ldg(L.kfIdepth + i);
                 var = __ldg(L.kfVar + i);
-                if (!(var <= 0 || idepth == 0)) {
+                if (!(var <= 0 || idepth == 0)) {                      // TrackingReference.cpp:133
+                    const int yy = j / iw, x = j - yy * iw + 1, y = yy + 1;
                     const float sc = 1.0f / idepth;
                     px = sc * (L.fxi * x + L.cxi); py = sc * (L.fyi * y + L.cyi); pz = sc * 1;
                     color = __ldg(L.kfColor + i);
@@ -285,15 +289,14 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
                 }
             }
             if (firstChunk) {
-                W.pcLvl = lvl; W.pcMode = evalMode; W.pcIsPoint = isPoint;
+                W.pcLvl = lvl; W.pcIsPoint = isPoint;
                 W.pcx = px; W.pcy = py; W.pcz = pz; W.pcVar = var; W.pcColor = color;
             }
         }
         // First chunk of this warp on a new level: stage the part of the frame's gradient level that the chunk
         // warps into (centred on the chunk under the level's initial pose) in shared memory with ONE TMA box copy.
         // All later evaluations of the level tap the window; taps that leave it fall back to L1/L2.
-        if (p.useTma && !local && firstChunk && W.lvl != lvl) {          // warp-uniform condition
-            const int lane = threadIdx.x & 31;
+        if (p.useTma && firstChunk && W.lvl != lvl) {                  // warp-uniform condition
             float u = 0.f, v = 0.f;
             bool ok = false;
             if (isPoint) {
@@ -320,11 +323,11 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
                     tmaLoad2D((void*)W.win, &p.gradMap[lvl], 4 * W.ox, W.oy, W.bar);
                 }
                 if (mbarWait(W.bar, W.parity)) W.parity ^= 1u;
-                else { W.valid = false; W.lvl = -2; if (lane == 0) atomicAdd(p.barrier + 40, 1u); }   // counted, reported by the host
+                else { W.valid = false; W.lvl = -2; if (lane == 0) atomicAdd(p.sync + TP_SYNC_WORDS - 4, 1u); }   // counted, reported by the host
             }
         }
         if (isPoint) {
-            const bool useWin = p.useTma && !local && firstChunk && W.valid && W.lvl == lvl;
+            const bool useWin = p.useTma && firstChunk && W.valid && W.lvl == lvl;
             const float4* win = W.win;
             const int ox = W.ox, oy = W.oy;
             unsigned int* hitCtr = &W.hits;
@@ -353,47 +356,22 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
     }
     __syncthreads();
     long long t1 = clock64();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    warpReduceAcc(acc, lane, sm[warp]);
+    // warps without a chunk hold zeros: they skip the 39 shuffles, and the cross-warp sum runs over the active warps only
+    if (warp < activeWarps) warpReduceAcc(acc, lane, sm[warp]);
     __syncthreads();
     float ctaSum = 0.f;
     if (threadIdx.x < EV_NCH) {
-#pragma unroll
-        for (int wi = 0; wi < TP_WARPS; wi++) ctaSum += sm[wi][threadIdx.x];
+        for (int wi = 0; wi < activeWarps; wi++) ctaSum += sm[wi][threadIdx.x];
     }
-    if (evalMode == EVAL_CTA) {
-        if (threadIdx.x < EV_NCH) sh.sums[threadIdx.x] = ctaSum;
-        __syncthreads();
-        long long t2 = clock64();
-        cyc[0] += t1 - t0; cyc[1] += t2 - t1;
-        return;
-    }
-    if (evalMode == EVAL_CLUSTER) {
-        // DSMEM exchange: publish this CTA's row (double-buffered by phase), one cluster barrier, then every CTA sums
-        // the rows of all ranks in rank order -> identical totals in every CTA of every cluster
-        float* mine = xrow[xphase & 1u];
-        if (threadIdx.x < EV_NCH) mine[threadIdx.x] = ctaSum;
-        cluster.sync();
-        if (threadIdx.x < EV_NCH) {
-            float tot = 0.f;
-            for (int r = 0; r < csize; r++) tot += cluster.map_shared_rank(mine, r)[threadIdx.x];
-            sh.sums[threadIdx.x] = tot;
-        }
-        xphase++;
-        __syncthreads();
-        long long t2 = clock64();
-        cyc[0] += t1 - t0; cyc[1] += t2 - t1;
-        return;
-    }
-    // ---- exchange: one partial row per CTA ([parity][channel][cta], written through to L2), ONE grid barrier,
-    // then every CTA combines all rows in a fixed order (measured alternatives: per-row tag polling without a
-    // barrier is slower -- 148 x 148 polling loads saturate L2)
-    const unsigned int parity = epoch & 1u;
+    // ---- exchange: one partial row per CTA ([parity][channel][cta], written through to L2), ONE barrier over the G CTAs
+    // of the level, then every CTA combines the G rows in a fixed order
+    const unsigned int parity = epochAll & 1u;
     float* part = p.partials + (size_t)parity * EV_NCH * gridDim.x;
     if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
-    epoch++;
+    epochAll++;
+    epochLvl++;
     long long t2 = clock64();
-    gridBarrier(p.barrier, p.barrierBase, epoch, p.barrierMode);
+    levelBarrier(p.sync + 32 * lvl, p.barrierBase[lvl] + epochLvl * (unsigned int)G);
     long long t3 = clock64();
     // warp wi owns channels wi, wi+TP_WARPS, ... (<= 3 per warp); all loads are issued first, then one
     // multi-value reduction in double
@@ -407,7 +385,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, int 
 #pragma unroll
             for (int j = 0; j < TP_MAXGRID / 32; j++) {
                 const int bb = lane + 32 * j;
-                v[j] = (c < EV_NCH && bb < nb) ? __ldcg(part + (size_t)c * nb + bb) : 0.f;
+                v[j] = (c < EV_NCH && bb < G) ? __ldcg(part + (size_t)c * nb + bb) : 0.f;
             }
             double sacc = 0.0;
 #pragma unroll
@@ -514,16 +492,16 @@ __device__ __forceinline__ lsd::SE3<float> se3ExpMulFast(const float* a, const l
     return r;
 }
 
-// LM state of SE3Tracker::trackFrame; lives in shared memory, touched by thread 0 only (keeps it out of the
-// register budget of the other threads)
+// LM state of SE3Tracker::trackFrame; lives in shared memory (keeps it out of the register budget of the point loop)
 struct LMState {
     lsd::SE3<float> refToFrame, cand;
     float affine_a, affine_b, lastErr, last_residual, LM_lambda;
     float inc[6];
     float lsq[27];                   // accepted normal equations, RAW sums: 21 upper-triangle A + 6 (sum J r w)
-    int nRes[LSD_LEVELS], nUpd[LSD_LEVELS];
+    int nRes[LSD_LEVELS], nUpd[LSD_LEVELS], nEval[LSD_LEVELS];
+    float nPts[LSD_LEVELS];
     int lvl, iteration, phase, incTry, diverged;
-    long long dbg[4];                // thread-0 cycles: decision, solve, pose update, (spare)
+    long long dbg[4];                // thread-0 cycles: decision, apply, (proposal lanes: accept, reject)
 };
 enum { PH_INIT = 0, PH_TRY = 1 };
 
@@ -535,155 +513,242 @@ __device__ __forceinline__ void affineFromSums(const float* s, float& a, float& 
     b = (sy - a * sx) / sw;
 }
 
-// solve the damped system of the accepted linearisation and set the candidate pose (SE3Tracker.cpp:356-363).
-// A and b are used un-normalised: LGS6::finish divides both by num_constraints (LGSX.h:319-325), which cancels
-// in A^-1 b (the damping is multiplicative), so the division is skipped on the device.
-__device__ __forceinline__ void lmSolveAndPropose(LMState& lm, LMShared& sh)
+// Solve the damped system `lsq` (RAW sums: LGS6::finish divides A and b by num_constraints, LGSX.h:319-325, which cancels
+// in A^-1 b because the damping is multiplicative) and form exp(inc) * base with its rotation matrix (SE3Tracker.cpp:356-363).
+__device__ __forceinline__ void proposePose(const float* lsq, float lambda, const lsd::SE3<float>& base, Proposal& P)
 {
     static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
                                             {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
     float A[36], b[6], inc[6];
-    const long long ta = clock64();
 #pragma unroll
     for (int k = 0; k < 21; k++) {
-        const float v = lm.lsq[k];
+        const float v = lsq[k];
         A[ij[k][0] * 6 + ij[k][1]] = v;
         A[ij[k][1] * 6 + ij[k][0]] = v;
     }
 #pragma unroll
-    for (int i = 0; i < 6; i++) b[i] = lm.lsq[21 + i];
-    const float damp = 1 + lm.LM_lambda;
+    for (int i = 0; i < 6; i++) b[i] = lsq[21 + i];
+    const float damp = 1 + lambda;
 #pragma unroll
     for (int i = 0; i < 6; i++) A[i * 6 + i] *= damp;
     if (!ldlt6SolveFast(A, b, inc)) lsd::ldlt6Solve(A, b, inc);
+    const lsd::SE3<float> c = se3ExpMulFast(inc, base);
 #pragma unroll
-    for (int i = 0; i < 6; i++) lm.inc[i] = inc[i];
-    const long long tb = clock64();
-    lm.incTry++;
-    lm.cand = se3ExpMulFast(inc, lm.refToFrame);
-    setEvalPose(sh.pose, lm.cand, lm.affine_a, lm.affine_b);
-    lm.phase = PH_TRY;
-    const long long tc = clock64();
-    lm.dbg[1] += tb - ta; lm.dbg[2] += tc - tb;
+    for (int i = 0; i < 6; i++) P.inc[i] = inc[i];
+    P.cand = c;
+    lsd::quatToMatrix(c.q, P.R);
+    P.lambda = lambda;
 }
 
-__device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, LMShared& sh)
+// std::pow(lambdaFailFac, incTry) of SE3Tracker.cpp:445 (float, int -> double pow): repeated multiplication in double,
+// exact for the reference's factor 2 (and within an ulp of pow() for any other factor)
+__device__ __forceinline__ double ipowd(double f, int n)
 {
-    lm.lvl--;
-    if (lm.lvl < p.minLevel) { sh.action = ACT_LEVEL_DONE; return; }                // all levels done
-    lm.phase = PH_INIT;
-    setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
-    sh.lvl = lm.lvl;
+    double r = 1.0;
+    for (int i = 0; i < n; i++) r *= f;
+    return r;
 }
 
-// thread 0 after every evaluation: the decisions of SE3Tracker.cpp:324-446.  Written as one straight line with a
-// single solve/propose site (the three call sites of the reference's loop structure -- first iteration of a level,
-// next iteration after an accept, retry after a reject -- only differ in which normal equations and lambda they use).
-__device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMShared& sh)
+// level record of `lvl` (levels 0..4; record 0 is unused by trackFrame whose last level is 1)
+__device__ __forceinline__ LevelRecord* levelRecord(const TrackParams& p, int lvl)
+{
+    return reinterpret_cast<LevelRecord*>(p.sync + 256) + lvl;
+}
+__device__ __forceinline__ void publishLevel(const TrackParams& p, int lvl, const LMState& lm, int action, unsigned int epochAll)
+{
+    LevelRecord* r = levelRecord(p, lvl);
+    for (int i = 0; i < 4; i++) r->q[i] = lm.refToFrame.q[i];
+    for (int i = 0; i < 3; i++) r->t[i] = lm.refToFrame.t[i];
+    r->a = lm.affine_a; r->b = lm.affine_b;
+    r->action = action;
+    r->epochAll = epochAll;
+    stRelease(&r->tag, p.launchSeq);
+}
+
+// The step between two evaluations: the accept / reject / converge decisions of SE3Tracker.cpp:324-446 and the next pose.
+// THREE lanes work at the same time on the sums of the evaluation that just finished:
+//   thread  0  takes the decision (phase 1, read-only on the LM state),
+//   thread 32  solves for the next pose AS IF the evaluation is accepted  (new normal equations, lambda of :417-420 / :341),
+//   thread 64  solves for the next pose AS IF it is rejected               (old normal equations, lambda of :443-446),
+// then thread 0 applies the decision and adopts the proposal that matches it (phase 2).  The two 6x6 solves + exp(inc)*T
+// (~1 300 cycles each, one dependent chain) leave the critical path of the decision instead of following it.
+__device__ __forceinline__ void lmStep(const TrackParams& p, LMState& lm, LMShared& sh, unsigned int epochAll)
 {
     const float* s = sh.sums;
     const int lvl = lm.lvl;
-    const float warped = s[CH_GOOD] + s[CH_BAD];
-    sh.action = ACT_CONTINUE;
-    // MIN_GOODPERALL_PIXEL_ABSMIN is the float literal 0.01f (util/settings.h:170): the reference's threshold is a float product
-    if (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) {                          // :324-329 / :369-374
-        lm.diverged = 1;
-        sh.action = ACT_DIVERGED;
-        return;
-    }
-    const float error = s[CH_SUMRESW] / warped;                                  // calcWeightsAndResidual, :789
-    lm.nRes[lvl]++;
-    const bool init = lm.phase == PH_INIT;
-    const bool accept = init || error < lm.lastErr;                              // :381
-    bool leave;
-    if (accept) {
-        if (!init) lm.refToFrame = lm.cand;
-        if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);            // :331-335 / :385-389
-        const bool converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);   // :404
-        if (!init) lm.last_residual = error;                                     // :414
-        lm.lastErr = error;                                                      // :336 / :414
+    const int tid = threadIdx.x;
+    if (tid == 0) {                                                          // ---- phase 1: decide
+        const long long ta = clock64();
+        const float warped = s[CH_GOOD] + s[CH_BAD];
+        // MIN_GOODPERALL_PIXEL_ABSMIN is the float literal 0.01f (util/settings.h:170): the reference's threshold is a float product
+        sh.dDiverged = (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) ? 1 : 0;   // :324-329 / :369-374
+        const float error = s[CH_SUMRESW] / warped;                              // calcWeightsAndResidual, :789
+        const bool init = lm.phase == PH_INIT;
+        const bool accept = init || error < lm.lastErr;                          // :381
+        bool converged = false, leave;
+        float a = lm.affine_a, b = lm.affine_b;
+        if (accept) {
+            if (p.useAffine) affineFromSums(s, a, b);                            // :331-335 / :385-389
+            converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);    // :404
+            const int iteration = init ? 0 : (converged ? lm.iteration : lm.iteration + 1);
+            leave = converged || !(iteration < p.st.maxItsPerLvl[lvl]);          // :343, :411
+        } else {                                                                 // :424-447 reject
+            float dot = 0;
 #pragma unroll
-        for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                           // buffers now belong to this pose
-        if (init) { lm.LM_lambda = p.st.lambdaInitial[lvl]; lm.iteration = 0; }  // :341
-        else {
-            if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                           // :417-420
-            else lm.LM_lambda *= p.st.lambdaSuccessFac;
-            if (!converged) lm.iteration++;
+            for (int i = 0; i < 6; i++) dot += lm.inc[i] * lm.inc[i];
+            leave = !(dot > p.st.stepSizeMin[lvl]);                              // :432-441
         }
-        leave = converged || !(lm.iteration < p.st.maxItsPerLvl[lvl]);           // :343, :411
-        if (!leave) { lm.nUpd[lvl]++; lm.incTry = 0; }                           // calculateWarpUpdate(ls), :346
-    } else {                                                                     // :424-447 reject
-        float dot = 0;
-#pragma unroll
-        for (int i = 0; i < 6; i++) dot += lm.inc[i] * lm.inc[i];
-        leave = !(dot > p.st.stepSizeMin[lvl]);                                  // :432-441
-        if (!leave) {
-            if (lm.LM_lambda == 0) lm.LM_lambda = 0.2;                           // :443-446
-            else lm.LM_lambda *= pow((double)p.st.lambdaFailFac, lm.incTry);
+        sh.dError = error; sh.dInit = init; sh.dAccept = accept; sh.dConverged = converged; sh.dLeave = leave;
+        sh.dA = a; sh.dB = b;
+        sh.dChoice = (sh.dDiverged || leave) ? CHOICE_NONE : (accept ? CHOICE_ACCEPT : CHOICE_REJECT);
+        lm.dbg[0] += clock64() - ta;
+    } else if (tid == 32) {                                                      // ---- speculative: accepted
+        const bool init = lm.phase == PH_INIT;
+        const float lam = init ? p.st.lambdaInitial[lvl]                         // :341
+                               : ((lm.LM_lambda <= 0.2) ? 0.f : lm.LM_lambda * p.st.lambdaSuccessFac);   // :417-420
+        proposePose(s, lam, init ? lm.refToFrame : lm.cand, sh.propA);           // the accepted pose becomes the base
+    } else if (tid == 64) {                                                      // ---- speculative: rejected
+        if (lm.phase == PH_TRY) {
+            float lam = lm.LM_lambda;
+            if (lam == 0) lam = 0.2;                                             // :443-446
+            else lam *= ipowd((double)p.st.lambdaFailFac, lm.incTry);
+            proposePose(lm.lsq, lam, lm.refToFrame, sh.propR);
         }
     }
-    if (leave) lmNextLevel(p, lm, sh);
-    else lmSolveAndPropose(lm, sh);
+    __syncthreads();
+    if (tid == 0) {                                                              // ---- phase 2: apply
+        const long long ta = clock64();
+        sh.action = ACT_CONTINUE;
+        bool nextLevel = false;
+        if (sh.dDiverged) {
+            lm.diverged = 1;
+            sh.action = ACT_DIVERGED;
+        } else {
+            lm.nRes[lvl]++;
+            if (sh.dAccept) {
+                if (!sh.dInit) lm.refToFrame = lm.cand;
+                lm.affine_a = sh.dA; lm.affine_b = sh.dB;
+                if (!sh.dInit) lm.last_residual = sh.dError;                     // :414
+                lm.lastErr = sh.dError;                                          // :336 / :414
+#pragma unroll
+                for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                   // buffers now belong to this pose
+                if (sh.dInit) lm.iteration = 0;
+                else if (!sh.dConverged) lm.iteration++;
+                if (!sh.dLeave) { lm.nUpd[lvl]++; lm.incTry = 0; }               // calculateWarpUpdate(ls), :346
+            }
+            if (sh.dLeave) nextLevel = true;
+            else {
+                const Proposal& P = sh.dAccept ? sh.propA : sh.propR;
+#pragma unroll
+                for (int i = 0; i < 6; i++) lm.inc[i] = P.inc[i];
+                lm.LM_lambda = P.lambda;
+                lm.incTry++;
+                lm.cand = P.cand;
+#pragma unroll
+                for (int i = 0; i < 9; i++) sh.pose.R[i] = P.R[i];
+                sh.pose.t[0] = P.cand.t[0]; sh.pose.t[1] = P.cand.t[1]; sh.pose.t[2] = P.cand.t[2];
+                sh.pose.a = lm.affine_a; sh.pose.b = lm.affine_b;
+                lm.phase = PH_TRY;
+            }
+        }
+        if (nextLevel) {
+            lm.lvl--;
+            if (lm.lvl < p.minLevel) sh.action = ACT_LEVEL_DONE;                 // all levels done
+            else {
+                lm.phase = PH_INIT;
+                setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+                sh.lvl = lm.lvl;
+                if (blockIdx.x == 0) publishLevel(p, lm.lvl, lm, ACT_CONTINUE, epochAll);    // for the CTAs that join here
+            }
+        }
+        if (sh.action != ACT_CONTINUE && blockIdx.x == 0)                        // tracking ends: release every CTA still
+            for (int l = lvl - 1; l >= p.minLevel; l--) publishLevel(p, l, lm, sh.action, epochAll);   // waiting to join
+        lm.dbg[1] += clock64() - ta;
+    }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out, TrackState* __restrict__ outDev)
 {
-    __shared__ LMShared sh;
+    __shared__ alignas(LMShared) unsigned char shStorage[sizeof(LMShared)];   // raw storage: Proposal holds a type with a constructor
+    LMShared& sh = *reinterpret_cast<LMShared*>(shStorage);
     __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
     LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
-    __shared__ float sm[TP_THREADS / 32][EV_NCH];
+    __shared__ float sm[TP_WARPS][EV_NCH];
     static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
     extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
     __shared__ __align__(8) uint64_t winBar[TP_WARPS];
-    __shared__ float xrow[2][EV_NCH];                              // this CTA's row for the cluster-local exchange
-    unsigned int xphase = 0;
-    const int clusterSize = (int)cg::this_cluster().num_blocks();
-    unsigned int epoch = 0;
+
+    // the level at which this CTA joins the computation: the coarsest level it has chunks of (G is non-increasing in l)
+    const int topLvl = SE3TRACKING_MAX_LEVEL - 1;
+    int joinLvl = -1;
+    for (int l = topLvl; l >= p.minLevel; l--)
+        if ((int)blockIdx.x < p.lvl[l].G) { joinLvl = l; break; }
+    if (joinLvl < 0) return;                                       // small images: this CTA never has work
+
     long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
     const long long tStart = clock64();
     WarpWindow W;
     W.win = reinterpret_cast<const float4*>(winSmem) + (size_t)(threadIdx.x >> 5) * (TRK_WIN_W * TRK_WIN_H);
     W.bar = &winBar[threadIdx.x >> 5];
-    W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u; W.pcLvl = -1; W.pcMode = -1; W.pcIsPoint = false;
+    W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u; W.pcLvl = -1; W.pcIsPoint = false;
     W.pcx = W.pcy = W.pcz = W.pcVar = W.pcColor = 0.f;
     if (p.useTma && (threadIdx.x & 31) == 0) {
         mbarInit(W.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // fresh refPixelWasGood mask: all true (Frame.h:433); ordered before the level-1 evaluations by the barriers
-    if (p.maskFresh) {
+    // fresh refPixelWasGood mask: all true (Frame.h:433).  Written by the CTAs of the FIRST level only: their stores are
+    // released by that level's barriers, which every later level record -- and so every level-1 evaluation -- follows.
+    if (p.maskFresh && joinLvl == topLvl) {
         uint32_t* m32 = reinterpret_cast<uint32_t*>(p.goodMask);
-        for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < p.maskBytes / 4; i += gridDim.x * TP_THREADS) m32[i] = 0x01010101u;
+        const int Gt = p.lvl[topLvl].G;
+        for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < p.maskBytes / 4; i += Gt * TP_THREADS) m32[i] = 0x01010101u;
     }
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = p.initRefToFrame[i];
-        for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
-        for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; }
-        lm.affine_a = 1.f; lm.affine_b = 0.f; lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
+        for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; lm.nEval[l] = 0; lm.nPts[l] = 0.f; }
+        lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
         lm.diverged = 0; lm.incTry = 0; lm.iteration = 0; lm.dbg[0] = lm.dbg[1] = lm.dbg[2] = lm.dbg[3] = 0;
-        lm.lvl = SE3TRACKING_MAX_LEVEL - 1; lm.phase = PH_INIT;
-        sh.lvl = lm.lvl; sh.action = ACT_CONTINUE;
+        lm.phase = PH_INIT;
+        sh.action = ACT_CONTINUE;
+        if (joinLvl == topLvl) {
+            for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = p.initRefToFrame[i];
+            for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
+            lm.affine_a = 1.f; lm.affine_b = 0.f;
+            sh.epochAll = 0u;
+        } else {
+            // wait until CTA 0 has finished the coarser levels and published the state this level starts from
+            LevelRecord* r = levelRecord(p, joinLvl);
+            while (ldAcquire(&r->tag) != p.launchSeq) __nanosleep(64);
+            for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = r->q[i];
+            for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = r->t[i];
+            lm.affine_a = r->a; lm.affine_b = r->b;
+            sh.action = r->action;
+            sh.epochAll = r->epochAll;
+        }
+        lm.lvl = joinLvl;
+        sh.lvl = joinLvl;
         setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
     }
     __syncthreads();
+    if (sh.action != ACT_CONTINUE) return;                          // tracking ended (diverged) before this CTA's level
+    unsigned int epochAll = sh.epochAll;
+    unsigned int epochLvl = 0u;
+    int curLvl = joinLvl;
 
     while (true) {
         const int lvl = sh.lvl;
-        const int npx = p.lvl[lvl].w * p.lvl[lvl].h;
-        const int evalMode = npx <= TP_LOCAL_MAX_PIXELS ? EVAL_CTA
-                           : (clusterSize > 1 && npx <= p.clusterLocalMaxPixels) ? EVAL_CLUSTER : EVAL_GRID;
-        gridEvaluate(p, lvl, evalMode, sh, sm, xrow, xphase, epoch, cyc, W);
-        if (threadIdx.x == 0) { const long long t0 = clock64(); lmAdvance(p, lm, sh); lm.dbg[0] += clock64() - t0; }
-        __syncthreads();
+        if (lvl != curLvl) { curLvl = lvl; epochLvl = 0u; }
+        levelEvaluate(p, lvl, sh, sm, epochAll, epochLvl, cyc, W);
+        if (threadIdx.x == 0) { lm.nEval[lvl]++; lm.nPts[lvl] = sh.sums[CH_REFNUM]; }
+        lmStep(p, lm, sh, epochAll);
         if (sh.action != ACT_CONTINUE) break;
     }
 
-    if (clusterSize > 1) cg::this_cluster().sync();             // nobody may exit while a peer can still read its xrow
     if (p.debug) {
-        atomicAdd(p.barrier + 41, W.hits & 0xffffu);
-        atomicAdd(p.barrier + 42, W.hits >> 16);
+        atomicAdd(p.sync + TP_SYNC_WORDS - 3, W.hits & 0xffffu);
+        atomicAdd(p.sync + TP_SYNC_WORDS - 2, W.hits >> 16);
     }
     if (p.debug && threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
         long long tot = clock64() - tStart;
@@ -700,8 +765,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         out->meanRes = ev.meanRes; out->lastResidual = lm.last_residual;
         out->affine_a = lm.affine_a; out->affine_b = lm.affine_b;
         out->diverged = lm.diverged;
-        for (int l = 0; l < LSD_LEVELS; l++) { out->numCalcResidualCalls[l] = lm.nRes[l]; out->numCalcWarpUpdateCalls[l] = lm.nUpd[l]; }
-        out->totalEvals = (int)epoch;
+        for (int l = 0; l < LSD_LEVELS; l++) {
+            out->numCalcResidualCalls[l] = lm.nRes[l]; out->numCalcWarpUpdateCalls[l] = lm.nUpd[l]; out->evalsAtLevel[l] = lm.nEval[l];
+            out->pointsAtLevel[l] = lm.nPts[l];
+        }
+        out->totalEvals = (int)epochAll;
         // device-resident copy of what the mapping kernels of the same frame need (no host round trip in between)
         for (int i = 0; i < 7; i++) outDev->refToFrame[i] = out->refToFrame[i];
         outDev->pointUsage = ev.pointUsage; outDev->goodCount = ev.goodCount; outDev->badCount = ev.badCount;
@@ -711,9 +779,30 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
-        if (p.debug) for (int i = 0; i < 3; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
+        if (p.debug) for (int i = 0; i < 2; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
         __threadfence_system();
         out->doneSeq = p.launchSeq;
+    }
+}
+
+// Environment switches are read ONCE, when the context is created (they used to cost several getenv() per frame).
+static void trackReadOptions(lsdgpu_ctx* ctx)
+{
+    const char* e;
+    ctx->optTrackTma = (e = getenv("LSDGPU_TRACK_TMA")) ? atoi(e) : 1;
+    ctx->optTrackDebug = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
+    ctx->optSingleSync = (e = getenv("LSDGPU_SINGLE_SYNC")) ? atoi(e) : 0;
+    // warps of a CTA that take a chunk on levels 4 / 3 / 2 / 1 ("a,b,c,d"); fewer warps per CTA = more CTAs behind the
+    // level's barrier but a cheaper CTA reduction
+    ctx->optTrackWpc[0] = 0;
+    for (int l = 1; l < LSD_LEVELS; l++) ctx->optTrackWpc[l] = TP_WARPS;
+    if ((e = getenv("LSDGPU_TRACK_WPC"))) {
+        int v[4] = { TP_WARPS, TP_WARPS, TP_WARPS, TP_WARPS };
+        sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
+        for (int k = 0; k < 4; k++) {
+            const int l = 4 - k;
+            ctx->optTrackWpc[l] = v[k] < 1 ? 1 : (v[k] > TP_WARPS ? TP_WARPS : v[k]);
+        }
     }
 }
 
@@ -725,44 +814,24 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
     if (!coop) return cudaErrorNotSupported;
     e = cudaFuncSetAttribute((const void*)k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_WIN_SMEM);
     if (e != cudaSuccess) return e;
-    // Optional (LSDGPU_TRACK_CLUSTER=2|4|8): launch as thread-block clusters and evaluate levels of <= 8192 pixels (L3, L4
-    // at 640x480) redundantly per cluster with a DSMEM exchange instead of the grid barrier.  Measured on B200: SLOWER
-    // (cluster 4: 228k vs 211k cycles per frame; cluster 2: 275k) -- a warp then walks 2-3 chunks sequentially and the
-    // per-chunk dependency chain (~2 700 cycles) dominates; the grid has enough warps to give every chunk its own.
-    // Default: no clusters.  The grid is the largest whole number of co-resident clusters (B200: 33 x 4 = 132 CTAs).
-    {
-        const char* ce = getenv("LSDGPU_TRACK_CLUSTER");
-        int cs = ce ? atoi(ce) : 1;
-        if (cs != 1 && cs != 2 && cs != 4 && cs != 8) cs = 1;
-        ctx->trackCluster = 1;
-        ctx->trackGrid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;
-        if (cs > 1) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ctx->smCount / cs * cs); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, (const void*)k_track_persistent, &cfg) == cudaSuccess && nc * cs >= 64) {
-                ctx->trackCluster = cs;
-                ctx->trackGrid = nc * cs < TP_MAXGRID ? nc * cs : (TP_MAXGRID / cs) * cs;
-            } else
-                cudaGetLastError();
-        }
+    trackReadOptions(ctx);
+    ctx->trackGrid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM, co-resident (cooperative launch)
+    // work split per level (see TrackLevelParams): interior pixels in chunks of 32, CTAs 0..G-1 take part
+    int gPrev = 1;
+    for (int l = LSD_LEVELS - 1; l >= 0; l--) {
+        const int w = ctx->cam[l].w, h = ctx->cam[l].h;
+        const int nInt = (w - 2) * (h - 2), nChunks = (nInt + 31) / 32;
+        int G = (nChunks + ctx->optTrackWpc[l > 0 ? l : 1] - 1) / ctx->optTrackWpc[l > 0 ? l : 1];
+        if (G > ctx->trackGrid) G = ctx->trackGrid;
+        if (G < gPrev) G = gPrev;                                  // finer levels never use fewer CTAs: a CTA joins once and stays
+        if (G > nChunks) G = nChunks;
+        ctx->trackG[l] = G;
+        gPrev = G;
     }
-    if (getenv("LSDGPU_TRACK_DEBUG")) {
-        fprintf(stderr, "[track] cluster %d, grid %d\n", ctx->trackCluster, ctx->trackGrid);
-        for (int cs = 1; cs <= 8; cs *= 2) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(ctx->smCount / cs * cs); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int nc = -1;
-            cudaError_t ce = cudaOccupancyMaxActiveClusters(&nc, (const void*)k_track_persistent, &cfg);
-            fprintf(stderr, "[track] cluster size %d: max active clusters %d (%s) -> %d CTAs\n", cs, nc, cudaGetErrorString(ce), nc * cs);
-        }
-        cudaGetLastError();
+    if (ctx->optTrackDebug) {
+        fprintf(stderr, "[track] grid %d, CTAs per level (L4..L1):", ctx->trackGrid);
+        for (int l = LSD_LEVELS - 1; l >= 1; l--) fprintf(stderr, " %d", ctx->trackG[l]);
+        fprintf(stderr, "\n");
     }
     return cudaSuccess;
 }
@@ -792,9 +861,11 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
         L.kfIdepth = kf->idepth[l]; L.kfVar = kf->idepthVar[l]; L.kfColor = kf->image[l]; L.frameGrad = fr->grad[l];
         L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
         L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
+        L.iw = c.w - 2; L.nInt = (c.w - 2) * (c.h - 2); L.nChunks = (L.nInt + 31) / 32;
+        L.G = ctx->trackG[l];
     }
     for (int l = 0; l < LSD_LEVELS; l++) P.gradMap[l] = fr->gradMap[l];
-    { const char* tm = getenv("LSDGPU_TRACK_TMA"); P.useTma = tm ? atoi(tm) : 1; }
+    P.useTma = ctx->optTrackTma;
     P.minLevel = SE3TRACKING_MIN_LEVEL;
     P.goodMask = fr->goodMask;
     P.maskFresh = fr->hasGoodMask ? 0 : 1;
@@ -810,29 +881,25 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     P.C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; P.C.var_weight = st->var_weight; P.C.huber_half = st->huber_d / 2;
     P.useAffine = ctx->g.useAffineLightningEstimation;
     P.partials = ctx->evPartials;
-    P.barrier = ctx->evCounter;
-    { const char* bm = getenv("LSDGPU_BARRIER_MODE"); P.barrierMode = bm ? atoi(bm) : 1; }
+    P.sync = ctx->trkSync;
+    for (int l = 0; l < LSD_LEVELS; l++) P.barrierBase[l] = ctx->trkBase[l];
     if (prep) { P.doPrepare = 1; P.prep = *prep; P.obsOut = ctx->dObs; P.skipOut = ctx->dSkipFlag; }
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* dOutDev = (TrackState*)ctx->dTrackState;
 
-    const int grid = ctx->trackGrid;                                               // one CTA per SM (whole clusters)
-    P.clusterLocalMaxPixels = ctx->trackCluster > 1 ? TP_CLUSTER_MAX_PIXELS : 0;
+    const int grid = ctx->trackGrid;                                               // one CTA per SM
     void* args[] = { (void*)&P, (void*)&dOut, (void*)&dOutDev };
-    const bool dbg = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
+    const bool dbg = ctx->optTrackDebug;
     P.debug = dbg ? 1 : 0;
-    P.barrierBase = ctx->barrierBase;
     P.launchSeq = ++ctx->trackSeq;
-    if (dbg) LSD_CHECK(ctx, cudaMemsetAsync(ctx->evCounter + 40, 0, 4 * sizeof(unsigned int), ctx->stream));
+    if (dbg) LSD_CHECK(ctx, cudaMemsetAsync(ctx->trkSync + TP_SYNC_WORDS - 4, 0, 4 * sizeof(unsigned int), ctx->stream));
     if (ctx->profileTrackKernel) cudaEventRecord(ctx->kBegin, ctx->stream);
     {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TP_THREADS); cfg.dynamicSmemBytes = TP_WIN_SMEM; cfg.stream = ctx->stream;
-        cudaLaunchAttribute at[2];
+        cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-        at[1].id = cudaLaunchAttributeClusterDimension;
-        at[1].val.clusterDim.x = ctx->trackCluster; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = ctx->trackCluster > 1 ? 2 : 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
         LSD_CHECK(ctx, cudaLaunchKernelExC(&cfg, (const void*)k_track_persistent, args));
     }
     ctx->launches++;
@@ -855,10 +922,9 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
 {
     memset(out, 0, sizeof(*out));
     TrackState* hOut = (TrackState*)ctx->hTrackState;
-    const int grid = ctx->trackGrid;
     // The result block lives in mapped pinned memory and its last word is a sequence number: spin on it (a few
     // hundred ns of latency) instead of a stream synchronisation.  Later launches are stream-ordered anyway.
-    if (getenv("LSDGPU_TRACK_DEBUG")) LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->optTrackDebug) LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     else {
         bool done = false;
         for (long long spin = 0; spin < 200000000LL; spin++) {
@@ -870,33 +936,50 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
     // the other fields of the mapped result block are read with plain loads below: keep them behind the doneSeq read.  Block 0
     // publishes doneSeq while other CTAs may still be exiting, so only STREAM-ORDERED consumers may assume the kernel has retired.
     std::atomic_thread_fence(std::memory_order_acquire);
-    ctx->barrierBase += (unsigned int)hOut->totalEvals * (unsigned int)grid;
+    for (int l = 0; l < LSD_LEVELS; l++)
+        ctx->trkBase[l] += (unsigned int)hOut->evalsAtLevel[l] * (unsigned int)ctx->trackG[l];   // the level counters are never reset
 
     if (ctx->profileTrackKernel) {           // the event pair is read lazily (flushTrackProfile): no extra sync on the path
+        // SURVEY 8d, fused single-pass kernel: B_fused(l) = 20 B per valid point + 16 B per texel of the frame's gradient
+        // level (+5 B per point on L1: mask byte + index) + 160 B of partial sums, per evaluation.  The kernel reads the three
+        // keyframe planes densely (12 B per pixel); the ALGORITHMIC figure charges only the valid points, as the survey defines it.
         double bytes = 0;
-        for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++)
-            bytes += (double)hOut->numCalcResidualCalls[l] * ((double)ctx->cam[l].w * ctx->cam[l].h * (12.0 + 16.0 + (l == 1 ? 1.0 : 0.0)) + EV_NCH * 4.0);
+        for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++) {
+            const double np_ = (double)hOut->pointsAtLevel[l];   // numData[level]: valid points of the level (CH_REFNUM)
+            bytes += (double)hOut->evalsAtLevel[l] * (20.0 * np_ + 16.0 * (double)ctx->cam[l].w * ctx->cam[l].h + (l == 1 ? 5.0 * np_ : 0.0) + EV_NCH * 4.0);
+        }
         ctx->trackKernelBytes += bytes;
         ctx->trackProfilePending = true;
     }
 
-    if (getenv("LSDGPU_TRACK_DEBUG")) {
-        unsigned int dbgc[3] = { 0, 0, 0 };
-        cudaMemcpy(dbgc, ctx->evCounter + 40, 12, cudaMemcpyDeviceToHost);
+    if (ctx->optTrackDebug) {
+        unsigned int dbgc[4] = { 0, 0, 0, 0 };
+        cudaMemcpy(dbgc, ctx->trkSync + TP_SYNC_WORDS - 4, 16, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[track] useTma=%d tmaTimeouts=%u taps: %u from the smem window, %u through L1/L2\n", ctx->trackUseTma, dbgc[0], dbgc[1], dbgc[2]);
-        fprintf(stderr, "[track] evals=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
-                hOut->totalEvals, hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
-        fprintf(stderr, "   thread0: lmAdvance=%lld (solve=%lld pose=%lld)\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2]);
+        fprintf(stderr, "[track] evals=%d (L4..L1: %d %d %d %d) cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
+                hOut->totalEvals, hOut->evalsAtLevel[4], hOut->evalsAtLevel[3], hOut->evalsAtLevel[2], hOut->evalsAtLevel[1],
+                hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
+        fprintf(stderr, "   thread0: decide=%lld apply=%lld\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1]);
         const char* nm[6] = { "points", "ctaReduce", "barrier", "combine", "serial", "total" };
+        const int gAll = ctx->trackG[SE3TRACKING_MIN_LEVEL];
         for (int k = 0; k < 6; k++) {
             long long mn = 1LL << 60, mx = 0, sum = 0; int imx = 0, imn = 0;
-            for (int b = 0; b < grid && b < TP_MAXGRID_DBG; b++) {
+            for (int b = 0; b < gAll && b < TP_MAXGRID_DBG - 1; b++) {
                 long long v = hOut->cycBlk[b][k];
                 if (v < mn) { mn = v; imn = b; }
                 if (v > mx) { mx = v; imx = b; }
                 sum += v;
             }
-            fprintf(stderr, "   %-9s min=%lld (cta %d) max=%lld (cta %d) mean=%lld\n", nm[k], mn, imn, mx, imx, sum / grid);
+            fprintf(stderr, "   %-9s min=%lld (cta %d) max=%lld (cta %d) mean=%lld\n", nm[k], mn, imn, mx, imx, sum / gAll);
+        }
+    }
+    // a TMA copy that never completed downgrades that warp to the L1/L2 path (same results): never silent
+    if (!ctx->optTrackDebug && (ctx->trackSeq & 0xff) == 0) {
+        unsigned int tmo = 0;
+        cudaMemcpy(&tmo, ctx->trkSync + TP_SYNC_WORDS - 4, 4, cudaMemcpyDeviceToHost);
+        if (tmo != ctx->tmaTimeoutsSeen) {
+            fprintf(stderr, "[lsdgpu] warning: %u TMA window copies timed out so far (tracking falls back to L1/L2 taps for those warps)\n", tmo);
+            ctx->tmaTimeoutsSeen = tmo;
         }
     }
     out->pointUsage = hOut->pointUsage; out->lastGoodCount = hOut->goodCount; out->lastBadCount = hOut->badCount;

@@ -44,30 +44,39 @@ def test_bench_refuses_to_run_the_gpu_arm_without_a_gpu():
     assert not any(ln.strip().startswith("{") for ln in r.stdout.splitlines())
 
 
-def _fake_gpu_run_factory(bench, perturb=0.0):
+def _fake_gpu_run_factory(bench):
     import numpy as np
 
     def fake_gpu_run(args, rank, world, local_rank):
         R = bench.n_passes(args.steps)
         n = args.warmup + R * args.steps
         seq, frames = bench.render_frames(args.width, args.height, 1234, n + 1)
-        poses = bench.cpu_loop(seq, frames, n, 0, time_budget_s=0, flavour=False)["poses"].copy()   # what a correct device run returns
-        poses[:, 4:7] *= (1.0 + perturb)
         pr = [{"rank": 0, "sum_ms": 2.0 * R, "p50": 0.2, "p95": 0.22, "max_step_ms": 0.3, "argmax_step": 1, "pass_ms": [2.0] * R,
                "sm_mhz": 1965.0, "reasons": [], "pinned_cores": None}]
         leg = dict(pass_ms=[2.0] * R, launches=53 * R, clocks={"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 5}, wall=0.1,
-                   kms=1.1, klaunch=10, kbytes=1.1e8, poses=poses, p50=0.2, p95=0.22, per_rank=pr)
+                   kms=1.1, klaunch=10, kbytes=1.1e8, poses=np.zeros((n, 7)), p50=0.2, p95=0.22, per_rank=pr)
         return seq, frames, {"resident": leg, "e2e": dict(leg, pass_ms=[2.2] * R)}
     return fake_gpu_run
 
 
+def _fake_parity_leg_factory(bench, pose_rel):
+    def fake_parity_leg(args, seq, frames, res):
+        n = min(len(frames), args.warmup + args.steps + 1)
+        o = bench.cpu_loop(seq, frames[:n], n - 1, 0, time_budget_s=0, flavour=False)
+        par = {"tolerance": bench.POSE_TOL, "frames": 5, "max_pose_rel": pose_rel, "maps_identical": True, "legs_bit_identical": True}
+        par["ok"] = pose_rel <= bench.POSE_TOL
+        return par, o["poses"]
+    return fake_parity_leg
+
+
 def test_product_arm_line_contract_with_mocked_device_results(monkeypatch, capsys):
     """the JSON line of the product arm (everything after the device timing): all contract keys, roofline, cpu_baseline,
-    e2e, clocks, gpu_launches, the in-run parity record -- exercised on the CPU by replacing only the device loop"""
+    e2e, clocks, gpu_launches, the in-run parity record -- exercised on the CPU by replacing only the two device loops"""
     sys.path.insert(0, ROOT)
     import bench
     from oracle import pyoracle
     monkeypatch.setattr(bench, "gpu_run", _fake_gpu_run_factory(bench))
+    monkeypatch.setattr(bench, "parity_leg", _fake_parity_leg_factory(bench, 2e-5))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "20", "--warmup", "3"])
     monkeypatch.setattr(bench, "n_passes", lambda steps: 1)
     bench.main()
@@ -87,21 +96,22 @@ def test_product_arm_line_contract_with_mocked_device_results(monkeypatch, capsy
     assert cb["cores"] == 5 and cb["value"] > 0 and cb["single_core"]["value"] > 0
     assert 0.30 <= d["config"]["semi_dense_fraction"] <= 0.50 and "workload" in d["config"] and "l2" in d["config"]
     par = d["parity"]
-    assert par["ok"] is True and par["max_pose_rel"] == 0.0 and par["frames"] == 23 and par["tolerance"] == 1e-4
+    assert par["ok"] is True and par["tolerance"] == 1e-4
     if cb["kind"] == "reference":
         assert par["reference_sse_vs_scalar"]["max_pose_rel"] > 1e-4        # the stock SSE build is NOT within 1e-4 of its scalar path
 
 
 def test_product_arm_fails_when_parity_is_off(monkeypatch, capsys):
-    """poses 3e-4 away from the oracle: the line still prints (parity.ok false) and the process exits non-zero"""
+    """a pose 3e-4 away from the oracle on a replayed step: the line still prints (parity.ok false), the process exits non-zero"""
     import pytest
     sys.path.insert(0, ROOT)
     import bench
-    monkeypatch.setattr(bench, "gpu_run", _fake_gpu_run_factory(bench, perturb=3e-4))
+    monkeypatch.setattr(bench, "gpu_run", _fake_gpu_run_factory(bench))
+    monkeypatch.setattr(bench, "parity_leg", _fake_parity_leg_factory(bench, 3e-4))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
     monkeypatch.setattr(bench, "n_passes", lambda steps: 1)
     with pytest.raises(SystemExit) as ei:
         bench.main()
     assert ei.value.code == 3
     d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][0])
-    assert d["parity"]["ok"] is False and 2e-4 < d["parity"]["max_pose_rel"] < 4e-4
+    assert d["parity"]["ok"] is False
