@@ -164,14 +164,20 @@ LSD_HD void mat3Inverse(const float m[9], float r[9])
     r[8] = (m[0] * m[4] - m[1] * m[3]) * inv;
 }
 
-// Eigen's unrolled reduction tree (Redux.h): sum(first n/2) + sum(rest)
+// Eigen's unrolled reduction tree (Redux.h): sum(first n/2) + sum(rest), written out for n <= 8 (no recursion: the
+// function must inline into device code, otherwise the caller's matrices are forced into local memory)
 LSD_HD float treeSumF(const float* v, int n)
 {
-    if (n == 1) return v[0];
-    if (n == 2) return v[0] + v[1];
-    if (n == 3) return v[0] + (v[1] + v[2]);
-    const int h = n / 2;
-    return treeSumF(v, h) + treeSumF(v + h, n - h);
+    switch (n) {
+    case 1: return v[0];
+    case 2: return v[0] + v[1];
+    case 3: return v[0] + (v[1] + v[2]);
+    case 4: return (v[0] + v[1]) + (v[2] + v[3]);
+    case 5: return (v[0] + v[1]) + (v[2] + (v[3] + v[4]));
+    case 6: return (v[0] + (v[1] + v[2])) + (v[3] + (v[4] + v[5]));
+    case 7: return (v[0] + (v[1] + v[2])) + ((v[3] + v[4]) + (v[5] + v[6]));
+    default: return ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
 }
 
 // x = A^-1 b for a symmetric NxN via LDL^T with largest-diagonal pivoting (float): Eigen's LDLT (unblocked lower

@@ -144,10 +144,12 @@ __device__ __forceinline__ void levelBarrier(unsigned int* counter, unsigned int
         unsigned int v;
         asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
         if (v != target - 1u) {
-            do { v = ldAcquire(counter); } while ((int)(v - target) < 0);
-        } else {
-            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            // poll with relaxed loads (served by L2, no cache maintenance per probe), ONE acquire fence once the epoch is complete
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+            } while ((int)(v - target) < 0);
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -373,29 +375,24 @@ __device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMS
     long long t2 = clock64();
     levelBarrier(p.sync + 32 * lvl, p.barrierBase[lvl] + epochLvl * (unsigned int)G);
     long long t3 = clock64();
-    // warp wi owns channels wi, wi+TP_WARPS, ... (<= 3 per warp); all loads are issued first, then one
-    // multi-value reduction in double
+    // 40 channels x 8 lanes: lane (c, q) adds rows q, q+8, ... of channel c in double (fixed order), three shuffles finish
     {
-        double ch[4];
         const int nb = (int)gridDim.x;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = warp + k * TP_WARPS;
-            float v[TP_MAXGRID / 32];
-#pragma unroll
-            for (int j = 0; j < TP_MAXGRID / 32; j++) {
-                const int bb = lane + 32 * j;
-                v[j] = (c < EV_NCH && bb < G) ? __ldcg(part + (size_t)c * nb + bb) : 0.f;
+        const int c = threadIdx.x >> 3, q = threadIdx.x & 7;
+        if (c < EV_NCH) {                                            // warps 0..9, whole warps
+            const float* row = part + (size_t)c * nb;
+            double a0 = 0.0, a1 = 0.0;
+            int bb = q;
+            for (; bb + 8 < G; bb += 16) {                           // two independent chains keep two loads in flight
+                const float v0 = __ldcg(row + bb), v1 = __ldcg(row + bb + 8);
+                a0 += (double)v0; a1 += (double)v1;
             }
-            double sacc = 0.0;
-#pragma unroll
-            for (int j = 0; j < TP_MAXGRID / 32; j++) sacc += (double)v[j];
-            ch[k] = sacc;
-        }
-        warpReduceMulti<4>(ch, lane);
-        if ((lane & 7) == 0) {
-            const int c = warp + warpReduceChannel<4>(lane) * TP_WARPS;
-            if (c < EV_NCH) sh.sums[c] = (float)ch[0];
+            if (bb < G) a0 += (double)__ldcg(row + bb);
+            double acc = a0 + a1;
+            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            if (q == 0) sh.sums[c] = (float)acc;
         }
     }
     __syncthreads();
@@ -513,26 +510,48 @@ __device__ __forceinline__ void affineFromSums(const float* s, float& a, float& 
     b = (sy - a * sx) / sw;
 }
 
+// Pivoted LDL^T fallback (hostmath.h, Eigen's algorithm) for the rare case that the unpivoted solve meets a non-positive pivot.
+// Out of line and fed from the sums in shared memory so that the fast path's matrices never have their address taken.
+__device__ __noinline__ void ldlt6SolvePivotedFromSums(const float* lsq, float lambda, float* incOut)
+{
+    static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
+                                            {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
+    float A[36], b[6];
+    for (int k = 0; k < 21; k++) { const float v = lsq[k]; A[ij[k][0] * 6 + ij[k][1]] = v; A[ij[k][1] * 6 + ij[k][0]] = v; }
+    for (int i = 0; i < 6; i++) b[i] = lsq[21 + i];
+    const float damp = 1 + lambda;
+    for (int i = 0; i < 6; i++) A[i * 6 + i] *= damp;
+    lsd::ldlt6Solve(A, b, incOut);
+}
+
 // Solve the damped system `lsq` (RAW sums: LGS6::finish divides A and b by num_constraints, LGSX.h:319-325, which cancels
 // in A^-1 b because the damping is multiplicative) and form exp(inc) * base with its rotation matrix (SE3Tracker.cpp:356-363).
 __device__ __forceinline__ void proposePose(const float* lsq, float lambda, const lsd::SE3<float>& base, Proposal& P)
 {
-    static const unsigned char ij[21][2] = { {0,0},{0,1},{0,2},{0,3},{0,4},{0,5},{1,1},{1,2},{1,3},{1,4},{1,5},
-                                            {2,2},{2,3},{2,4},{2,5},{3,3},{3,4},{3,5},{4,4},{4,5},{5,5} };
     float A[36], b[6], inc[6];
+    {
+        int k = 0;
 #pragma unroll
-    for (int k = 0; k < 21; k++) {
-        const float v = lsq[k];
-        A[ij[k][0] * 6 + ij[k][1]] = v;
-        A[ij[k][1] * 6 + ij[k][0]] = v;
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++) {
+                const float v = lsq[k++];
+                A[i * 6 + j] = v;
+                A[j * 6 + i] = v;
+            }
     }
 #pragma unroll
     for (int i = 0; i < 6; i++) b[i] = lsq[21 + i];
     const float damp = 1 + lambda;
 #pragma unroll
     for (int i = 0; i < 6; i++) A[i * 6 + i] *= damp;
-    if (!ldlt6SolveFast(A, b, inc)) lsd::ldlt6Solve(A, b, inc);
-    const lsd::SE3<float> c = se3ExpMulFast(inc, base);
+    if (!ldlt6SolveFast(A, b, inc)) {
+        ldlt6SolvePivotedFromSums(lsq, lambda, P.inc);
+#pragma unroll
+        for (int i = 0; i < 6; i++) inc[i] = P.inc[i];
+    }
+    const lsd::SE3<float> base_ = base;
+    const lsd::SE3<float> c = se3ExpMulFast(inc, base_);
 #pragma unroll
     for (int i = 0; i < 6; i++) P.inc[i] = inc[i];
     P.cand = c;
@@ -603,67 +622,87 @@ __device__ __forceinline__ void lmStep(const TrackParams& p, LMState& lm, LMShar
         sh.dChoice = (sh.dDiverged || leave) ? CHOICE_NONE : (accept ? CHOICE_ACCEPT : CHOICE_REJECT);
         lm.dbg[0] += clock64() - ta;
     } else if (tid == 32) {                                                      // ---- speculative: accepted
+        const long long ta = clock64();
         const bool init = lm.phase == PH_INIT;
         const float lam = init ? p.st.lambdaInitial[lvl]                         // :341
                                : ((lm.LM_lambda <= 0.2) ? 0.f : lm.LM_lambda * p.st.lambdaSuccessFac);   // :417-420
         proposePose(s, lam, init ? lm.refToFrame : lm.cand, sh.propA);           // the accepted pose becomes the base
+        lm.dbg[2] += clock64() - ta;
     } else if (tid == 64) {                                                      // ---- speculative: rejected
         if (lm.phase == PH_TRY) {
+            const long long ta = clock64();
             float lam = lm.LM_lambda;
             if (lam == 0) lam = 0.2;                                             // :443-446
             else lam *= ipowd((double)p.st.lambdaFailFac, lm.incTry);
             proposePose(lm.lsq, lam, lm.refToFrame, sh.propR);
+            lm.dbg[3] += clock64() - ta;
         }
     }
     __syncthreads();
-    if (tid == 0) {                                                              // ---- phase 2: apply
+    if (tid < 32) {                                                              // ---- phase 2: apply (warp 0; lane-parallel copies)
         const long long ta = clock64();
-        sh.action = ACT_CONTINUE;
-        bool nextLevel = false;
-        if (sh.dDiverged) {
-            lm.diverged = 1;
-            sh.action = ACT_DIVERGED;
-        } else {
-            lm.nRes[lvl]++;
-            if (sh.dAccept) {
-                if (!sh.dInit) lm.refToFrame = lm.cand;
-                lm.affine_a = sh.dA; lm.affine_b = sh.dB;
-                if (!sh.dInit) lm.last_residual = sh.dError;                     // :414
-                lm.lastErr = sh.dError;                                          // :336 / :414
-#pragma unroll
-                for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                   // buffers now belong to this pose
-                if (sh.dInit) lm.iteration = 0;
-                else if (!sh.dConverged) lm.iteration++;
-                if (!sh.dLeave) { lm.nUpd[lvl]++; lm.incTry = 0; }               // calculateWarpUpdate(ls), :346
+        const bool div = sh.dDiverged != 0, accept = sh.dAccept != 0, init = sh.dInit != 0, leave = sh.dLeave != 0;
+        const Proposal& P = accept ? sh.propA : sh.propR;
+        // every read of the state the scalar updates below overwrite happens BEFORE the __syncwarp
+        float lsqNew = 0.f, incNew = 0.f, rNew = 0.f, candNew = 0.f;
+        if (tid < 27) lsqNew = s[tid];
+        if (tid < 6) incNew = P.inc[tid];
+        if (tid < 9) rNew = P.R[tid];
+        if (tid < 7) candNew = tid < 4 ? P.cand.q[tid] : P.cand.t[tid - 4];
+        float acceptedPose = 0.f;
+        if (tid < 7) acceptedPose = tid < 4 ? lm.cand.q[tid] : lm.cand.t[tid - 4];
+        __syncwarp();
+        if (!div) {
+            if (accept) {
+                if (!init && tid < 7) { if (tid < 4) lm.refToFrame.q[tid] = acceptedPose; else lm.refToFrame.t[tid - 4] = acceptedPose; }
+                if (tid < 27) lm.lsq[tid] = lsqNew;                              // buffers now belong to this pose
             }
-            if (sh.dLeave) nextLevel = true;
-            else {
-                const Proposal& P = sh.dAccept ? sh.propA : sh.propR;
-#pragma unroll
-                for (int i = 0; i < 6; i++) lm.inc[i] = P.inc[i];
-                lm.LM_lambda = P.lambda;
-                lm.incTry++;
-                lm.cand = P.cand;
-#pragma unroll
-                for (int i = 0; i < 9; i++) sh.pose.R[i] = P.R[i];
-                sh.pose.t[0] = P.cand.t[0]; sh.pose.t[1] = P.cand.t[1]; sh.pose.t[2] = P.cand.t[2];
-                sh.pose.a = lm.affine_a; sh.pose.b = lm.affine_b;
-                lm.phase = PH_TRY;
+            if (!leave) {
+                if (tid < 6) lm.inc[tid] = incNew;
+                if (tid < 7) { if (tid < 4) lm.cand.q[tid] = candNew; else lm.cand.t[tid - 4] = candNew; }
+                if (tid < 9) sh.pose.R[tid] = rNew;
+                if (tid >= 4 && tid < 7) sh.pose.t[tid - 4] = candNew;
             }
         }
-        if (nextLevel) {
-            lm.lvl--;
-            if (lm.lvl < p.minLevel) sh.action = ACT_LEVEL_DONE;                 // all levels done
-            else {
-                lm.phase = PH_INIT;
-                setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
-                sh.lvl = lm.lvl;
-                if (blockIdx.x == 0) publishLevel(p, lm.lvl, lm, ACT_CONTINUE, epochAll);    // for the CTAs that join here
+        __syncwarp();
+        if (tid == 0) {
+            sh.action = ACT_CONTINUE;
+            bool nextLevel = false;
+            if (div) {
+                lm.diverged = 1;
+                sh.action = ACT_DIVERGED;
+            } else {
+                lm.nRes[lvl]++;
+                if (accept) {
+                    lm.affine_a = sh.dA; lm.affine_b = sh.dB;
+                    if (!init) lm.last_residual = sh.dError;                     // :414
+                    lm.lastErr = sh.dError;                                      // :336 / :414
+                    if (init) lm.iteration = 0;
+                    else if (!sh.dConverged) lm.iteration++;
+                    if (!leave) { lm.nUpd[lvl]++; lm.incTry = 0; }               // calculateWarpUpdate(ls), :346
+                }
+                if (leave) nextLevel = true;
+                else {
+                    lm.LM_lambda = P.lambda;
+                    lm.incTry++;
+                    sh.pose.a = lm.affine_a; sh.pose.b = lm.affine_b;
+                    lm.phase = PH_TRY;
+                }
             }
+            if (nextLevel) {
+                lm.lvl--;
+                if (lm.lvl < p.minLevel) sh.action = ACT_LEVEL_DONE;             // all levels done
+                else {
+                    lm.phase = PH_INIT;
+                    setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+                    sh.lvl = lm.lvl;
+                    if (blockIdx.x == 0) publishLevel(p, lm.lvl, lm, ACT_CONTINUE, epochAll);    // for the CTAs that join here
+                }
+            }
+            if (sh.action != ACT_CONTINUE && blockIdx.x == 0)                    // tracking ends: release every CTA still
+                for (int l = lvl - 1; l >= p.minLevel; l--) publishLevel(p, l, lm, sh.action, epochAll);   // waiting to join
+            lm.dbg[1] += clock64() - ta;
         }
-        if (sh.action != ACT_CONTINUE && blockIdx.x == 0)                        // tracking ends: release every CTA still
-            for (int l = lvl - 1; l >= p.minLevel; l--) publishLevel(p, l, lm, sh.action, epochAll);   // waiting to join
-        lm.dbg[1] += clock64() - ta;
     }
     __syncthreads();
 }
@@ -779,7 +818,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
-        if (p.debug) for (int i = 0; i < 2; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
+        if (p.debug) for (int i = 0; i < 4; i++) out->cycBlk[TP_MAXGRID_DBG - 1][i] = lm.dbg[i];
         __threadfence_system();
         out->doneSeq = p.launchSeq;
     }
@@ -959,7 +998,8 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
         fprintf(stderr, "[track] evals=%d (L4..L1: %d %d %d %d) cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
                 hOut->totalEvals, hOut->evalsAtLevel[4], hOut->evalsAtLevel[3], hOut->evalsAtLevel[2], hOut->evalsAtLevel[1],
                 hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
-        fprintf(stderr, "   thread0: decide=%lld apply=%lld\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1]);
+        fprintf(stderr, "   LM lanes: decide=%lld apply=%lld proposeAccepted=%lld proposeRejected=%lld\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0],
+                hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2], hOut->cycBlk[TP_MAXGRID_DBG - 1][3]);
         const char* nm[6] = { "points", "ctaReduce", "barrier", "combine", "serial", "total" };
         const int gAll = ctx->trackG[SE3TRACKING_MIN_LEVEL];
         for (int k = 0; k < 6; k++) {
