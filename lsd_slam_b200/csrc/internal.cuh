@@ -155,7 +155,7 @@ struct lsdgpu_ctx {
     // environment switches, read once at lsdgpu_create
     int optTrackTma = 1, optSingleSync = 0;
     bool optTrackDebug = false;
-    int optTrackWpc[LSD_LEVELS] = { 16, 16, 16, 16, 16 };
+    int optTrackKmax = 3;
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
     unsigned int trackSeq = 0;           // sequence number of the last tracking launch (TrackState::doneSeq)

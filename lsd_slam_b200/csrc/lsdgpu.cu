@@ -1232,6 +1232,7 @@ extern "C" int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_id
     P.C.cameraPixelNoise2 = ctx->g.cameraPixelNoise2; P.C.var_weight = st.var_weight; P.C.huber_half = st.huber_d / 2;
     P.useAffine = ctx->g.useAffineLightningEstimation;
     P.minLevel = QUICK_KF_CHECK_LVL;
+    P.kmax = 1;                                   // one pose per pass: the candidates are independent CTAs already
     PermaResult* dRes = (PermaResult*)ctx->dPermaResults;
     k_perma_track<<<n, PERMA_THREADS, 0, ctx->stream>>>(P, (const PermaItem*)ctx->dPermaItems, dRes);
     LAUNCH(ctx);

@@ -7,7 +7,7 @@
 // Callers in the reference evaluate MANY keyframe candidates against one frame, one call after the other
 // (Relocalizer.cpp:172,188; TrackableKeyFrameSearch.cpp:126,135; SlamSystem.cpp:1298,1304).  Here a whole candidate list
 // is one launch: one CTA per candidate runs the complete level-4 LM loop on its own (the problems are independent, so
-// there is no grid barrier and no exchange at all) with the same evalPoint() / lmStep() as the main tracker.
+// there is no grid barrier and no exchange at all) with the same evalPoint() / lmAdvance() as the main tracker (one pose per pass: kmax = 1).
 #pragma once
 #include "internal.cuh"
 #include "track.cuh"
@@ -75,18 +75,19 @@ __global__ void __launch_bounds__(PERMA_THREADS) k_perma_track(const __grid_cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = it.refToFrame[i];
         for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = it.refToFrame[4 + i];
-        for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; }
+        for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; lm.nEval[l] = 0; lm.nPts[l] = 0.f; }
+        lm.chainBase = 0; lm.statsFrom = 0; lm.commitLast = 0; lm.posesEvaluated = 0;
         lm.affine_a = 1.f; lm.affine_b = 0.f; lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
         lm.diverged = 0; lm.incTry = 0; lm.iteration = 0; lm.dbg[0] = lm.dbg[1] = lm.dbg[2] = lm.dbg[3] = 0;
         lm.lvl = QUICK_KF_CHECK_LVL; lm.phase = PH_INIT;
-        sh.lvl = lm.lvl; sh.action = ACT_CONTINUE;
-        setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+        sh.lvl = lm.lvl; sh.action = ACT_CONTINUE; sh.nPose = 1;
+        setEvalPose(sh.pose[0], lm.refToFrame, lm.affine_a, lm.affine_b);
     }
     __syncthreads();
     const float4* fg = L.frameGrad;
     const int w = L.w, h = L.h;
     while (true) {
-        const EvalPose P = sh.pose;
+        const EvalPose P = sh.pose[0];      // p.kmax == 1: one pose per pass
         PointAcc acc;
 #pragma unroll
         for (int c = 0; c < EV_NCH; c++) acc.v[c] = 0.f;
@@ -105,7 +106,8 @@ __global__ void __launch_bounds__(PERMA_THREADS) k_perma_track(const __grid_cons
             sh.sums[threadIdx.x] = s;
         }
         __syncthreads();
-        lmStep(p, lm, sh, 0u);           // all threads: decision on thread 0, the two speculative solves on threads 32 and 64
+        if (threadIdx.x < 32) lmAdvance(p, lm, sh, threadIdx.x);        // warp 0: decisions on lane 0, the solve in buildChain
+        __syncthreads();
         if (sh.action != ACT_CONTINUE) break;
     }
     if (threadIdx.x == 0) {

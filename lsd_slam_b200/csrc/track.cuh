@@ -142,6 +142,79 @@ __device__ __forceinline__ int evalPoint(float px, float py, float pz, float col
     return isGood ? 1 : 0;
 }
 
+// ---- speculative candidates of the persistent tracker (track_persistent.cuh) -------------------------------------------
+// A pass evaluates up to three poses of one LM iteration: the try itself (evalPoint: all channels) and the next one or two
+// tries the reference would make IF it rejects (same normal equations, larger lambda, SE3Tracker.cpp:424-447).  Those only
+// need what the accept test and the bookkeeping read: the weighted error and the warped-point count -- and, for the last
+// candidate of the chain (the pose the level usually ends on), the statistics SlamSystem reads after trackFrame.
+// Channel layout of the 16-float extension block:
+enum {
+    XL_SUMRESW = 0, XL_SUMRESU = 1, XL_SIGNED = 2, XL_GOOD = 3, XL_BAD = 4, XL_USAGE = 5,
+    XL_SXX = 6, XL_SYY = 7, XL_SX = 8, XL_SY = 9, XL_SW = 10,           // last candidate: 11 channels
+    XM_SUMRESW = 11, XM_GOOD = 12, XM_BAD = 13                          // middle candidate: 3 channels (14, 15: unused)
+};
+#define EV_NX 16                     // extension channels
+#define EV_NCHX (EV_NCH + EV_NX)     // channels of a pass with more than one candidate
+
+// evalPoint without the Jacobian and the normal equations: identical arithmetic for every quantity it accumulates, so that the
+// error of a pose evaluated here equals, bit for bit, the error evalPoint gives for the same pose (same reduction tree).
+// STATS: also the statistics and affine-lighting sums (last candidate); otherwise error + good / bad counts only.
+template <bool STATS, typename TapFn>
+__device__ __forceinline__ int evalPointLight(float px, float py, float pz, float color, float var,
+                                              const EvalPose& P, const EvalConsts& C,
+                                              float fx_l, float fy_l, float cx_l, float cy_l, int w, int h,
+                                              TapFn tap, float* x)
+{
+    float Wx = ((P.R[0] * px + P.R[1] * py) + P.R[2] * pz) + P.t[0];
+    float Wy = ((P.R[3] * px + P.R[4] * py) + P.R[5] * pz) + P.t[1];
+    float Wz = ((P.R[6] * px + P.R[7] * py) + P.R[8] * pz) + P.t[2];
+    float u_new = (Wx / Wz) * fx_l + cx_l;
+    float v_new = (Wy / Wz) * fy_l + cy_l;
+    if (!(u_new > 1 && v_new > 1 && u_new < w - 2 && v_new < h - 2)) return 0;
+
+    float gi0, gi1, gi2;
+    tap(u_new, v_new, gi0, gi1, gi2);
+
+    float c1 = P.a * color + P.b;
+    float c2 = gi2;
+    float residual = c1 - c2;
+    if (STATS) {
+        float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
+        x[XL_SXX] += c1 * c1 * weight;
+        x[XL_SYY] += c2 * c2 * weight;
+        x[XL_SX] += c1 * weight;
+        x[XL_SY] += c2 * weight;
+        x[XL_SW] += weight;
+    }
+    bool isGood = residual * residual / ((40.0f * 40.0f) + (0.5f * 0.5f) * (gi0 * gi0 + gi1 * gi1)) < 1;
+
+    float gx = fx_l * gi0, gy = fy_l * gi1;
+    float d = 1.0f / pz;
+    if (STATS) {
+        if (isGood) {
+            x[XL_SUMRESU] += residual * residual;
+            x[XL_SIGNED] += residual;
+            x[XL_GOOD] += 1.f;
+        } else
+            x[XL_BAD] += 1.f;
+        float depthChange = pz / Wz;
+        x[XL_USAGE] += depthChange < 1 ? depthChange : 1;
+    } else {
+        if (isGood) x[XM_GOOD] += 1.f;
+        else x[XM_BAD] += 1.f;
+    }
+
+    float s = C.var_weight * var;
+    float g0 = (P.t[0] * Wz - P.t[2] * Wx) / (Wz * Wz * d);
+    float g1 = (P.t[1] * Wz - P.t[2] * Wy) / (Wz * Wz * d);
+    float drpdd = gx * g0 + gy * g1;
+    float w_p = 1.0f / ((C.cameraPixelNoise2) + s * drpdd * drpdd);
+    float weighted_rp = fabsf(residual * sqrtf(w_p));
+    float wh = fabsf(weighted_rp < C.huber_half ? 1 : C.huber_half / weighted_rp);
+    x[STATS ? XL_SUMRESW : XM_SUMRESW] += wh * w_p * residual * residual;
+    return isGood ? 1 : 0;
+}
+
 // CTA-level reduction of all channels: warp shuffles, then one smem stage.  Result valid in warp 0, lane c.
 template <int NWARPS>
 __device__ __forceinline__ void blockReduceChannels(PointAcc& acc, float (*sm)[EV_NCH], float* blockRow)

@@ -1,31 +1,42 @@
 // track_persistent.cuh -- SE3Tracker::trackFrame as ONE persistent cooperative kernel (mode 1).
 //
 // The whole coarse-to-fine Levenberg-Marquardt loop of Tracking/SE3Tracker.cpp:280-486 runs on the device:
-// every CTA evaluates its share of the keyframe pixels with evalPoint() (track.cuh), the CTAs exchange
-// EV_NCH partial sums through L2 behind ONE grid-wide barrier per evaluation, and then EVERY CTA redundantly
-// (and deterministically: same instructions on the same data) combines the partials in block order, solves
-// the damped 6x6 system (LDL^T), applies exp(inc) * T and takes the accept / reject / converge decision of
-// :381-446.  No host round trip, no second barrier, no float atomics.  The host sees one launch and one
+// every CTA evaluates its share of the keyframe pixels with evalPoint() (track.cuh), the CTAs exchange their
+// partial sums through L2 behind ONE grid-wide barrier per pass, and then EVERY CTA redundantly (and
+// deterministically: same instructions on the same data) combines the partials in block order, takes the
+// accept / reject / converge decisions of :381-446, solves the damped 6x6 systems (LDL^T) and applies
+// exp(inc) * T.  No host round trip, no second barrier, no float atomics.  The host sees one launch and one
 // 200-byte result per frame.
 //
-// Why this shape on B200: a 640x480 frame has <= 77k points on the finest tracked level, i.e. ~2 per resident
-// thread; one evaluation is a few microseconds of latency, so the reference's structure (3 passes per
-// evaluation, one host decision between evaluations, 15-60 evaluations per frame) is launch/latency bound by
-// two orders of magnitude.  Grid = one CTA per SM (148), co-residency guaranteed by the cooperative launch.
+// CANDIDATE CHAINS.  Measured on B200 one pass costs ~14 000 cycles of which ~10 000 are latency that no byte
+// count touches (CTA reduction, ~5 dependent L2 round trips of barrier + combine, the serial LM step), and on the
+// bench stream 10 of the 13 tries of a frame are REJECTED: after the first accepted step or two of a level the
+// reference walks lambda = 0, 0.2, 0.8, 6.4, ... until the step is too small (:424-447).  All tries of one iteration
+// share the normal equations, and lambda does not depend on the evaluations, so the whole chain is known the moment
+// the iteration starts.  A pass therefore evaluates up to TP_KMAX poses: the try itself with all channels, and the
+// next tries the reference would make if it rejects (error + counts; statistics for the chain's last pose).  The
+// decisions are then replayed in the reference's order; whatever the reference would not have evaluated is
+// discarded.  Results, call counters and the good-mask are exactly those of the one-pose-per-pass kernel (same
+// per-point arithmetic, same reduction trees); only the number of passes drops (17 -> 11 on frame 1 of the stream).
+//
+// Why this shape on B200: a 640x480 frame has <= 77k points on the finest tracked level, i.e. ~1 per resident
+// thread; the reference's structure (3 loops per evaluation, one host decision between evaluations, 15-60
+// evaluations per frame) is launch/latency bound by two orders of magnitude.  Grid = one CTA per SM (148),
+// co-residency guaranteed by the cooperative launch.
 #pragma once
 #include "internal.cuh"
 #include "track.cuh"
 #include <stdlib.h>
 #include <atomic>
-#include <cooperative_groups.h>
-namespace cg = cooperative_groups;
 
 #define TP_THREADS 512
 #define TP_WARPS (TP_THREADS / 32)
 #define TP_MAXGRID 160               // combine code is unrolled for <= 160 CTAs (B200: 148 SMs)
 #define TP_MAXGRID_DBG 160
 #define TP_WIN_SMEM (TP_WARPS * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
-#define TP_SYNC_WORDS 1024           // ctx->trkSync: barrier counter of level l at word 32*l, level records from word 256 on
+#define TP_SYNC_WORDS 1024           // ctx->trkSync: word 0 = arrival counter of the grid barrier; last 4 words: debug counters
+#define TP_KMAX 3                    // poses per pass: the try + up to two speculative successors
+#define TP_ROW 64                    // floats per exchange row (256 B, one row per CTA; EV_NCHX = 56 used)
 
 struct TrackLevelParams {
     const float* kfIdepth;
@@ -34,19 +45,11 @@ struct TrackLevelParams {
     const float4* frameGrad;
     int w, h;
     float fx, fy, cx, cy, fxi, fyi, cxi, cyi;
-    // Work split of the persistent tracker.  Only INTERIOR pixels can be points (TrackingReference.cpp:128-129 scans
-    // 1..w-2 x 1..h-2); they are numbered row by row, j = (x-1) + (y-1)*iw, and cut into chunks of 32 consecutive j.
+    // Only INTERIOR pixels can be points (TrackingReference.cpp:128-129 scans 1..w-2 x 1..h-2); they are numbered row by row,
+    // j = (x-1) + (y-1)*iw, and cut into chunks of 32 consecutive j (chunk c -> CTA c % gridDim, warp slot c / gridDim).
     // At 640x480 level 1 has 318*238 = 75 684 interior pixels = 2 366 chunks <= 148 CTAs x 16 warps: one chunk per warp.
     int iw, nInt, nChunks;
-    int G;                           // CTAs 0..G-1 evaluate this level (chunk c -> CTA c % G, warp slot c / G); non-increasing in l
-};
-
-// what CTA 0 leaves in global memory when a level starts, for the CTAs that join the computation at that level
-struct alignas(128) LevelRecord {
-    float q[4], t[3], a, b;          // refToFrame and the affine estimate at the start of the level
-    int action;                      // ACT_CONTINUE, or a stop code if tracking ended before this level
-    unsigned int epochAll;           // evaluations done so far in this launch (parity of the exchange buffer)
-    unsigned int tag;                // == launchSeq once the record is complete (written last, release)
+    int G;                           // unused by trackFrame (all CTAs take part in every level); kept for the batch trackers
 };
 
 struct alignas(64) TrackParams {
@@ -60,13 +63,14 @@ struct alignas(64) TrackParams {
     lsdgpu_track_settings st;
     EvalConsts C;
     int useAffine;
-    float* partials;                 // [2][EV_NCH][gridDim]
-    unsigned int* sync;              // per-level arrival counters (monotonic) + level records, see TP_SYNC_WORDS
-    unsigned int barrierBase[LSD_LEVELS];   // arrivals counted on each level's counter by earlier launches (never reset)
+    float* partials;                 // [2][gridDim][TP_ROW]
+    unsigned int* sync;              // word 0: arrival counter of the grid barrier (monotonic, never reset)
+    unsigned int barrierBase[LSD_LEVELS];   // [0]: arrivals counted by earlier launches
     int debug;                       // 1: also write the per-CTA cycle table
     unsigned int launchSeq;          // value the kernel stores in TrackState::doneSeq when the result block is complete
     int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
+    int kmax;                        // candidate poses per pass (1 = no speculation; <= TP_KMAX)
     int doPrepare;                   // 1: the last thread also turns the result into the observe parameters of the same frame
     PrepareConsts prep;              //    (Frame::prepareForStereoWith + head of DepthMap::updateKeyframe), no host round trip
     ObserveParams* obsOut;
@@ -81,9 +85,10 @@ struct TrackState {
     int diverged;
     int numCalcResidualCalls[LSD_LEVELS];
     int numCalcWarpUpdateCalls[LSD_LEVELS];
-    int evalsAtLevel[LSD_LEVELS];    // evaluations per level (advances the per-level barrier bases on the host)
+    int evalsAtLevel[LSD_LEVELS];    // passes per level
     float pointsAtLevel[LSD_LEVELS]; // numData[level]: valid points of the keyframe on each tracked level (CH_REFNUM)
-    int totalEvals;
+    int posesEvaluated;              // poses evaluated including the speculative ones (>= sum of numCalcResidualCalls)
+    int totalEvals;                  // passes (= grid barriers) of this launch
     volatile unsigned int doneSeq;   // written last (after a system-wide fence): the host polls it instead of a stream sync
     long long cyc[6];                // block-0 cycle breakdown: points, CTA reduce, barrier, combine, serial LM, total
     long long cycBlk[TP_MAXGRID_DBG][6];   // the same per CTA (debug)
@@ -121,60 +126,45 @@ __device__ __forceinline__ void tmaLoad2D(void* dst, const CUtensorMap* map, int
                  ::"r"(smemU32(dst)), "l"(map), "r"(x), "r"(y), "r"(smemU32(bar)) : "memory");
 }
 
-__device__ __forceinline__ unsigned int ldAcquire(const unsigned int* p)
-{
-    unsigned int v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void stRelease(unsigned int* p, unsigned int v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
-// Barrier over the CTAs that evaluate one level.  Arrivals are counted on the level's own counter (monotonic: epoch e
-// of this launch completes at base + e * G arrivals, the counter is never reset): release-add, then acquire-poll of the
-// counter itself.  Thread 0 carries the release / acquire for its CTA (cumulative over the __syncthreads on both sides).
-// Measured alternatives (round 1, B200): a separate release flag written by the last arriver (+1 800 cycles), fire-and-
-// forget red.release + poll (no gain), tagged-row polling without a counter (148 x 148 polling loads saturate L2, +35 %).
-__device__ __forceinline__ void levelBarrier(unsigned int* counter, unsigned int target)
+// Grid-wide barrier.  Arrivals are counted on one word (monotonic: epoch e completes at base + e * gridDim arrivals, the
+// counter is never reset): release-add, then polling of the counter itself; thread 0 carries the release / acquire for its
+// CTA (cumulative over the __syncthreads on both sides).  Measured alternatives (B200): a separate release flag written by
+// the last arriver (+1 800 cycles), red.release + poll (no gain), tagged-row polling without a counter (148 x 148 polling
+// loads saturate L2, +35 %), barriers over the few CTAs a small level needs (the ~5 dependent L2 round trips stay; no gain).
+__device__ __forceinline__ void gridBarrier(unsigned int* counter, unsigned int target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int v;
         asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(counter) : "memory");
         if (v != target - 1u) {
-            // poll with relaxed loads (served by L2, no cache maintenance per probe), ONE acquire fence once the epoch is complete
             do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
             } while ((int)(v - target) < 0);
+        } else {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
         }
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
 
 enum { ACT_CONTINUE = 0, ACT_LEVEL_DONE = 1, ACT_DIVERGED = 2 };
-enum { CHOICE_NONE = 0, CHOICE_ACCEPT = 1, CHOICE_REJECT = 2 };
 
-// next pose proposed by one of the two speculative lanes (see lmStep)
-struct Proposal {
+// one candidate pose of a chain
+struct Cand {
+    lsd::SE3<float> T;
     float inc[6];
-    lsd::SE3<float> cand;
-    float R[9];
-    float lambda;
+    float lambda, incSq;
 };
 
 struct LMShared {
-    float sums[EV_NCH];
-    EvalPose pose;                   // pose being evaluated
+    float sums[EV_NCHX];             // [0, EV_NCH): candidate 0; [EV_NCH, EV_NCHX): extension block of the other candidates
+    EvalPose pose[TP_KMAX];          // poses of the next pass
+    int nPose;                       // how many of them
     int action;
-    int lvl;                         // level of the next evaluation
-    unsigned int epochAll;
-    // decision of thread 0 about the evaluation just summed (phase 1 of lmStep; applied in phase 2)
-    int dDiverged, dAccept, dInit, dConverged, dLeave, dChoice;
-    float dError, dA, dB;
-    Proposal propA, propR;
+    int lvl;                         // level of the next pass
+    Cand cand[TP_KMAX];
 };
 
 __device__ __forceinline__ void setEvalPose(EvalPose& P, const lsd::SE3<float>& T, float a, float b)
@@ -216,7 +206,9 @@ template <int K> __device__ __forceinline__ int warpReduceChannel(int lane)
     return c;
 }
 
-// all EV_NCH (= 32 + 8) channels of a thread's accumulator -> per-warp totals in sm[warp][*] (39 shuffles)
+
+// all channels of a thread's accumulators -> per-warp totals in smRow: EV_NCH (= 32 + 8; 39 shuffles) and, when the pass
+// carries more than one candidate, the 16 extension channels (16 more)
 __device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* smRow)
 {
     float a32[32], a8[8];
@@ -229,6 +221,11 @@ __device__ __forceinline__ void warpReduceAcc(PointAcc& acc, int lane, float* sm
     smRow[lane] = a32[0];
     if ((lane & 3) == 0) smRow[32 + warpReduceChannel<8>(lane)] = a8[0];
 }
+__device__ __forceinline__ void warpReduceExt(float (&x)[EV_NX], int lane, float* smRow)
+{
+    warpReduceMulti<EV_NX>(x, lane);
+    if ((lane & 1) == 0) smRow[EV_NCH + warpReduceChannel<EV_NX>(lane)] = x[0];
+}
 
 struct WarpWindow {
     const float4* win;               // this warp's TRK_WIN_H x TRK_WIN_W window in shared memory
@@ -238,32 +235,39 @@ struct WarpWindow {
     int ox, oy;                      // window origin in level pixels
     bool valid;
     unsigned int hits;               // low 16 bits: taps served from the window, high 16: taps through L1/L2
-    // the thread's first pixel of the current level, reconstructed once (see levelEvaluate)
+    // the thread's first pixel of the current level, reconstructed once (see gridEvaluate)
     int pcLvl;
     bool pcIsPoint;
     float pcx, pcy, pcz, pcVar, pcColor;
+    // level-1 good flags of the LAST candidate of the most recent pass, one bit per chunk slot of this thread (the mask itself
+    // always holds candidate 0's flags); committed at the end if that candidate was the last pose the reference evaluates
+    unsigned int lastBits, pointBits;
 };
 
-// One evaluation of level `lvl` by the CTAs 0..G-1 of that level: points, CTA reduction, one row per CTA through L2 behind
-// ONE barrier over the G CTAs, then every CTA sums the G rows in rank order.  On return sh.sums holds the EV_NCH totals,
-// bit-identical in every CTA.
-__device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCH],
-                                              unsigned int& epochAll, unsigned int& epochLvl, long long* cyc, WarpWindow& W)
+// One pass: nPose candidate poses over this CTA's chunks of level `lvl`, CTA reduction, one row per CTA through L2 behind ONE
+// grid barrier, then every CTA sums the rows in block order.  On return sh.sums holds the totals, bit-identical in every CTA.
+__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCHX], double (*comb)[TP_ROW],
+                                             unsigned int& epoch, long long* cyc, WarpWindow& W)
 {
     long long t0 = clock64();
     const TrackLevelParams& L = p.lvl[lvl];
-    const EvalPose P = sh.pose;
+    const int K = sh.nPose;
+    const EvalPose P = sh.pose[0];
     PointAcc acc;
+    float ext[EV_NX];
 #pragma unroll
     for (int c = 0; c < EV_NCH; c++) acc.v[c] = 0.f;
-    const int w = L.w, h = L.h, iw = L.iw, nInt = L.nInt, G = L.G;
+#pragma unroll
+    for (int c = 0; c < EV_NX; c++) ext[c] = 0.f;
+    const int w = L.w, h = L.h, iw = L.iw, nInt = L.nInt, G = (int)gridDim.x;
     const float4* fg = L.frameGrad;
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // chunks of this CTA: c = blockIdx.x + G * k, k = 0 .. nMine-1; warp `warp` takes k = warp, warp + 16, ...
     const int nMine = ((int)blockIdx.x < L.nChunks) ? (L.nChunks - (int)blockIdx.x + G - 1) / G : 0;
-    const int activeWarps = nMine < TP_WARPS ? nMine : TP_WARPS;
-    for (int k = warp; k < nMine; k += TP_WARPS) {
+    if (mask) { W.lastBits = 0u; W.pointBits = 0u; }
+    int slot = 0;
+    for (int k = warp; k < nMine; k += TP_WARPS, slot++) {
         const int j = (((int)blockIdx.x + G * k) << 5) + lane;        // interior pixel number
         const bool firstChunk = (k == warp);
         bool isPoint = false;
@@ -274,9 +278,9 @@ __device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMS
             i = (j - yy * iw + 1) + (yy + 1) * w;                      // x = 1 + j % iw, y = 1 + j / iw
         }
         if (firstChunk && W.pcLvl == lvl) {
-            // the thread's first pixel of a level never changes between the evaluations of that level: keep the
+            // the thread's first pixel of a level never changes between the passes of that level: keep the
             // reconstructed point in registers instead of re-reading the keyframe planes (an L2 round trip at the head
-            // of every evaluation's dependency chain)
+            // of every pass's dependency chain)
             isPoint = W.pcIsPoint; px = W.pcx; py = W.pcy; pz = W.pcz; var = W.pcVar; color = W.pcColor;
         } else {
             if (j < nInt) {
@@ -297,7 +301,7 @@ __device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMS
         }
         // First chunk of this warp on a new level: stage the part of the frame's gradient level that the chunk
         // warps into (centred on the chunk under the level's initial pose) in shared memory with ONE TMA box copy.
-        // All later evaluations of the level tap the window; taps that leave it fall back to L1/L2.
+        // All later passes of the level tap the window; taps that leave it fall back to L1/L2.
         if (p.useTma && firstChunk && W.lvl != lvl) {                  // warp-uniform condition
             float u = 0.f, v = 0.f;
             bool ok = false;
@@ -352,48 +356,63 @@ __device__ __forceinline__ void levelEvaluate(const TrackParams& p, int lvl, LMS
                     interp43(fg, u, v, w, o0, o1, o2);
                 }
             };
-            int good = evalPoint(px, py, pz, color, var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
-            if (mask) mask[i] = (uint8_t)good;
+            const int good = evalPoint(px, py, pz, color, var, P, p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, acc);
+            if (K > 1) {                                               // block-uniform
+                if (K > 2) evalPointLight<false>(px, py, pz, color, var, sh.pose[1], p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, ext);
+                const int goodL = evalPointLight<true>(px, py, pz, color, var, sh.pose[K - 1], p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, ext);
+                if (mask) W.lastBits |= (unsigned int)goodL << slot;
+            }
+            if (mask) { mask[i] = (uint8_t)good; W.pointBits |= 1u << slot; }
         }
     }
     __syncthreads();
     long long t1 = clock64();
-    // warps without a chunk hold zeros: they skip the 39 shuffles, and the cross-warp sum runs over the active warps only
-    if (warp < activeWarps) warpReduceAcc(acc, lane, sm[warp]);
+    warpReduceAcc(acc, lane, sm[warp]);
+    if (K > 1) warpReduceExt(ext, lane, sm[warp]);
     __syncthreads();
+    const int nch = K > 1 ? EV_NCHX : EV_NCH;
     float ctaSum = 0.f;
-    if (threadIdx.x < EV_NCH) {
-        for (int wi = 0; wi < activeWarps; wi++) ctaSum += sm[wi][threadIdx.x];
+    if (threadIdx.x < nch) {
+#pragma unroll
+        for (int wi = 0; wi < TP_WARPS; wi++) ctaSum += sm[wi][threadIdx.x];
     }
-    // ---- exchange: one partial row per CTA ([parity][channel][cta], written through to L2), ONE barrier over the G CTAs
-    // of the level, then every CTA combines the G rows in a fixed order
-    const unsigned int parity = epochAll & 1u;
-    float* part = p.partials + (size_t)parity * EV_NCH * gridDim.x;
-    if (threadIdx.x < EV_NCH) __stcg(part + (size_t)threadIdx.x * gridDim.x + blockIdx.x, ctaSum);
-    epochAll++;
-    epochLvl++;
+    // ---- exchange: ONE 256-byte row per CTA ([parity][cta][64 floats], written through to L2 as one coalesced store),
+    // ONE grid barrier, then every CTA combines all rows in a fixed order.  (Round 1 laid the buffer out [channel][cta]:
+    // 40 four-byte writes per CTA into lines shared with 31 other CTAs -- 5 920 partial-sector writes per pass behind the
+    // release of the barrier, and the combine's loads then waited ~5 000 cycles on those lines: 25 % of the kernel, ncu.)
+    const unsigned int parity = epoch & 1u;
+    float* part = p.partials + (size_t)parity * TP_ROW * gridDim.x;
+    if (threadIdx.x < nch) __stcg(part + (size_t)blockIdx.x * TP_ROW + threadIdx.x, ctaSum);
+    epoch++;
     long long t2 = clock64();
-    levelBarrier(p.sync + 32 * lvl, p.barrierBase[lvl] + epochLvl * (unsigned int)G);
+    gridBarrier(p.sync, p.barrierBase[0] + epoch * gridDim.x);
     long long t3 = clock64();
-    // 40 channels x 8 lanes: lane (c, q) adds rows q, q+8, ... of channel c in double (fixed order), three shuffles finish
+    // warp wi adds rows wi, wi+16, ... (<= 10) in row order, lane = channel (and channel 32 + lane): every load is one full
+    // line, all of them in flight before the first add; the 16 per-warp partial sums are then added in warp order.  Double
+    // throughout: every CTA executes the same additions in the same order, so the totals are bit-identical everywhere.
     {
         const int nb = (int)gridDim.x;
-        const int c = threadIdx.x >> 3, q = threadIdx.x & 7;
-        if (c < EV_NCH) {                                            // warps 0..9, whole warps
-            const float* row = part + (size_t)c * nb;
-            double a0 = 0.0, a1 = 0.0;
-            int bb = q;
-            for (; bb + 8 < G; bb += 16) {                           // two independent chains keep two loads in flight
-                const float v0 = __ldcg(row + bb), v1 = __ldcg(row + bb + 8);
-                a0 += (double)v0; a1 += (double)v1;
-            }
-            if (bb < G) a0 += (double)__ldcg(row + bb);
-            double acc = a0 + a1;
-            acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            if (q == 0) sh.sums[c] = (float)acc;
+        const bool hi = (32 + lane) < nch;
+        float v0[TP_MAXGRID / TP_WARPS], v1[TP_MAXGRID / TP_WARPS];
+#pragma unroll
+        for (int r = 0; r < TP_MAXGRID / TP_WARPS; r++) {
+            const int row = warp + r * TP_WARPS;
+            const bool ok = row < nb;
+            v0[r] = ok ? __ldcg(part + (size_t)row * TP_ROW + lane) : 0.f;
+            v1[r] = (ok && hi) ? __ldcg(part + (size_t)row * TP_ROW + 32 + lane) : 0.f;
         }
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < TP_MAXGRID / TP_WARPS; r++) { a0 += (double)v0[r]; a1 += (double)v1[r]; }
+        comb[warp][lane] = a0;
+        comb[warp][32 + lane] = a1;
+    }
+    __syncthreads();
+    if (threadIdx.x < nch) {
+        double t = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < TP_WARPS; wi++) t += comb[wi][threadIdx.x];
+        sh.sums[threadIdx.x] = (float)t;
     }
     __syncthreads();
     long long t4 = clock64();
@@ -489,7 +508,9 @@ __device__ __forceinline__ lsd::SE3<float> se3ExpMulFast(const float* a, const l
     return r;
 }
 
-// LM state of SE3Tracker::trackFrame; lives in shared memory (keeps it out of the register budget of the point loop)
+
+// LM state of SE3Tracker::trackFrame; lives in shared memory, touched by warp 0 only (keeps it out of the
+// register budget of the point loop)
 struct LMState {
     lsd::SE3<float> refToFrame, cand;
     float affine_a, affine_b, lastErr, last_residual, LM_lambda;
@@ -498,9 +519,13 @@ struct LMState {
     int nRes[LSD_LEVELS], nUpd[LSD_LEVELS], nEval[LSD_LEVELS];
     float nPts[LSD_LEVELS];
     int lvl, iteration, phase, incTry, diverged;
-    long long dbg[4];                // thread-0 cycles: decision, apply, (proposal lanes: accept, reject)
+    int chainBase;                   // lm.incTry when the chain of the pass in flight was built
+    int statsFrom;                   // where the statistics of the last evaluated pose are: 0 = main block, 1 = extension block
+    int commitLast;                  // 1: the good-mask of the last evaluated pose is in WarpWindow::lastBits, not yet in the mask
+    int posesEvaluated;
+    long long dbg[4];                // warp-0 cycles: decisions, chain building
 };
-enum { PH_INIT = 0, PH_TRY = 1 };
+enum { PH_INIT = 0, PH_TRY = 1, PH_REEVAL = 2 };
 
 // affine lighting estimate of the last evaluation, SE3Tracker.cpp:1023-1024
 __device__ __forceinline__ void affineFromSums(const float* s, float& a, float& b)
@@ -524,9 +549,10 @@ __device__ __noinline__ void ldlt6SolvePivotedFromSums(const float* lsq, float l
     lsd::ldlt6Solve(A, b, incOut);
 }
 
+
 // Solve the damped system `lsq` (RAW sums: LGS6::finish divides A and b by num_constraints, LGSX.h:319-325, which cancels
 // in A^-1 b because the damping is multiplicative) and form exp(inc) * base with its rotation matrix (SE3Tracker.cpp:356-363).
-__device__ __forceinline__ void proposePose(const float* lsq, float lambda, const lsd::SE3<float>& base, Proposal& P)
+__device__ __forceinline__ void solveCandidate(const float* lsq, float lambda, const lsd::SE3<float>& base, Cand& P, EvalPose& E, float affA, float affB)
 {
     float A[36], b[6], inc[6];
     {
@@ -550,13 +576,16 @@ __device__ __forceinline__ void proposePose(const float* lsq, float lambda, cons
 #pragma unroll
         for (int i = 0; i < 6; i++) inc[i] = P.inc[i];
     }
-    const lsd::SE3<float> base_ = base;
-    const lsd::SE3<float> c = se3ExpMulFast(inc, base_);
+    const lsd::SE3<float> c = se3ExpMulFast(inc, base);
+    float dot = 0;
 #pragma unroll
-    for (int i = 0; i < 6; i++) P.inc[i] = inc[i];
-    P.cand = c;
-    lsd::quatToMatrix(c.q, P.R);
+    for (int i = 0; i < 6; i++) { P.inc[i] = inc[i]; dot += inc[i] * inc[i]; }        // inc.dot(inc), :432
+    P.incSq = dot;
+    P.T = c;
     P.lambda = lambda;
+    lsd::quatToMatrix(c.q, E.R);
+    E.t[0] = c.t[0]; E.t[1] = c.t[1]; E.t[2] = c.t[2];
+    E.a = affA; E.b = affB;
 }
 
 // std::pow(lambdaFailFac, incTry) of SE3Tracker.cpp:445 (float, int -> double pow): repeated multiplication in double,
@@ -568,163 +597,146 @@ __device__ __forceinline__ double ipowd(double f, int n)
     return r;
 }
 
-// level record of `lvl` (levels 0..4; record 0 is unused by trackFrame whose last level is 1)
-__device__ __forceinline__ LevelRecord* levelRecord(const TrackParams& p, int lvl)
+// Build the chain of the iteration that starts (or continues) now: lanes 0..kmax-1 of warp 0 solve, in parallel, for
+// lambda_1 = lm.LM_lambda and its successors under rejection (lambda == 0 ? 0.2 : lambda * failFac^incTry, :443-446).
+// The chain ends with the first candidate whose step is too small (its rejection ends the level, :432-441).
+__device__ __forceinline__ void buildChain(const TrackParams& p, LMState& lm, LMShared& sh, int lane)
 {
-    return reinterpret_cast<LevelRecord*>(p.sync + 256) + lvl;
-}
-__device__ __forceinline__ void publishLevel(const TrackParams& p, int lvl, const LMState& lm, int action, unsigned int epochAll)
-{
-    LevelRecord* r = levelRecord(p, lvl);
-    for (int i = 0; i < 4; i++) r->q[i] = lm.refToFrame.q[i];
-    for (int i = 0; i < 3; i++) r->t[i] = lm.refToFrame.t[i];
-    r->a = lm.affine_a; r->b = lm.affine_b;
-    r->action = action;
-    r->epochAll = epochAll;
-    stRelease(&r->tag, p.launchSeq);
+    const int lvl = lm.lvl;
+    if (lane < p.kmax) {
+        float lam = lm.LM_lambda;
+        for (int u = 1; u <= lane; u++) {
+            if (lam == 0) lam = 0.2;
+            else lam *= ipowd((double)p.st.lambdaFailFac, lm.incTry + u);
+        }
+        solveCandidate(lm.lsq, lam, lm.refToFrame, sh.cand[lane], sh.pose[lane], lm.affine_a, lm.affine_b);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int K = 1;
+        while (K < p.kmax && (sh.cand[K - 1].incSq > p.st.stepSizeMin[lvl])) K++;
+        sh.nPose = K;
+        lm.chainBase = lm.incTry;
+        lm.phase = PH_TRY;
+    }
 }
 
-// The step between two evaluations: the accept / reject / converge decisions of SE3Tracker.cpp:324-446 and the next pose.
-// THREE lanes work at the same time on the sums of the evaluation that just finished:
-//   thread  0  takes the decision (phase 1, read-only on the LM state),
-//   thread 32  solves for the next pose AS IF the evaluation is accepted  (new normal equations, lambda of :417-420 / :341),
-//   thread 64  solves for the next pose AS IF it is rejected               (old normal equations, lambda of :443-446),
-// then thread 0 applies the decision and adopts the proposal that matches it (phase 2).  The two 6x6 solves + exp(inc)*T
-// (~1 300 cycles each, one dependent chain) leave the critical path of the decision instead of following it.
-__device__ __forceinline__ void lmStep(const TrackParams& p, LMState& lm, LMShared& sh, unsigned int epochAll)
+__device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, LMShared& sh)
 {
-    const float* s = sh.sums;
-    const int lvl = lm.lvl;
-    const int tid = threadIdx.x;
-    if (tid == 0) {                                                          // ---- phase 1: decide
+    lm.lvl--;
+    if (lm.lvl < p.minLevel) { sh.action = ACT_LEVEL_DONE; return; }                // all levels done
+    lm.phase = PH_INIT;
+    setEvalPose(sh.pose[0], lm.refToFrame, lm.affine_a, lm.affine_b);
+    sh.nPose = 1;
+    sh.lvl = lm.lvl;
+}
+
+// Warp 0 after every pass: the decisions of SE3Tracker.cpp:324-446, replayed candidate by candidate in the reference's order.
+// Lane 0 decides; all lanes of the warp take part in buildChain.
+__device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMShared& sh, int lane)
+{
+    int build = 0;                       // 1: start / continue an iteration (lane 0 decides, broadcast below)
+    if (lane == 0) {
         const long long ta = clock64();
-        const float warped = s[CH_GOOD] + s[CH_BAD];
-        // MIN_GOODPERALL_PIXEL_ABSMIN is the float literal 0.01f (util/settings.h:170): the reference's threshold is a float product
-        sh.dDiverged = (warped < 0.01f * (p.W >> lvl) * (p.H >> lvl)) ? 1 : 0;   // :324-329 / :369-374
-        const float error = s[CH_SUMRESW] / warped;                              // calcWeightsAndResidual, :789
-        const bool init = lm.phase == PH_INIT;
-        const bool accept = init || error < lm.lastErr;                          // :381
-        bool converged = false, leave;
-        float a = lm.affine_a, b = lm.affine_b;
-        if (accept) {
-            if (p.useAffine) affineFromSums(s, a, b);                            // :331-335 / :385-389
-            converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);    // :404
-            const int iteration = init ? 0 : (converged ? lm.iteration : lm.iteration + 1);
-            leave = converged || !(iteration < p.st.maxItsPerLvl[lvl]);          // :343, :411
-        } else {                                                                 // :424-447 reject
-            float dot = 0;
+        const float* s = sh.sums;
+        const int lvl = lm.lvl;
+        const int K = sh.nPose;
+        const float divTh = 0.01f * (p.W >> lvl) * (p.H >> lvl);     // MIN_GOODPERALL_PIXEL_ABSMIN is the float literal 0.01f (util/settings.h:170)
+        sh.action = ACT_CONTINUE;
+        lm.posesEvaluated += K;
+        bool leave = false;
+        // `accepted`: candidate 0 accepted with its normal equations at hand (init, re-evaluation or a first try)
+        auto acceptActions = [&](bool init, float error) {
+            if (!init) lm.refToFrame = lm.cand;
+            if (p.useAffine) affineFromSums(s, lm.affine_a, lm.affine_b);               // :331-335 / :385-389
+            const bool converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);   // :404
+            if (!init) lm.last_residual = error;                                         // :414
+            lm.lastErr = error;                                                          // :336 / :414
 #pragma unroll
-            for (int i = 0; i < 6; i++) dot += lm.inc[i] * lm.inc[i];
-            leave = !(dot > p.st.stepSizeMin[lvl]);                              // :432-441
-        }
-        sh.dError = error; sh.dInit = init; sh.dAccept = accept; sh.dConverged = converged; sh.dLeave = leave;
-        sh.dA = a; sh.dB = b;
-        sh.dChoice = (sh.dDiverged || leave) ? CHOICE_NONE : (accept ? CHOICE_ACCEPT : CHOICE_REJECT);
-        lm.dbg[0] += clock64() - ta;
-    } else if (tid == 32) {                                                      // ---- speculative: accepted
-        const long long ta = clock64();
-        const bool init = lm.phase == PH_INIT;
-        const float lam = init ? p.st.lambdaInitial[lvl]                         // :341
-                               : ((lm.LM_lambda <= 0.2) ? 0.f : lm.LM_lambda * p.st.lambdaSuccessFac);   // :417-420
-        proposePose(s, lam, init ? lm.refToFrame : lm.cand, sh.propA);           // the accepted pose becomes the base
-        lm.dbg[2] += clock64() - ta;
-    } else if (tid == 64) {                                                      // ---- speculative: rejected
-        if (lm.phase == PH_TRY) {
-            const long long ta = clock64();
-            float lam = lm.LM_lambda;
-            if (lam == 0) lam = 0.2;                                             // :443-446
-            else lam *= ipowd((double)p.st.lambdaFailFac, lm.incTry);
-            proposePose(lm.lsq, lam, lm.refToFrame, sh.propR);
-            lm.dbg[3] += clock64() - ta;
-        }
-    }
-    __syncthreads();
-    if (tid < 32) {                                                              // ---- phase 2: apply (warp 0; lane-parallel copies)
-        const long long ta = clock64();
-        const bool div = sh.dDiverged != 0, accept = sh.dAccept != 0, init = sh.dInit != 0, leave = sh.dLeave != 0;
-        const Proposal& P = accept ? sh.propA : sh.propR;
-        // every read of the state the scalar updates below overwrite happens BEFORE the __syncwarp
-        float lsqNew = 0.f, incNew = 0.f, rNew = 0.f, candNew = 0.f;
-        if (tid < 27) lsqNew = s[tid];
-        if (tid < 6) incNew = P.inc[tid];
-        if (tid < 9) rNew = P.R[tid];
-        if (tid < 7) candNew = tid < 4 ? P.cand.q[tid] : P.cand.t[tid - 4];
-        float acceptedPose = 0.f;
-        if (tid < 7) acceptedPose = tid < 4 ? lm.cand.q[tid] : lm.cand.t[tid - 4];
-        __syncwarp();
-        if (!div) {
-            if (accept) {
-                if (!init && tid < 7) { if (tid < 4) lm.refToFrame.q[tid] = acceptedPose; else lm.refToFrame.t[tid - 4] = acceptedPose; }
-                if (tid < 27) lm.lsq[tid] = lsqNew;                              // buffers now belong to this pose
+            for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                               // buffers now belong to this pose
+            if (init) { lm.LM_lambda = p.st.lambdaInitial[lvl]; lm.iteration = 0; }      // :341
+            else {
+                if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                               // :417-420
+                else lm.LM_lambda *= p.st.lambdaSuccessFac;
+                if (!converged) lm.iteration++;
             }
-            if (!leave) {
-                if (tid < 6) lm.inc[tid] = incNew;
-                if (tid < 7) { if (tid < 4) lm.cand.q[tid] = candNew; else lm.cand.t[tid - 4] = candNew; }
-                if (tid < 9) sh.pose.R[tid] = rNew;
-                if (tid >= 4 && tid < 7) sh.pose.t[tid - 4] = candNew;
-            }
-        }
-        __syncwarp();
-        if (tid == 0) {
-            sh.action = ACT_CONTINUE;
-            bool nextLevel = false;
-            if (div) {
-                lm.diverged = 1;
-                sh.action = ACT_DIVERGED;
+            leave = converged || !(lm.iteration < p.st.maxItsPerLvl[lvl]);               // :343, :411
+            if (!leave) { lm.nUpd[lvl]++; lm.incTry = 0; build = 1; }                    // calculateWarpUpdate(ls), :346
+            lm.statsFrom = 0; lm.commitLast = 0;
+        };
+        if (lm.phase == PH_INIT || lm.phase == PH_REEVAL) {
+            const float warped = s[CH_GOOD] + s[CH_BAD];
+            if (lm.phase == PH_INIT && warped < divTh) {                                 // :324-329
+                lm.diverged = 1; sh.action = ACT_DIVERGED; lm.statsFrom = 0; lm.commitLast = 0;
             } else {
+                const float error = s[CH_SUMRESW] / warped;                              // calcWeightsAndResidual, :789
+                if (lm.phase == PH_INIT) lm.nRes[lvl]++;                                 // a re-evaluated pose was counted when it was accepted
+                acceptActions(lm.phase == PH_INIT, error);
+            }
+        } else {
+            for (int k = 0; k < K; k++) {
+                // sums of candidate k: main block (k == 0), last-candidate block (k == K-1) or the middle block
+                const bool isLast = (k > 0 && k == K - 1);
+                const float good = k == 0 ? s[CH_GOOD] : (isLast ? s[EV_NCH + XL_GOOD] : s[EV_NCH + XM_GOOD]);
+                const float bad = k == 0 ? s[CH_BAD] : (isLast ? s[EV_NCH + XL_BAD] : s[EV_NCH + XM_BAD]);
+                const float srw = k == 0 ? s[CH_SUMRESW] : (isLast ? s[EV_NCH + XL_SUMRESW] : s[EV_NCH + XM_SUMRESW]);
+                const float warped = good + bad;
+                lm.statsFrom = isLast ? 1 : 0;
+                lm.commitLast = (isLast && lvl == SE3TRACKING_MIN_LEVEL) ? 1 : 0;     // only level 1 has a mask
+                lm.cand = sh.cand[k].T;
+#pragma unroll
+                for (int i = 0; i < 6; i++) lm.inc[i] = sh.cand[k].inc[i];
+                lm.LM_lambda = sh.cand[k].lambda;
+                lm.incTry = lm.chainBase + k + 1;                                         // incTry++ after the solve, :361
+                if (warped < divTh) {                                                    // :369-374
+                    lm.diverged = 1; sh.action = ACT_DIVERGED;
+                    break;
+                }
+                const float error = srw / warped;
                 lm.nRes[lvl]++;
-                if (accept) {
-                    lm.affine_a = sh.dA; lm.affine_b = sh.dB;
-                    if (!init) lm.last_residual = sh.dError;                     // :414
-                    lm.lastErr = sh.dError;                                      // :336 / :414
-                    if (init) lm.iteration = 0;
-                    else if (!sh.dConverged) lm.iteration++;
-                    if (!leave) { lm.nUpd[lvl]++; lm.incTry = 0; }               // calculateWarpUpdate(ls), :346
+                if (error < lm.lastErr) {                                                // :381 accepted
+                    if (k == 0) acceptActions(false, error);
+                    else {
+                        // a speculative candidate is the one the reference accepts: its normal equations and statistics were
+                        // not accumulated -> evaluate it once more with all channels (same sums, bit for bit), then go on
+                        lm.phase = PH_REEVAL;
+                        setEvalPose(sh.pose[0], lm.cand, lm.affine_a, lm.affine_b);
+                        sh.nPose = 1;
+                    }
+                    break;
                 }
-                if (leave) nextLevel = true;
-                else {
-                    lm.LM_lambda = P.lambda;
-                    lm.incTry++;
-                    sh.pose.a = lm.affine_a; sh.pose.b = lm.affine_b;
-                    lm.phase = PH_TRY;
-                }
+                // rejected, :424-447
+                if (!(sh.cand[k].incSq > p.st.stepSizeMin[lvl])) { leave = true; break; }        // :432-441
+                if (lm.LM_lambda == 0) lm.LM_lambda = 0.2;                               // :443-446
+                else lm.LM_lambda *= ipowd((double)p.st.lambdaFailFac, lm.incTry);
+                if (k == K - 1) build = 1;                                               // chain used up: continue it
             }
-            if (nextLevel) {
-                lm.lvl--;
-                if (lm.lvl < p.minLevel) sh.action = ACT_LEVEL_DONE;             // all levels done
-                else {
-                    lm.phase = PH_INIT;
-                    setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
-                    sh.lvl = lm.lvl;
-                    if (blockIdx.x == 0) publishLevel(p, lm.lvl, lm, ACT_CONTINUE, epochAll);    // for the CTAs that join here
-                }
-            }
-            if (sh.action != ACT_CONTINUE && blockIdx.x == 0)                    // tracking ends: release every CTA still
-                for (int l = lvl - 1; l >= p.minLevel; l--) publishLevel(p, l, lm, sh.action, epochAll);   // waiting to join
-            lm.dbg[1] += clock64() - ta;
         }
+        if (leave) { lmNextLevel(p, lm, sh); build = 0; }
+        if (sh.action != ACT_CONTINUE) build = 0;
+        lm.dbg[0] += clock64() - ta;
     }
-    __syncthreads();
+    build = __shfl_sync(0xffffffffu, build, 0);
+    if (build) {
+        const long long tb = clock64();
+        __syncwarp();
+        buildChain(p, lm, sh, lane);
+        if (lane == 0) lm.dbg[1] += clock64() - tb;
+    }
 }
 
 __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid_constant__ TrackParams p, TrackState* __restrict__ out, TrackState* __restrict__ outDev)
 {
-    __shared__ alignas(LMShared) unsigned char shStorage[sizeof(LMShared)];   // raw storage: Proposal holds a type with a constructor
+    __shared__ alignas(LMShared) unsigned char shStorage[sizeof(LMShared)];   // raw storage: Cand holds a type with a constructor
     LMShared& sh = *reinterpret_cast<LMShared*>(shStorage);
     __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
     LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
-    __shared__ float sm[TP_WARPS][EV_NCH];
-    static_assert(EV_NCH == 40, "warpReduceAcc is written for 32 + 8 channels");
+    __shared__ float sm[TP_WARPS][EV_NCHX];
+    __shared__ double comb[TP_WARPS][TP_ROW];                      // per-warp partial sums of the combine
+    static_assert(EV_NCH == 40 && EV_NX == 16, "warpReduceAcc / warpReduceExt are written for 32 + 8 (+ 16) channels");
     extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
     __shared__ __align__(8) uint64_t winBar[TP_WARPS];
-
-    // the level at which this CTA joins the computation: the coarsest level it has chunks of (G is non-increasing in l)
-    const int topLvl = SE3TRACKING_MAX_LEVEL - 1;
-    int joinLvl = -1;
-    for (int l = topLvl; l >= p.minLevel; l--)
-        if ((int)blockIdx.x < p.lvl[l].G) { joinLvl = l; break; }
-    if (joinLvl < 0) return;                                       // small images: this CTA never has work
-
+    unsigned int epoch = 0;
     long long cyc[6] = { 0, 0, 0, 0, 0, 0 };
     const long long tStart = clock64();
     WarpWindow W;
@@ -732,72 +744,79 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     W.bar = &winBar[threadIdx.x >> 5];
     W.parity = 0u; W.lvl = -1; W.ox = 0; W.oy = 0; W.valid = false; W.hits = 0u; W.pcLvl = -1; W.pcIsPoint = false;
     W.pcx = W.pcy = W.pcz = W.pcVar = W.pcColor = 0.f;
+    W.lastBits = 0u; W.pointBits = 0u;
     if (p.useTma && (threadIdx.x & 31) == 0) {
         mbarInit(W.bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
-    // fresh refPixelWasGood mask: all true (Frame.h:433).  Written by the CTAs of the FIRST level only: their stores are
-    // released by that level's barriers, which every later level record -- and so every level-1 evaluation -- follows.
-    if (p.maskFresh && joinLvl == topLvl) {
+    // fresh refPixelWasGood mask: all true (Frame.h:433); ordered before the level-1 passes by the barriers
+    if (p.maskFresh) {
         uint32_t* m32 = reinterpret_cast<uint32_t*>(p.goodMask);
-        const int Gt = p.lvl[topLvl].G;
-        for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < p.maskBytes / 4; i += Gt * TP_THREADS) m32[i] = 0x01010101u;
+        for (int i = blockIdx.x * TP_THREADS + threadIdx.x; i < p.maskBytes / 4; i += gridDim.x * TP_THREADS) m32[i] = 0x01010101u;
     }
 
     if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = p.initRefToFrame[i];
+        for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
         for (int l = 0; l < LSD_LEVELS; l++) { lm.nRes[l] = 0; lm.nUpd[l] = 0; lm.nEval[l] = 0; lm.nPts[l] = 0.f; }
-        lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
+        lm.affine_a = 1.f; lm.affine_b = 0.f; lm.lastErr = 0.f; lm.last_residual = 0.f; lm.LM_lambda = 0.f;
         lm.diverged = 0; lm.incTry = 0; lm.iteration = 0; lm.dbg[0] = lm.dbg[1] = lm.dbg[2] = lm.dbg[3] = 0;
-        lm.phase = PH_INIT;
-        sh.action = ACT_CONTINUE;
-        if (joinLvl == topLvl) {
-            for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = p.initRefToFrame[i];
-            for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = p.initRefToFrame[4 + i];
-            lm.affine_a = 1.f; lm.affine_b = 0.f;
-            sh.epochAll = 0u;
-        } else {
-            // wait until CTA 0 has finished the coarser levels and published the state this level starts from
-            LevelRecord* r = levelRecord(p, joinLvl);
-            while (ldAcquire(&r->tag) != p.launchSeq) __nanosleep(64);
-            for (int i = 0; i < 4; i++) lm.refToFrame.q[i] = r->q[i];
-            for (int i = 0; i < 3; i++) lm.refToFrame.t[i] = r->t[i];
-            lm.affine_a = r->a; lm.affine_b = r->b;
-            sh.action = r->action;
-            sh.epochAll = r->epochAll;
-        }
-        lm.lvl = joinLvl;
-        sh.lvl = joinLvl;
-        setEvalPose(sh.pose, lm.refToFrame, lm.affine_a, lm.affine_b);
+        lm.chainBase = 0; lm.statsFrom = 0; lm.commitLast = 0; lm.posesEvaluated = 0;
+        lm.lvl = SE3TRACKING_MAX_LEVEL - 1; lm.phase = PH_INIT;
+        sh.lvl = lm.lvl; sh.action = ACT_CONTINUE; sh.nPose = 1;
+        setEvalPose(sh.pose[0], lm.refToFrame, lm.affine_a, lm.affine_b);
     }
     __syncthreads();
-    if (sh.action != ACT_CONTINUE) return;                          // tracking ended (diverged) before this CTA's level
-    unsigned int epochAll = sh.epochAll;
-    unsigned int epochLvl = 0u;
-    int curLvl = joinLvl;
 
     while (true) {
         const int lvl = sh.lvl;
-        if (lvl != curLvl) { curLvl = lvl; epochLvl = 0u; }
-        levelEvaluate(p, lvl, sh, sm, epochAll, epochLvl, cyc, W);
-        if (threadIdx.x == 0) { lm.nEval[lvl]++; lm.nPts[lvl] = sh.sums[CH_REFNUM]; }
-        lmStep(p, lm, sh, epochAll);
+        gridEvaluate(p, lvl, sh, sm, comb, epoch, cyc, W);
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) { lm.nEval[lvl]++; lm.nPts[lvl] = sh.sums[CH_REFNUM]; }
+            lmAdvance(p, lm, sh, threadIdx.x);
+        }
+        __syncthreads();
         if (sh.action != ACT_CONTINUE) break;
+    }
+
+    // The mask holds the flags of candidate 0 of the last level-1 pass; if the last pose the reference evaluates was the chain's
+    // last candidate instead, its flags (kept per thread) replace them now.  Same threads, same pixels: no synchronisation.
+    if (lm.commitLast && p.minLevel == SE3TRACKING_MIN_LEVEL) {
+        const TrackLevelParams& L = p.lvl[SE3TRACKING_MIN_LEVEL];
+        const int G = (int)gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int nMine = ((int)blockIdx.x < L.nChunks) ? (L.nChunks - (int)blockIdx.x + G - 1) / G : 0;
+        int slot = 0;
+        for (int k = warp; k < nMine; k += TP_WARPS, slot++) {
+            if (!((W.pointBits >> slot) & 1u)) continue;
+            const int j = (((int)blockIdx.x + G * k) << 5) + lane;
+            const int yy = j / L.iw;
+            p.goodMask[(j - yy * L.iw + 1) + (yy + 1) * L.w] = (uint8_t)((W.lastBits >> slot) & 1u);
+        }
     }
 
     if (p.debug) {
         atomicAdd(p.sync + TP_SYNC_WORDS - 3, W.hits & 0xffffu);
         atomicAdd(p.sync + TP_SYNC_WORDS - 2, W.hits >> 16);
     }
-    if (p.debug && threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG) {
+    if (p.debug && threadIdx.x == 0 && blockIdx.x < TP_MAXGRID_DBG - 1) {
         long long tot = clock64() - tStart;
         for (int i = 0; i < 4; i++) out->cycBlk[blockIdx.x][i] = cyc[i];
         out->cycBlk[blockIdx.x][5] = tot;
         out->cycBlk[blockIdx.x][4] = tot - cyc[0] - cyc[1] - cyc[2] - cyc[3];
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        // statistics of the LAST EVALUATED pose: main block, or the extension block's last candidate
+        float fin[EV_NCH];
+        for (int c = 0; c < EV_NCH; c++) fin[c] = sh.sums[c];
+        if (lm.statsFrom == 1) {
+            const float* x = sh.sums + EV_NCH;
+            fin[CH_SUMRESW] = x[XL_SUMRESW]; fin[CH_SUMRESU] = x[XL_SUMRESU]; fin[CH_SIGNED] = x[XL_SIGNED];
+            fin[CH_GOOD] = x[XL_GOOD]; fin[CH_BAD] = x[XL_BAD]; fin[CH_USAGE] = x[XL_USAGE];
+            fin[CH_SXX] = x[XL_SXX]; fin[CH_SYY] = x[XL_SYY]; fin[CH_SX] = x[XL_SX]; fin[CH_SY] = x[XL_SY]; fin[CH_SW] = x[XL_SW];
+        }
         lsdgpu_eval_result ev;
-        evalFinish(sh.sums, &ev);        // statistics of the LAST EVALUATED pose
+        evalFinish(fin, &ev);
         for (int i = 0; i < 4; i++) out->refToFrame[i] = lm.refToFrame.q[i];
         for (int i = 0; i < 3; i++) out->refToFrame[4 + i] = lm.refToFrame.t[i];
         out->pointUsage = ev.pointUsage; out->goodCount = ev.goodCount; out->badCount = ev.badCount;
@@ -808,7 +827,8 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
             out->numCalcResidualCalls[l] = lm.nRes[l]; out->numCalcWarpUpdateCalls[l] = lm.nUpd[l]; out->evalsAtLevel[l] = lm.nEval[l];
             out->pointsAtLevel[l] = lm.nPts[l];
         }
-        out->totalEvals = (int)epochAll;
+        out->posesEvaluated = lm.posesEvaluated;
+        out->totalEvals = (int)epoch;
         // device-resident copy of what the mapping kernels of the same frame need (no host round trip in between)
         for (int i = 0; i < 7; i++) outDev->refToFrame[i] = out->refToFrame[i];
         outDev->pointUsage = ev.pointUsage; outDev->goodCount = ev.goodCount; outDev->badCount = ev.badCount;
@@ -831,18 +851,10 @@ static void trackReadOptions(lsdgpu_ctx* ctx)
     ctx->optTrackTma = (e = getenv("LSDGPU_TRACK_TMA")) ? atoi(e) : 1;
     ctx->optTrackDebug = getenv("LSDGPU_TRACK_DEBUG") != nullptr;
     ctx->optSingleSync = (e = getenv("LSDGPU_SINGLE_SYNC")) ? atoi(e) : 0;
-    // warps of a CTA that take a chunk on levels 4 / 3 / 2 / 1 ("a,b,c,d"); fewer warps per CTA = more CTAs behind the
-    // level's barrier but a cheaper CTA reduction
-    ctx->optTrackWpc[0] = 0;
-    for (int l = 1; l < LSD_LEVELS; l++) ctx->optTrackWpc[l] = TP_WARPS;
-    if ((e = getenv("LSDGPU_TRACK_WPC"))) {
-        int v[4] = { TP_WARPS, TP_WARPS, TP_WARPS, TP_WARPS };
-        sscanf(e, "%d,%d,%d,%d", &v[0], &v[1], &v[2], &v[3]);
-        for (int k = 0; k < 4; k++) {
-            const int l = 4 - k;
-            ctx->optTrackWpc[l] = v[k] < 1 ? 1 : (v[k] > TP_WARPS ? TP_WARPS : v[k]);
-        }
-    }
+    // candidate poses per pass (1 = one pose per pass, the round-1 behaviour; default TP_KMAX)
+    ctx->optTrackKmax = (e = getenv("LSDGPU_TRACK_KMAX")) ? atoi(e) : TP_KMAX;
+    if (ctx->optTrackKmax < 1) ctx->optTrackKmax = 1;
+    if (ctx->optTrackKmax > TP_KMAX) ctx->optTrackKmax = TP_KMAX;
 }
 
 static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
@@ -855,23 +867,7 @@ static cudaError_t trackPersistentSetup(lsdgpu_ctx* ctx)
     if (e != cudaSuccess) return e;
     trackReadOptions(ctx);
     ctx->trackGrid = ctx->smCount < TP_MAXGRID ? ctx->smCount : TP_MAXGRID;      // one CTA per SM, co-resident (cooperative launch)
-    // work split per level (see TrackLevelParams): interior pixels in chunks of 32, CTAs 0..G-1 take part
-    int gPrev = 1;
-    for (int l = LSD_LEVELS - 1; l >= 0; l--) {
-        const int w = ctx->cam[l].w, h = ctx->cam[l].h;
-        const int nInt = (w - 2) * (h - 2), nChunks = (nInt + 31) / 32;
-        int G = (nChunks + ctx->optTrackWpc[l > 0 ? l : 1] - 1) / ctx->optTrackWpc[l > 0 ? l : 1];
-        if (G > ctx->trackGrid) G = ctx->trackGrid;
-        if (G < gPrev) G = gPrev;                                  // finer levels never use fewer CTAs: a CTA joins once and stays
-        if (G > nChunks) G = nChunks;
-        ctx->trackG[l] = G;
-        gPrev = G;
-    }
-    if (ctx->optTrackDebug) {
-        fprintf(stderr, "[track] grid %d, CTAs per level (L4..L1):", ctx->trackGrid);
-        for (int l = LSD_LEVELS - 1; l >= 1; l--) fprintf(stderr, " %d", ctx->trackG[l]);
-        fprintf(stderr, "\n");
-    }
+    if (ctx->optTrackDebug) fprintf(stderr, "[track] grid %d, candidate poses per pass <= %d\n", ctx->trackGrid, ctx->optTrackKmax);
     return cudaSuccess;
 }
 
@@ -901,7 +897,7 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
         L.w = c.w; L.h = c.h; L.fx = c.fx; L.fy = c.fy; L.cx = c.cx; L.cy = c.cy;
         L.fxi = c.fxi; L.fyi = c.fyi; L.cxi = c.cxi; L.cyi = c.cyi;
         L.iw = c.w - 2; L.nInt = (c.w - 2) * (c.h - 2); L.nChunks = (L.nInt + 31) / 32;
-        L.G = ctx->trackG[l];
+        L.G = ctx->trackGrid;
     }
     for (int l = 0; l < LSD_LEVELS; l++) P.gradMap[l] = fr->gradMap[l];
     P.useTma = ctx->optTrackTma;
@@ -921,7 +917,8 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     P.useAffine = ctx->g.useAffineLightningEstimation;
     P.partials = ctx->evPartials;
     P.sync = ctx->trkSync;
-    for (int l = 0; l < LSD_LEVELS; l++) P.barrierBase[l] = ctx->trkBase[l];
+    P.barrierBase[0] = ctx->trkBase[0];
+    P.kmax = ctx->optTrackKmax;
     if (prep) { P.doPrepare = 1; P.prep = *prep; P.obsOut = ctx->dObs; P.skipOut = ctx->dSkipFlag; }
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* dOutDev = (TrackState*)ctx->dTrackState;
@@ -975,17 +972,17 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
     // the other fields of the mapped result block are read with plain loads below: keep them behind the doneSeq read.  Block 0
     // publishes doneSeq while other CTAs may still be exiting, so only STREAM-ORDERED consumers may assume the kernel has retired.
     std::atomic_thread_fence(std::memory_order_acquire);
-    for (int l = 0; l < LSD_LEVELS; l++)
-        ctx->trkBase[l] += (unsigned int)hOut->evalsAtLevel[l] * (unsigned int)ctx->trackG[l];   // the level counters are never reset
+    ctx->trkBase[0] += (unsigned int)hOut->totalEvals * (unsigned int)ctx->trackGrid;    // the arrival counter is never reset
 
     if (ctx->profileTrackKernel) {           // the event pair is read lazily (flushTrackProfile): no extra sync on the path
         // SURVEY 8d, fused single-pass kernel: B_fused(l) = 20 B per valid point + 16 B per texel of the frame's gradient
-        // level (+5 B per point on L1: mask byte + index) + 160 B of partial sums, per evaluation.  The kernel reads the three
-        // keyframe planes densely (12 B per pixel); the ALGORITHMIC figure charges only the valid points, as the survey defines it.
+        // level (+5 B per point on L1: mask byte + index) + 160 B of partial sums, per evaluation OF THE REFERENCE
+        // (numCalcResidualCalls; speculative candidates the reference would not evaluate are not counted).  The kernel reads the
+        // three keyframe planes densely (12 B per pixel); the ALGORITHMIC figure charges only the valid points, as the survey defines it.
         double bytes = 0;
         for (int l = SE3TRACKING_MIN_LEVEL; l < SE3TRACKING_MAX_LEVEL; l++) {
             const double np_ = (double)hOut->pointsAtLevel[l];   // numData[level]: valid points of the level (CH_REFNUM)
-            bytes += (double)hOut->evalsAtLevel[l] * (20.0 * np_ + 16.0 * (double)ctx->cam[l].w * ctx->cam[l].h + (l == 1 ? 5.0 * np_ : 0.0) + EV_NCH * 4.0);
+            bytes += (double)hOut->numCalcResidualCalls[l] * (20.0 * np_ + 16.0 * (double)ctx->cam[l].w * ctx->cam[l].h + (l == 1 ? 5.0 * np_ : 0.0) + EV_NCH * 4.0);
         }
         ctx->trackKernelBytes += bytes;
         ctx->trackProfilePending = true;
@@ -995,13 +992,13 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
         unsigned int dbgc[4] = { 0, 0, 0, 0 };
         cudaMemcpy(dbgc, ctx->trkSync + TP_SYNC_WORDS - 4, 16, cudaMemcpyDeviceToHost);
         fprintf(stderr, "[track] useTma=%d tmaTimeouts=%u taps: %u from the smem window, %u through L1/L2\n", ctx->trackUseTma, dbgc[0], dbgc[1], dbgc[2]);
-        fprintf(stderr, "[track] evals=%d (L4..L1: %d %d %d %d) cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
-                hOut->totalEvals, hOut->evalsAtLevel[4], hOut->evalsAtLevel[3], hOut->evalsAtLevel[2], hOut->evalsAtLevel[1],
+        fprintf(stderr, "[track] passes=%d (L4..L1: %d %d %d %d) poses=%d reference evaluations=%d cycles: points=%lld ctaReduce=%lld barrier=%lld combine=%lld serialLM=%lld total=%lld\n",
+                hOut->totalEvals, hOut->evalsAtLevel[4], hOut->evalsAtLevel[3], hOut->evalsAtLevel[2], hOut->evalsAtLevel[1], hOut->posesEvaluated,
+                hOut->numCalcResidualCalls[4] + hOut->numCalcResidualCalls[3] + hOut->numCalcResidualCalls[2] + hOut->numCalcResidualCalls[1],
                 hOut->cyc[0], hOut->cyc[1], hOut->cyc[2], hOut->cyc[3], hOut->cyc[4], hOut->cyc[5]);
-        fprintf(stderr, "   LM lanes: decide=%lld apply=%lld proposeAccepted=%lld proposeRejected=%lld\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0],
-                hOut->cycBlk[TP_MAXGRID_DBG - 1][1], hOut->cycBlk[TP_MAXGRID_DBG - 1][2], hOut->cycBlk[TP_MAXGRID_DBG - 1][3]);
+        fprintf(stderr, "   warp 0: decisions=%lld chain building=%lld\n", hOut->cycBlk[TP_MAXGRID_DBG - 1][0], hOut->cycBlk[TP_MAXGRID_DBG - 1][1]);
         const char* nm[6] = { "points", "ctaReduce", "barrier", "combine", "serial", "total" };
-        const int gAll = ctx->trackG[SE3TRACKING_MIN_LEVEL];
+        const int gAll = ctx->trackGrid;
         for (int k = 0; k < 6; k++) {
             long long mn = 1LL << 60, mx = 0, sum = 0; int imx = 0, imn = 0;
             for (int b = 0; b < gAll && b < TP_MAXGRID_DBG - 1; b++) {
