@@ -76,7 +76,7 @@ void lsdo_default_globals(lsdo_globals* g)
 {   /* util/settings.cpp:77-88 */
     g->minUseGrad = 5; g->cameraPixelNoise2 = 4*4; g->depthSmoothingFactor = 1;
     g->allowNegativeIdepths = 1; g->useSubpixelStereo = 1; g->useAffineLightningEstimation = 1;
-    g->multiThreading = 1; g->useSSE = 0; g->exactAffineSums = 0;
+    g->multiThreading = 1; g->useSSE = 0; g->exactAffineSums = 0; g->exactTrackingSums = 0;
 }
 void lsdo_set_globals(const lsdo_globals* g) { G = *g; }
 void lsdo_get_globals(lsdo_globals* g) { *g = G; }
@@ -767,6 +767,7 @@ int lsdo_make_point_cloud(lsdo_frame* kf, int level, float* posData, float* grad
 typedef struct {
     float A[36], b[6], error; size_t num_constraints;
     float SSEData[4*28] __attribute__((aligned(16)));
+    double dA[36], db[6], derror;     /* diagnostic twin (lsdo_globals.exactTrackingSums): the same terms accumulated in double */
 } LGS6;
 
 static void lgs6_initialize(LGS6* ls) { memset(ls, 0, sizeof(*ls)); }
@@ -777,6 +778,11 @@ static inline void lgs6_update(LGS6* ls, const float J[6], float res, float weig
     for (int i = 0; i < 6; i++) ls->b[i] -= J[i]*rw;
     ls->error += res*res*weight;
     ls->num_constraints += 1;
+    if (G.exactTrackingSums) {        /* the same fp32 terms, summed without accumulation error */
+        for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) ls->dA[i*6+j] += (double)(J[i]*J[j]*weight);
+        for (int i = 0; i < 6; i++) ls->db[i] -= (double)(J[i]*rw);
+        ls->derror += (double)(res*res*weight);
+    }
 }
 static inline void lgs6_updateSSE(LGS6* ls, __m128 J1, __m128 J2, __m128 J3, __m128 J4, __m128 J5, __m128 J6, __m128 res, __m128 weight)
 {   /* LGSX.h:328-386 */
@@ -818,6 +824,11 @@ static void lgs6_finish(LGS6* ls)
     }
     for (int k = 0; k < 6; k++) ls->b[k] -= S[4*(21+k)+0] + S[4*(21+k)+1] + S[4*(21+k)+2] + S[4*(21+k)+3];
     ls->error += S[4*27+0] + S[4*27+1] + S[4*27+2] + S[4*27+3];
+    if (G.exactTrackingSums && !G.useSSE) {
+        for (int i = 0; i < 36; i++) ls->A[i] = (float)ls->dA[i];
+        for (int i = 0; i < 6; i++) ls->b[i] = (float)ls->db[i];
+        ls->error = (float)ls->derror;
+    }
     float n = (float)ls->num_constraints;
     for (int i = 0; i < 36; i++) ls->A[i] /= n;
     for (int i = 0; i < 6; i++) ls->b[i] /= n;
@@ -872,6 +883,7 @@ static float calcResidualAndBuffers(Tracker* t, const float* refPoint, const flo
     float sumSignedRes = 0;
     float sxx = 0, syy = 0, sx = 0, sy = 0, sw = 0;
     float usageCount = 0;
+    double dxx = 0, dyy = 0, dx = 0, dy = 0, dw = 0, dUsage = 0, dResU = 0, dSigned = 0;   /* exactTrackingSums twin */
     for (; refPoint < refPoint_max; refPoint += 3, refColVar += 2, idxBuf++) {
         float Wxp[3];
         for (int i = 0; i < 3; i++)
@@ -889,6 +901,7 @@ static float calcResidualAndBuffers(Tracker* t, const float* refPoint, const flo
         float residual = c1 - c2;
         float weight = fabsf(residual) < 5.0f ? 1 : 5.0f / fabsf(residual);
         sxx += c1*c1*weight; syy += c2*c2*weight; sx += c1*weight; sy += c2*weight; sw += weight;
+        dxx += (double)(c1*c1*weight); dyy += (double)(c2*c2*weight); dx += (double)(c1*weight); dy += (double)(c2*weight); dw += (double)weight;
         int isGood = residual*residual / (MAX_DIFF_CONSTANT + MAX_DIFF_GRAD_MULT*(resInterp[0]*resInterp[0] + resInterp[1]*resInterp[1])) < 1;
         if (isGoodOutBuffer != 0) isGoodOutBuffer[*idxBuf] = isGood;
         t->buf_warped_x[idx] = Wxp[0]; t->buf_warped_y[idx] = Wxp[1]; t->buf_warped_z[idx] = Wxp[2];
@@ -898,10 +911,15 @@ static float calcResidualAndBuffers(Tracker* t, const float* refPoint, const flo
         t->buf_d[idx] = 1.0f / refPoint[2];
         t->buf_idepthVar[idx] = refColVar[1];
         idx++;
-        if (isGood) { sumResUnweighted += residual*residual; sumSignedRes += residual; goodCount++; }
+        if (isGood) { sumResUnweighted += residual*residual; sumSignedRes += residual; goodCount++; dResU += (double)(residual*residual); dSigned += (double)residual; }
         else badCount++;
         float depthChange = refPoint[2] / Wxp[2];
         usageCount += depthChange < 1 ? depthChange : 1;
+        dUsage += (double)(depthChange < 1 ? depthChange : 1);
+    }
+    if (G.exactTrackingSums) {
+        sxx = (float)dxx; syy = (float)dyy; sx = (float)dx; sy = (float)dy; sw = (float)dw;
+        usageCount = (float)dUsage; sumResUnweighted = (float)dResU; sumSignedRes = (float)dSigned;
     }
     t->buf_warped_size = idx;
     t->pointUsage = usageCount / (float)refNum;
@@ -919,6 +937,7 @@ static float calcWeightsAndResidual(Tracker* t, const float refToFrame[7])
 {
     float tx = refToFrame[4], ty = refToFrame[5], tz = refToFrame[6];
     float sumRes = 0;
+    double dSumRes = 0;               /* exactTrackingSums twin */
     for (int i = 0; i < t->buf_warped_size; i++) {
         float px = t->buf_warped_x[i], py = t->buf_warped_y[i], pz = t->buf_warped_z[i];
         float d = t->buf_d[i];
@@ -932,8 +951,10 @@ static float calcWeightsAndResidual(Tracker* t, const float refToFrame[7])
         float weighted_rp = fabsf(rp*sqrtf(w_p));
         float wh = fabsf(weighted_rp < (t->settings.huber_d/2) ? 1 : (t->settings.huber_d/2) / weighted_rp);
         sumRes += wh * w_p * rp*rp;
+        dSumRes += (double)(wh * w_p * rp*rp);
         t->buf_weight_p[i] = wh * w_p;
     }
+    if (G.exactTrackingSums) sumRes = (float)dSumRes;
     return sumRes / t->buf_warped_size;
 }
 

@@ -63,6 +63,10 @@ typedef struct {
     int   exactAffineSums;            /* DIAGNOSTIC, default 0 = the reference: 1 accumulates the five affine-lighting sums of
                                        * calcSim3Buffers in double, to separate the float-accumulation noise of the reference
                                        * (sums ~1e9 in fp32) from real differences when a parity test looks at residuals */
+    int   exactTrackingSums;          /* DIAGNOSTIC, default 0 = the reference: 1 accumulates every sum of the SE3 tracker (affine-lighting
+                                       * sums, residual sums, LGS6 A / b / error) in double from the same fp32 terms -- the result the
+                                       * reference's sequential fp32 accumulation approximates.  Used to measure the reference's OWN
+                                       * summation noise in the tracked pose (tests/test_gpu_fullsize.py) */
 } lsdo_globals;
 
 /* DenseDepthTrackerSettings, util/settings.h:355-402 */

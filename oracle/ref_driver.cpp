@@ -177,6 +177,7 @@ void lsdo_default_globals(lsdo_globals* g)
     g->useSSE = 0;
 #endif
     g->exactAffineSums = 0;
+    g->exactTrackingSums = 0;          // diagnostic switches of the C restatement: no equivalent in the reference
 }
 void lsdo_set_globals(const lsdo_globals* g)
 {

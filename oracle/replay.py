@@ -8,7 +8,10 @@ parallel reduction cannot reproduce the CPU's sequential float sums bit for bit,
 frames measures that sensitivity, not the kernels.  `north_star` asks for parity "for identical inputs": this module takes
 the device's state before a step (hypotheses, keyframe, counters, initial pose), replays the SAME step on the CPU oracle,
 and compares
-  * the tracked pose (<= 1e-4 relative) and the LM call counters, and
+  * the tracked pose and the LM call counters: <= 1e-4 relative, plus the reference's OWN summation noise on that step (the
+    distance between the oracle and its diagnostic twin that accumulates the same fp32 terms exactly -- up to 1.7e-4 on the
+    bench streams: the sequential fp32 sums of SE3Tracker.cpp carry ~1e-5 relative error into a 6x6 system whose weak
+    directions amplify it), and
   * with the device's pose, residual and good-mask handed to the oracle, the depth map after the step BIT FOR BIT
     (keyframe changes: within the rescale factor's 2e-5, DepthMap.cpp:1286-1294).
 Only tests/ and bench.py's parity leg import this.
@@ -67,15 +70,27 @@ def replay_step(seq, snap: Snapshot, fid: int, image_u8, gs, settings=None):
     L = po.lib(fl)
     st = settings or po.default_track_settings(fl)
     # keyframe + depth map in the device's pre-step state
-    okf = po.Frame(snap.kf_id, snap.kf_image, seq.K, fast=fl)
-    okf.setDepthFromGroundTruth(np.ones((seq.h, seq.w), np.float32))       # only to attach the frame as the active keyframe
-    odm = po.DepthMap(seq.w, seq.h, seq.K, fast=fl)
-    odm.initializeFromGTDepth(okf)
-    odm.set_current(snap.hyp)
     hyp_c = np.ascontiguousarray(snap.hyp)
-    L.lsdo_frame_setDepth(okf.ptr, hyp_c.ctypes.data_as(po.C.POINTER(po.Hyp)))   # Frame::setDepth(currentDepthMap), DepthMap.cpp:1153 / 1311
-    L.lsdo_frame_set_counters(okf.ptr, int(snap.counters[0]), int(snap.counters[1]))
-    L.lsdo_frame_set_depthHasBeenUpdatedFlag(okf.ptr, 0)
+
+    def make_kf():
+        kf = po.Frame(snap.kf_id, snap.kf_image, seq.K, fast=fl)
+        kf.setDepthFromGroundTruth(np.ones((seq.h, seq.w), np.float32))    # only to attach the frame as the active keyframe
+        dm = po.DepthMap(seq.w, seq.h, seq.K, fast=fl)
+        dm.initializeFromGTDepth(kf)
+        dm.set_current(snap.hyp)
+        L.lsdo_frame_setDepth(kf.ptr, hyp_c.ctypes.data_as(po.C.POINTER(po.Hyp)))   # Frame::setDepth(currentDepthMap), DepthMap.cpp:1153 / 1311
+        L.lsdo_frame_set_counters(kf.ptr, int(snap.counters[0]), int(snap.counters[1]))
+        L.lsdo_frame_set_depthHasBeenUpdatedFlag(kf.ptr, 0)
+        return kf, dm
+
+    # the reference's OWN summation noise on this step: the same tracking with every sum accumulated exactly (diagnostic twin of
+    # the oracle, lsdo_globals.exactTrackingSums) -- what the sequential fp32 sums of SE3Tracker.cpp approximate
+    po.set_globals(fl, exactTrackingSums=1)
+    xkf, _xdm = make_kf()
+    xf = po.Frame(fid, image_u8, seq.K, fast=fl)
+    pose_x = np.array(po.se3_track(xkf, xf, snap.last_pose, st).frameToRef_qt, np.float64)
+    po.set_globals(fl)
+    okf, odm = make_kf()
     of = po.Frame(fid, image_u8, seq.K, fast=fl)
     r = po.se3_track(okf, of, snap.last_pose, st)
     res = gs.tracker.last
@@ -83,6 +98,8 @@ def replay_step(seq, snap: Snapshot, fid: int, image_u8, gs, settings=None):
     pose_o = np.array(r.frameToRef_qt, np.float64)
     out = {"frame": fid, "kf_change": snap.kf_change}
     out["pose_rel"], out["rot_rad"] = pose_err(pose_g, pose_o)
+    out["ref_noise_rel"], out["ref_noise_rot"] = pose_err(pose_o, pose_x)      # reference (fp32 sequential sums) vs exact sums
+    out["pose_rel_exact"], _ = pose_err(pose_g, pose_x)                        # device vs exact sums
     out["counts_equal"] = (list(res.numCalcResidualCalls) == list(r.numCalcResidualCalls)
                            and list(res.numCalcWarpUpdateCalls) == list(r.numCalcWarpUpdateCalls))
     out["stats"] = {"lastResidual": (res.lastResidual, r.lastResidual), "pointUsage": (res.pointUsage, r.pointUsage),
