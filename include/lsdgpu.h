@@ -284,6 +284,11 @@ int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs
 /* DepthMap::createKeyFrame(new_keyframe) :1222-1327; writes the rescaled thisToParent_raw of the new KF */
 int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, double new_thisToParent_qts[8]);
 int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx);                      /* finalizeKeyFrame :1363-1395 */
+/* The `float sumIdepth` loop of createKeyFrame (:1286-1293) on host data: sum of x[i] over valid[i] != 0 (valid == NULL: all) in
+ * index order with fp32 round-to-nearest after EVERY addition -- computed by the parallel kernels createKeyFrame itself uses
+ * (csrc/seqsum.cuh), bit-identical to the sequential loop for any input.  A parity hook: it lets the tests feed ties, binade
+ * crossings, negative and non-finite terms. */
+int lsdgpu_seq_sum_f32(lsdgpu_ctx* ctx, const float* x, const unsigned char* valid, int n, float* sum, int* count);
 int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx);                        /* id or -1 */
 /* currentDepthMap in the reference's 32-byte AoS layout (Frame::setDepth / takeReActivationData input) */
 int lsdgpu_depth_download(lsdgpu_ctx* ctx, lsdgpu_hyp* aos_out);

@@ -142,6 +142,7 @@ SYMBOLS = [
     ("lsdgpu_depth_set_hypotheses", C.c_int, [_vp, C.c_int, C.POINTER(Hyp), C.c_int, C.c_int]),
     ("lsdgpu_depth_update_keyframe", C.c_int, [_vp, _ip, C.c_int]),
     ("lsdgpu_depth_create_keyframe", C.c_int, [_vp, C.c_int, _dp]),
+    ("lsdgpu_seq_sum_f32", C.c_int, [_vp, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("lsdgpu_depth_finalize_keyframe", C.c_int, [_vp]),
     ("lsdgpu_depth_active_keyframe", C.c_int, [_vp]),
     ("lsdgpu_depth_download", C.c_int, [_vp, C.POINTER(Hyp)]),
@@ -160,6 +161,9 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("LSDGPU_LIB"):                 # A/B runs of two builds of the library (scripts/ab_track.py, profiling)
+        LIB_PATH = os.path.abspath(os.environ["LSDGPU_LIB"])
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m lsd_slam_b200.build` "
                            "(the product path has no CPU fallback)")
@@ -327,6 +331,14 @@ class Context:
         pid, itr = C.c_int(), C.c_float()
         self._ck(self.L.lsdgpu_frame_get_pose(self.ptr, fid, q.ctypes.data_as(_dp), C.byref(pid), C.byref(itr)))
         return q, pid.value, itr.value
+
+    def seq_sum_f32(self, x, valid=None):
+        """the sequential fp32 `sum += x[i]` of DepthMap.cpp:1286-1293 through the kernels createKeyFrame uses"""
+        x = np.ascontiguousarray(x, np.float32).ravel()
+        v = None if valid is None else np.ascontiguousarray(valid, np.uint8).ravel()
+        s, c = C.c_float(), C.c_int()
+        self._ck(self.L.lsdgpu_seq_sum_f32(self.ptr, x.ctypes.data, None if v is None else v.ctypes.data, x.size, C.byref(s), C.byref(c)))
+        return np.float32(s.value), c.value
 
     def get_counters(self, fid: int):
         a, b = C.c_int(), C.c_int()

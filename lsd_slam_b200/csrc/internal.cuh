@@ -156,6 +156,9 @@ struct lsdgpu_ctx {
     int optTrackTma = 1, optSingleSync = 0;
     bool optTrackDebug = false;
     int optTrackKmax = 3;
+    int2* seqTable = nullptr;            // seqsum.cuh: per-run maps of the sequential fp32 sum, [SEQ_NBIN][runs]
+    unsigned char* seqFlags = nullptr;
+    int* seqCounts = nullptr;
     int* dSkipFlag = nullptr;            // device flag: the frame's tracking diverged -> its mapping kernels do nothing
     ObserveParams* dObs = nullptr;       // device-resident observe parameters written by k_prepare_observe
     unsigned int trackSeq = 0;           // sequence number of the last tracking launch (TrackState::doneSeq)

@@ -5,6 +5,7 @@
 #include "frame.cuh"
 #include "track.cuh"
 #include "depth.cuh"
+#include "seqsum.cuh"
 #include "track_persistent.cuh"
 #include "perma.cuh"
 #include "sim3.cuh"
@@ -92,6 +93,8 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     size_t scratch = alignUp((size_t)maxBlocks * EV_NCH * 4 + 65536, 256) + 4096 + alignUp(sizeof(ObserveParams), 256)
                      + 2 * alignUp(n0, 256) + alignUp(n0 * 32, 256) + alignUp((size_t)maxBlocks * 2 * 8 + 64, 256) + (256 + 2 * alignUp((n0 >> 8) * 16, 256) + 2 * alignUp(n0 * 4, 256) + alignUp(n0, 256)) * (size_t)max_frames + alignUp(n0 * 12, 256) + alignUp(LSD_MAX_PERMA_BATCH * (sizeof(PermaItem) + sizeof(PermaResult)), 256) + 1024 + alignUp(S3_MAX_BATCH * sizeof(Sim3Item), 256) + alignUp(S3_MAX_BATCH * sizeof(Sim3Out), 256)
                      + alignUp(sizeof(TrackState), 256) + alignUp(sizeof(ObserveParams), 256) + 8192 + TP_SYNC_WORDS * 4;
+    const int seqRuns = divUp((int)n0, SEQ_RUN);
+    scratch += alignUp((size_t)seqRuns * SEQ_NBIN * sizeof(int2), 256) + alignUp((size_t)seqRuns, 256) + alignUp((size_t)seqRuns * 4, 256);
     ctx->arenaBytes = perFrame * max_frames + depthBytes + scratch;
     LSD_CHECK(ctx, cudaMalloc((void**)&ctx->arena, ctx->arenaBytes));
     LSD_CHECK(ctx, cudaMemsetAsync(ctx->arena, 0, ctx->arenaBytes, ctx->stream));
@@ -162,6 +165,9 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     ctx->dTrackState = take(sizeof(TrackState));
     ctx->dObs = (ObserveParams*)take(sizeof(ObserveParams));
     ctx->dSkipFlag = (int*)take(256);
+    ctx->seqTable = (int2*)take((size_t)seqRuns * SEQ_NBIN * sizeof(int2));
+    ctx->seqFlags = (unsigned char*)take((size_t)seqRuns);
+    ctx->seqCounts = (int*)take((size_t)seqRuns * 4);
     if ((size_t)(p - ctx->arena) > ctx->arenaBytes) return lsd_fail(ctx, "arena overflow");
 
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hEvOut, EV_NCH * 4, cudaHostAllocDefault));
@@ -1024,7 +1030,11 @@ extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, doub
     if (r) return r;
     const int n = ctx->w * ctx->h;
     const int nb = divUp(n, 256);
-    k_sum_idepth<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars + 8, ctx->evCounter + 48, ctx->dScalars);   // :1286-1293
+    // :1286-1294: the reference's sequential `float +=` over the valid hypotheses, reproduced bit for bit (seqsum.cuh)
+    const int seqRuns = divUp(n, SEQ_RUN);
+    k_seqsum_table<<<divUp(seqRuns, 8), 256, 0, ctx->stream>>>(ctx->cur.hf, ctx->cur.hi, n, seqRuns, ctx->seqTable, ctx->seqFlags, ctx->seqCounts);
+    LAUNCH(ctx);
+    k_seqsum_walk<<<1, 32, 0, ctx->stream>>>(ctx->cur.hf, ctx->cur.hi, n, seqRuns, ctx->seqTable, ctx->seqFlags, ctx->seqCounts, ctx->dScalars);
     LAUNCH(ctx);
     k_rescale<<<nb, 256, 0, ctx->stream>>>(ctx->cur, n, ctx->dScalars);                          // :1295-1304
     LAUNCH(ctx);
@@ -1038,6 +1048,54 @@ extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, doub
     nk->thisToParent[7] = rescaleFactor;
     if (new_qts) memcpy(new_qts, nk->thisToParent, sizeof(nk->thisToParent));
     return setDepthOnKeyframe(ctx, nk);                            // :1311
+}
+
+__global__ void k_seqsum_pack(const float* __restrict__ x, const unsigned char* __restrict__ valid, int n, float4* hf, int4* hi)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    hf[i] = make_float4(0.f, 0.f, x[i], 0.f);
+    hi[i] = make_int4(valid ? (valid[i] != 0) : 1, 0, 0, 0);
+}
+
+// The sequential `float sum = 0; for (i) if (valid[i]) sum += x[i];` of DepthMap.cpp:1286-1293 on arbitrary host data, through
+// the kernels createKeyFrame uses (seqsum.cuh) -- exposed so the bit-exactness of that reproduction can be tested on adversarial
+// inputs (ties, binade crossings, negative / non-finite terms), which real depth maps rarely contain.
+extern "C" int lsdgpu_seq_sum_f32(lsdgpu_ctx* ctx, const float* x, const unsigned char* valid, int n, float* sum, int* count)
+{
+    if (!ctx || !x || n < 0 || !sum) return lsd_fail(ctx, "seq_sum_f32: bad arguments");
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (n == 0) { *sum = 0.f; if (count) *count = 0; return 0; }
+    const int runs = divUp(n, SEQ_RUN);
+    char* buf = nullptr;
+    const size_t bx = alignUp((size_t)n * 4, 256), bv = alignUp((size_t)n, 256), bf = alignUp((size_t)n * 16, 256),
+                 bt = alignUp((size_t)runs * SEQ_NBIN * sizeof(int2), 256), bg = alignUp((size_t)runs, 256), bc = alignUp((size_t)runs * 4, 256);
+    LSD_CHECK(ctx, cudaMalloc((void**)&buf, bx + bv + 2 * bf + bt + bg + bc + 256));
+    char* p = buf;
+    float* dx = (float*)p; p += bx;
+    unsigned char* dv = (unsigned char*)p; p += bv;
+    float4* hf = (float4*)p; p += bf;
+    int4* hi = (int4*)p; p += bf;
+    int2* table = (int2*)p; p += bt;
+    unsigned char* flags = (unsigned char*)p; p += bg;
+    int* counts = (int*)p; p += bc;
+    double* out = (double*)p;
+    int rc = 0;
+    do {
+        if (cudaMemcpyAsync(dx, x, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
+        if (valid && cudaMemcpyAsync(dv, valid, (size_t)n, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = 1; break; }
+        k_seqsum_pack<<<divUp(n, 256), 256, 0, ctx->stream>>>(dx, valid ? dv : nullptr, n, hf, hi);
+        k_seqsum_table<<<divUp(runs, 8), 256, 0, ctx->stream>>>(hf, hi, n, runs, table, flags, counts);
+        k_seqsum_walk<<<1, 32, 0, ctx->stream>>>(hf, hi, n, runs, table, flags, counts, out);
+        double h[3];
+        if (cudaMemcpyAsync(h, out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { rc = 1; break; }
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { rc = 1; break; }
+        *sum = (float)h[0];
+        if (count) *count = (int)h[1];
+    } while (0);
+    cudaFree(buf);
+    if (rc) return lsd_fail(ctx, "seq_sum_f32: CUDA error");
+    return 0;
 }
 
 // Frame::takeReActivationData(currentDepthMap), Frame.cpp:107-145.  The pool buffers of a fresh Frame are defined as
