@@ -281,6 +281,19 @@ int lsdgpu_depth_init_from_gt(lsdgpu_ctx* ctx, int kf_id);                /* ini
 int lsdgpu_depth_set_hypotheses(lsdgpu_ctx* ctx, int kf_id, const lsdgpu_hyp* aos, int reactivated, int do_set_depth);
 /* DepthMap::updateKeyframe(referenceFrames) :1072-1213; ref_ids oldest first, all tracked on the active KF */
 int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs);
+/* The same with the reference-frame set-up of :1085-1101 spelled out.  DepthMap::updateKeyframe accepts frames that were tracked
+ * on ANOTHER keyframe (the frames still queued in unmappedTrackedFrames when the keyframe changes, SlamSystem.cpp:559-575):
+ *   refToKf = frame->pose->trackingParent == activeKeyFrame ? frame->pose->thisToParent_raw                           (:1096-1097)
+ *           : activeKeyFrame->getScaledCamToWorld().inverse() * frame->getScaledCamToWorld()                          (:1098-1099)
+ * and such frames do not apply their tracking mask (the `refFrame->getTrackingParent() == activeKeyFrame` gate of :245 / :322).
+ * The absolute poses belong to the caller's pose graph (FramePoseStruct::getCamToWorld, KeyFrameGraph), so the caller passes the
+ * product; tracked_on_kf != 0 uses the pose stored by the tracker and ignores refToKf_qts. */
+typedef struct lsdgpu_ref_desc {
+    int32_t frame_id;
+    int32_t tracked_on_kf;          /* frame->getTrackingParent() == activeKeyFrame */
+    double  refToKf_qts[8];         /* unit quaternion x,y,z,w, translation, scale; read when tracked_on_kf == 0 */
+} lsdgpu_ref_desc;
+int lsdgpu_depth_update_keyframe_refs(lsdgpu_ctx* ctx, const lsdgpu_ref_desc* refs, int n_refs);
 /* DepthMap::createKeyFrame(new_keyframe) :1222-1327; writes the rescaled thisToParent_raw of the new KF */
 int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, double new_thisToParent_qts[8]);
 int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx);                      /* finalizeKeyFrame :1363-1395 */

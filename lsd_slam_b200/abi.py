@@ -38,6 +38,11 @@ HYP_DTYPE = np.dtype([("isValid", np.uint8), ("_pad", np.uint8, 3), ("blackliste
 POINT_DENSE = np.dtype([("idepth", np.float32), ("idepth_var", np.float32), ("color", np.uint8, (4,))])     # InputPointDense
 
 
+class RefDesc(C.Structure):
+    """lsdgpu_ref_desc (include/lsdgpu.h)"""
+    _fields_ = [("frame_id", C.c_int32), ("tracked_on_kf", C.c_int32), ("refToKf_qts", C.c_double * 8)]
+
+
 class Globals(C.Structure):
     _fields_ = [("minUseGrad", C.c_float), ("cameraPixelNoise2", C.c_float), ("depthSmoothingFactor", C.c_float),
                 ("allowNegativeIdepths", C.c_int), ("useSubpixelStereo", C.c_int),
@@ -141,6 +146,7 @@ SYMBOLS = [
     ("lsdgpu_depth_init_from_gt", C.c_int, [_vp, C.c_int]),
     ("lsdgpu_depth_set_hypotheses", C.c_int, [_vp, C.c_int, C.POINTER(Hyp), C.c_int, C.c_int]),
     ("lsdgpu_depth_update_keyframe", C.c_int, [_vp, _ip, C.c_int]),
+    ("lsdgpu_depth_update_keyframe_refs", C.c_int, [_vp, C.c_void_p, C.c_int]),
     ("lsdgpu_depth_create_keyframe", C.c_int, [_vp, C.c_int, _dp]),
     ("lsdgpu_seq_sum_f32", C.c_int, [_vp, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("lsdgpu_depth_finalize_keyframe", C.c_int, [_vp]),
@@ -536,8 +542,22 @@ class DepthMap:
         self.ctx._ck(self.ctx.L.lsdgpu_depth_set_from_existing_kf(self.ctx.ptr, kf_id))
 
     def updateKeyframe(self, referenceFrames):
-        a, p, n = self._ids(referenceFrames)
-        self.ctx._ck(self.ctx.L.lsdgpu_depth_update_keyframe(self.ctx.ptr, p, n))
+        """DepthMap::updateKeyframe (DepthMap.cpp:1072-1213).  An item is a frame id (tracked on the active keyframe) or a pair
+        (frame id, refToKf_qts) for a frame tracked on another keyframe -- refToKf = activeKeyFrame->getScaledCamToWorld().inverse()
+        * frame->getScaledCamToWorld() (:1099), which the owner of the pose graph computes."""
+        items = list(referenceFrames)
+        if all(isinstance(it, (int, np.integer)) for it in items):
+            a, p, n = self._ids(items)
+            self.ctx._ck(self.ctx.L.lsdgpu_depth_update_keyframe(self.ctx.ptr, p, n))
+            return
+        descs = (RefDesc * len(items))()
+        for d, it in zip(descs, items):
+            if isinstance(it, (int, np.integer)):
+                d.frame_id, d.tracked_on_kf = int(it), 1
+            else:
+                d.frame_id, d.tracked_on_kf = int(it[0]), 0
+                d.refToKf_qts[:] = [float(v) for v in it[1]]
+        self.ctx._ck(self.ctx.L.lsdgpu_depth_update_keyframe_refs(self.ctx.ptr, descs, len(items)))
 
     def createKeyFrame(self, new_kf_id: int) -> np.ndarray:
         q = np.zeros(8, np.float64)

@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -102,6 +103,11 @@ struct ObserveParams {
 #define EV_NCH 40
 
 struct lsdgpu_ctx {
+    // Every entry point of the C ABI holds this for its whole duration (LSD_LOCK): one context may be shared by SlamSystem's
+    // tracking and mapping threads (SlamSystem.cpp:111, :206) -- their calls serialise here, as they do on the frame / keyframe
+    // locks of the reference (Frame::getActiveLock, SE3Tracker.cpp:286, DepthMap.cpp:1104).  Recursive: the fused entry points
+    // (lsdgpu_track_and_map, lsdgpu_sim3_track) call other entry points.
+    mutable std::recursive_mutex mu;
     int device = 0;
     int w = 0, h = 0;
     LevelCam cam[LSD_LEVELS];
@@ -181,6 +187,14 @@ struct lsdgpu_ctx {
     bool trackProfilePending = false;
     void* encodeTiled = nullptr;         // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
 };
+
+struct CtxLock {
+    std::recursive_mutex* m;
+    explicit CtxLock(const lsdgpu_ctx* c) : m(c ? &c->mu : nullptr) { if (m) m->lock(); }
+    ~CtxLock() { if (m) m->unlock(); }
+    CtxLock(const CtxLock&) = delete;
+};
+#define LSD_LOCK(ctx) CtxLock lsd_lock_(ctx)
 
 #define LSD_CHECK(ctx, expr)                                                                              \
     do {                                                                                                  \

@@ -213,31 +213,37 @@ extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
     delete ctx;
 }
 
-extern "C" const char* lsdgpu_last_error(const lsdgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-extern "C" int lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g) { ctx->g = *g; return 0; }
-extern "C" int lsdgpu_get_globals(const lsdgpu_ctx* ctx, lsdgpu_globals* g) { *g = ctx->g; return 0; }
+extern "C" const char* lsdgpu_last_error(const lsdgpu_ctx* ctx) {   // a copy per calling thread: another thread may fail (and overwrite ctx->err) right after this one
+    static thread_local std::string mine;
+    if (!ctx) return "null context";
+    LSD_LOCK(ctx);
+    mine = ctx->err;
+    return mine.c_str();
+}
+extern "C" int lsdgpu_set_globals(lsdgpu_ctx* ctx, const lsdgpu_globals* g) { LSD_LOCK(ctx); ctx->g = *g; return 0; }
+extern "C" int lsdgpu_get_globals(const lsdgpu_ctx* ctx, lsdgpu_globals* g) { LSD_LOCK(ctx); *g = ctx->g; return 0; }
 extern "C" int lsdgpu_synchronize(lsdgpu_ctx* ctx)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
-extern "C" long long lsdgpu_launch_count(const lsdgpu_ctx* ctx) { return ctx->launches; }
+extern "C" long long lsdgpu_launch_count(const lsdgpu_ctx* ctx) { LSD_LOCK(ctx); return ctx->launches; }
 
 extern "C" int lsdgpu_timer_begin(lsdgpu_ctx* ctx, int slot)
-{
+{ LSD_LOCK(ctx);
     if (slot < 0 || slot >= 8) return -2;
     LSD_CHECK(ctx, cudaEventRecord(ctx->tBegin[slot], ctx->stream));
     return 0;
 }
 extern "C" int lsdgpu_timer_end(lsdgpu_ctx* ctx, int slot)
-{
+{ LSD_LOCK(ctx);
     if (slot < 0 || slot >= 8) return -2;
     LSD_CHECK(ctx, cudaEventRecord(ctx->tEnd[slot], ctx->stream));
     return 0;
 }
 extern "C" int lsdgpu_timer_elapsed_ms(lsdgpu_ctx* ctx, int slot, float* ms)
-{
+{ LSD_LOCK(ctx);
     if (slot < 0 || slot >= 8) return -2;
     LSD_CHECK(ctx, cudaEventSynchronize(ctx->tEnd[slot]));
     LSD_CHECK(ctx, cudaEventElapsedTime(ms, ctx->tBegin[slot], ctx->tEnd[slot]));
@@ -245,7 +251,7 @@ extern "C" int lsdgpu_timer_elapsed_ms(lsdgpu_ctx* ctx, int slot, float* ms)
 }
 static void flushTrackProfile(lsdgpu_ctx* ctx);
 extern "C" int lsdgpu_track_kernel_stats(lsdgpu_ctx* ctx, int reset, double* ms, long long* launches, double* bytes)
-{
+{ LSD_LOCK(ctx);
     flushTrackProfile(ctx);
     if (ms) *ms = ctx->trackKernelMs;
     if (launches) *launches = ctx->trackKernelLaunches;
@@ -284,7 +290,7 @@ static FrameSlot* acquireSlot(lsdgpu_ctx* ctx, int id)
 static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* dsrc, bool remap = false);
 
 extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* gray)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = acquireSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");
@@ -305,7 +311,7 @@ extern "C" int lsdgpu_frame_upload_u8(lsdgpu_ctx* ctx, int frame_id, const uint8
 }
 
 extern "C" int lsdgpu_stage_reserve(lsdgpu_ctx* ctx, int n_entries)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     if (n_entries <= 0) return lsd_fail(ctx, "bad ring size");
     LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -315,7 +321,7 @@ extern "C" int lsdgpu_stage_reserve(lsdgpu_ctx* ctx, int n_entries)
     return 0;
 }
 extern "C" int lsdgpu_stage_put(lsdgpu_ctx* ctx, int index, const uint8_t* gray)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     if (index < 0 || index >= ctx->stageEntries) return lsd_fail(ctx, "bad ring index");
     const size_t n0 = (size_t)ctx->w * ctx->h;
@@ -326,7 +332,7 @@ extern "C" int lsdgpu_stage_put(lsdgpu_ctx* ctx, int index, const uint8_t* gray)
     return 0;
 }
 extern "C" int lsdgpu_frame_from_stage(lsdgpu_ctx* ctx, int frame_id, int index)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     if (index < 0 || index >= ctx->stageEntries) return lsd_fail(ctx, "bad ring index");
     FrameSlot* s = acquireSlot(ctx, frame_id);
@@ -354,7 +360,7 @@ static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* 
 }
 
 extern "C" int lsdgpu_frame_release(lsdgpu_ctx* ctx, int frame_id)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     if (ctx->activeKf == frame_id) return lsd_fail(ctx, "frame is the active keyframe of the depth map");
@@ -376,7 +382,7 @@ static int ensureIdepthPyramid(lsdgpu_ctx* ctx, FrameSlot* s)
 }
 
 extern "C" int lsdgpu_frame_download(lsdgpu_ctx* ctx, int frame_id, int what, int level, void* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
@@ -404,7 +410,7 @@ extern "C" int lsdgpu_frame_download(lsdgpu_ctx* ctx, int frame_id, int what, in
 }
 
 extern "C" int lsdgpu_frame_set_depth_gt(lsdgpu_ctx* ctx, int frame_id, const float* depth, float cov_scale)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
@@ -421,7 +427,7 @@ extern "C" int lsdgpu_frame_set_depth_gt(lsdgpu_ctx* ctx, int frame_id, const fl
 }
 
 extern "C" int lsdgpu_frame_set_idepth(lsdgpu_ctx* ctx, int frame_id, const float* idepth, const float* idepthVar)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
@@ -436,7 +442,7 @@ extern "C" int lsdgpu_frame_set_idepth(lsdgpu_ctx* ctx, int frame_id, const floa
 }
 
 extern "C" int lsdgpu_frame_set_pose(lsdgpu_ctx* ctx, int frame_id, const double qts[8], int parent_id, float itr)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     memcpy(s->thisToParent, qts, sizeof(s->thisToParent));
@@ -444,7 +450,7 @@ extern "C" int lsdgpu_frame_set_pose(lsdgpu_ctx* ctx, int frame_id, const double
     return 0;
 }
 extern "C" int lsdgpu_frame_get_pose(lsdgpu_ctx* ctx, int frame_id, double qts[8], int* parent_id, float* itr)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     if (qts) memcpy(qts, s->thisToParent, sizeof(s->thisToParent));
@@ -453,7 +459,7 @@ extern "C" int lsdgpu_frame_get_pose(lsdgpu_ctx* ctx, int frame_id, double qts[8
     return 0;
 }
 extern "C" int lsdgpu_frame_get_counters(lsdgpu_ctx* ctx, int frame_id, int* tracked, int* mapped)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     if (tracked) *tracked = s->numFramesTrackedOnThis;
@@ -461,14 +467,14 @@ extern "C" int lsdgpu_frame_get_counters(lsdgpu_ctx* ctx, int frame_id, int* tra
     return 0;
 }
 extern "C" int lsdgpu_frame_set_counters(lsdgpu_ctx* ctx, int frame_id, int tracked, int mapped)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     s->numFramesTrackedOnThis = tracked; s->numMappedOnThis = mapped;
     return 0;
 }
 extern "C" int lsdgpu_frame_get_depth_stats(lsdgpu_ctx* ctx, int frame_id, float* meanIdepth, int* numPoints, int* flag)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     if ((meanIdepth || numPoints) && s->statsPending) {      // fetched lazily: keeps updateKeyframe free of host syncs
@@ -485,7 +491,7 @@ extern "C" int lsdgpu_frame_get_depth_stats(lsdgpu_ctx* ctx, int frame_id, float
     return 0;
 }
 extern "C" int lsdgpu_frame_clear_good_mask(lsdgpu_ctx* ctx, int frame_id)
-{
+{ LSD_LOCK(ctx);
     FrameSlot* s = findSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "unknown frame id");
     s->hasGoodMask = false;
@@ -496,7 +502,7 @@ extern "C" int lsdgpu_frame_clear_good_mask(lsdgpu_ctx* ctx, int frame_id)
 // tracking
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lsdgpu_ref_import(lsdgpu_ctx* ctx, int kf_id)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -561,7 +567,7 @@ static int runEval(lsdgpu_ctx* ctx, const EvalLevel& L, const lsd::SE3<float>& r
 extern "C" int lsdgpu_se3_eval(lsdgpu_ctx* ctx, int kf_id, int frame_id, int level, const float refToFrame_qt[7],
                                float affine_a, float affine_b, const lsdgpu_track_settings* s, int write_good_mask,
                                lsdgpu_eval_result* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     FrameSlot* fr = findSlot(ctx, frame_id);
@@ -676,7 +682,7 @@ static int trackHostLM(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr, const doub
 
 extern "C" int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double init_qt[7],
                                 const lsdgpu_track_settings* s, int mode, lsdgpu_track_result* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     FrameSlot* fr = findSlot(ctx, frame_id);
@@ -703,7 +709,7 @@ static_assert(LSDGPU_EVAL_NSUMS == EV_NCH, "ABI constant out of sync with the ke
 extern "C" int lsdgpu_se3_track_sharded(lsdgpu_ctx* ctx, int kf_id, int frame_id, const double init_qt[7],
                                         const lsdgpu_track_settings* s, int shard, int n_shards,
                                         lsdgpu_allreduce_fn allreduce, void* user, lsdgpu_track_result* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     FrameSlot* fr = findSlot(ctx, frame_id);
@@ -747,7 +753,7 @@ static DepthGlobals depthGlobals(const lsdgpu_ctx* ctx)
 }
 
 extern "C" int lsdgpu_depth_reset(lsdgpu_ctx* ctx)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)ctx->w * ctx->h;
     // isValid = false everywhere (the int4 plane: isValid, blacklisted, validity, nextId)
@@ -755,9 +761,9 @@ extern "C" int lsdgpu_depth_reset(lsdgpu_ctx* ctx)
     LSD_CHECK(ctx, cudaMemsetAsync(ctx->oth.hi, 0, n * 16, ctx->stream));
     return 0;
 }
-extern "C" int lsdgpu_depth_is_valid(lsdgpu_ctx* ctx) { return ctx->activeKf >= 0 ? 1 : 0; }
-extern "C" int lsdgpu_depth_invalidate(lsdgpu_ctx* ctx) { ctx->activeKf = -1; return 0; }
-extern "C" int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx) { return ctx->activeKf; }
+extern "C" int lsdgpu_depth_is_valid(lsdgpu_ctx* ctx) { LSD_LOCK(ctx); return ctx->activeKf >= 0 ? 1 : 0; }
+extern "C" int lsdgpu_depth_invalidate(lsdgpu_ctx* ctx) { LSD_LOCK(ctx); ctx->activeKf = -1; return 0; }
+extern "C" int lsdgpu_depth_active_keyframe(lsdgpu_ctx* ctx) { LSD_LOCK(ctx); return ctx->activeKf; }
 
 // Frame::setDepth(currentDepthMap) of the active keyframe
 static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf, const int* skip = nullptr)
@@ -777,7 +783,7 @@ static int setDepthOnKeyframe(lsdgpu_ctx* ctx, FrameSlot* kf, const int* skip = 
 }
 
 extern "C" int lsdgpu_depth_init_from_gt(lsdgpu_ctx* ctx, int kf_id)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -843,7 +849,7 @@ static int runFillHoles(lsdgpu_ctx* ctx, const int* skip = nullptr)
 }
 
 extern "C" int lsdgpu_depth_set_hypotheses(lsdgpu_ctx* ctx, int kf_id, const lsdgpu_hyp* aos, int reactivated, int do_set_depth)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -865,7 +871,7 @@ extern "C" int lsdgpu_depth_set_hypotheses(lsdgpu_ctx* ctx, int kf_id, const lsd
 }
 
 extern "C" int lsdgpu_depth_download(lsdgpu_ctx* ctx, lsdgpu_hyp* aos_out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     const int n = ctx->w * ctx->h;
     k_hyp_to_aos<<<divUp(n, 256), 256, 0, ctx->stream>>>(ctx->cur, (lsdgpu_hyp*)ctx->dStageF, n);
@@ -877,7 +883,7 @@ extern "C" int lsdgpu_depth_download(lsdgpu_ctx* ctx, lsdgpu_hyp* aos_out)
 }
 
 extern "C" int lsdgpu_depth_download_integral(lsdgpu_ctx* ctx, int32_t* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     k_integral_rows<<<divUp(ctx->h, 64), 64, 0, ctx->stream>>>(ctx->cur, ctx->integral, ctx->w, ctx->h);
     LAUNCH(ctx);
@@ -894,21 +900,31 @@ static void prepareForStereoWith(const lsdgpu_ctx* ctx, const FrameSlot* fr, Ref
     prepareStereoConsts(ctx->cam[0].K, fr->thisToParent, fr->thisToParent + 4, fr->thisToParent[7], rc);
 }
 
-static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
+static int setupObserve(lsdgpu_ctx* ctx, const lsdgpu_ref_desc* refs, int n_refs, FrameSlot* kf)
 {   // DepthMap.cpp:1079-1105
     if (n_refs <= 0 || n_refs > LSD_MAX_REFS) return lsd_fail(ctx, "bad number of reference frames");
     ObserveParams& OP = ctx->hObs;
     OP.nRefs = n_refs;
     OP.byIdSize = 0;
     for (int k = 0; k < n_refs; k++) {
-        FrameSlot* fr = findSlot(ctx, ref_ids[k]);
+        FrameSlot* fr = findSlot(ctx, refs[k].frame_id);
         if (!fr) return lsd_fail(ctx, "unknown reference frame id");
-        if (fr->parentId != kf->id) return lsd_fail(ctx, "reference frame was not tracked on the active keyframe (needs the global pose graph: out of scope)");
         RefConst& rc = OP.refs[k];
-        prepareForStereoWith(ctx, fr, rc);
+        if (refs[k].tracked_on_kf) {
+            // :1096-1097 refToKf = frame->pose->thisToParent_raw
+            if (fr->parentId != kf->id) return lsd_fail(ctx, "reference frame declared tracked_on_kf but its tracking parent is not the active keyframe");
+            prepareForStereoWith(ctx, fr, rc);
+        } else {
+            // :1098-1099 refToKf = activeKeyFrame->getScaledCamToWorld().inverse() * frame->getScaledCamToWorld(): the absolute
+            // poses live in the caller's pose graph (FramePoseStruct / KeyFrameGraph), so the caller hands the product over
+            const double* q = refs[k].refToKf_qts;
+            const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+            if (!(n2 > 0.25 && n2 < 4.0) || !(q[7] > 0)) return lsd_fail(ctx, "reference frame not tracked on the active keyframe: refToKf_qts must hold a unit quaternion and a positive scale");
+            prepareStereoConsts(ctx->cam[0].K, q, q + 4, q[7], rc);
+        }
         rc.initialTrackedResidual = fr->initialTrackedResidual;
         rc.id = fr->id;
-        rc.trackedOnActive = 1;
+        rc.trackedOnActive = refs[k].tracked_on_kf ? 1 : 0;       // gate of the tracking mask, DepthMap.cpp:245 / :322
         rc.image = fr->image[0];
         rc.goodMask = fr->hasGoodMask ? fr->goodMask : nullptr;
         if (k == 0) OP.byIdOffset = fr->id;
@@ -923,11 +939,26 @@ static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSl
     return 0;
 }
 
-static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devParams = false, const int* skip = nullptr)
+// ids only: every frame was tracked on the active keyframe (the common case, SlamSystem.cpp:559-575)
+static int setupObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, FrameSlot* kf)
+{
+    if (n_refs <= 0 || n_refs > LSD_MAX_REFS) return lsd_fail(ctx, "bad number of reference frames");
+    lsdgpu_ref_desc d[LSD_MAX_REFS];
+    memset(d, 0, sizeof(d));
+    for (int k = 0; k < n_refs; k++) {
+        d[k].frame_id = ref_ids[k]; d[k].tracked_on_kf = 1;
+        const FrameSlot* fr = findSlot(ctx, ref_ids[k]);
+        if (fr && fr->parentId != kf->id)
+            return lsd_fail(ctx, "reference frame was not tracked on the active keyframe: pass its refToKf through lsdgpu_depth_update_keyframe_refs");
+    }
+    return setupObserve(ctx, d, n_refs, kf);
+}
+
+static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devParams = false, const int* skip = nullptr, bool hostParamsReady = false)
 {
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "no active keyframe");
-    if (!devParams) {
+    if (!devParams && !hostParamsReady) {
         int r = setupObserve(ctx, ref_ids, n_refs, kf);
         if (r) return r;
     }
@@ -941,23 +972,23 @@ static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devP
 }
 
 extern "C" int lsdgpu_depth_observe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     return runObserve(ctx, ref_ids, n_refs);
 }
 extern "C" int lsdgpu_depth_regularize_fill_holes(lsdgpu_ctx* ctx)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     return runFillHoles(ctx);
 }
 extern "C" int lsdgpu_depth_regularize(lsdgpu_ctx* ctx, int removeOcclusions, int validityTH)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     return runRegularize(ctx, removeOcclusions != 0, validityTH);
 }
 
 extern "C" int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs)
-{   // DepthMap::updateKeyframe :1072-1213
+{ LSD_LOCK(ctx);   // DepthMap::updateKeyframe :1072-1213
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "updateKeyframe: depth map is not valid (no active keyframe)");
@@ -965,6 +996,22 @@ extern "C" int lsdgpu_depth_update_keyframe(lsdgpu_ctx* ctx, const int* ref_ids,
     if (r) return r;
     r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr,      // :1135 + :1143 (+ setDepth :1150-1157 in the same kernel)
                           kf->depthHasBeenUpdatedFlag ? nullptr : kf);
+    if (r) return r;
+    kf->numMappedOnThis++;                                         // :1165
+    return 0;
+}
+
+extern "C" int lsdgpu_depth_update_keyframe_refs(lsdgpu_ctx* ctx, const lsdgpu_ref_desc* refs, int n_refs)
+{ LSD_LOCK(ctx);   // DepthMap::updateKeyframe :1072-1213 with the reference-frame set-up of :1085-1101 spelled out by the caller
+    if (!ctx || !refs) return lsd_fail(ctx, "update_keyframe_refs: null argument");
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    FrameSlot* kf = findSlot(ctx, ctx->activeKf);
+    if (!kf) return lsd_fail(ctx, "updateKeyframe: depth map is not valid (no active keyframe)");
+    int r = setupObserve(ctx, refs, n_refs, kf);
+    if (r) return r;
+    r = runObserve(ctx, nullptr, n_refs, false, nullptr, true);    // :1127 (parameters already in ctx->hObs)
+    if (r) return r;
+    r = runFillRegularize(ctx, VAL_SUM_MIN_FOR_KEEP, nullptr, kf->depthHasBeenUpdatedFlag ? nullptr : kf);
     if (r) return r;
     kf->numMappedOnThis++;                                         // :1165
     return 0;
@@ -1000,7 +1047,7 @@ static int runPropagate(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* nk)
 }
 
 extern "C" int lsdgpu_depth_propagate(lsdgpu_ctx* ctx, int new_kf_id)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     FrameSlot* nk = findSlot(ctx, new_kf_id);
@@ -1009,7 +1056,7 @@ extern "C" int lsdgpu_depth_propagate(lsdgpu_ctx* ctx, int new_kf_id)
 }
 
 extern "C" int lsdgpu_depth_create_keyframe(lsdgpu_ctx* ctx, int new_kf_id, double new_qts[8])
-{   // DepthMap::createKeyFrame :1222-1327
+{ LSD_LOCK(ctx);   // DepthMap::createKeyFrame :1222-1327
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     FrameSlot* nk = findSlot(ctx, new_kf_id);
@@ -1062,7 +1109,7 @@ __global__ void k_seqsum_pack(const float* __restrict__ x, const unsigned char* 
 // the kernels createKeyFrame uses (seqsum.cuh) -- exposed so the bit-exactness of that reproduction can be tested on adversarial
 // inputs (ties, binade crossings, negative / non-finite terms), which real depth maps rarely contain.
 extern "C" int lsdgpu_seq_sum_f32(lsdgpu_ctx* ctx, const float* x, const unsigned char* valid, int n, float* sum, int* count)
-{
+{ LSD_LOCK(ctx);
     if (!ctx || !x || n < 0 || !sum) return lsd_fail(ctx, "seq_sum_f32: bad arguments");
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     if (n == 0) { *sum = 0.f; if (count) *count = 0; return 0; }
@@ -1117,7 +1164,7 @@ static int takeReactivationData(lsdgpu_ctx* ctx, FrameSlot* kf)
 }
 
 extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
-{   // DepthMap::finalizeKeyFrame :1363-1395
+{ LSD_LOCK(ctx);   // DepthMap::finalizeKeyFrame :1363-1395
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, ctx->activeKf);
     if (!kf) return lsd_fail(ctx, "finalizeKeyFrame: depth map is not valid");
@@ -1129,7 +1176,7 @@ extern "C" int lsdgpu_depth_finalize_keyframe(lsdgpu_ctx* ctx)
 extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, const uint8_t* gray, int stage_index,
                                     const double init_qt[7], const lsdgpu_track_settings* s, int mode,
                                     int keyframe_change, lsdgpu_track_result* out, double new_qts[8])
-{
+{ LSD_LOCK(ctx);
     int r = gray ? lsdgpu_frame_upload_u8(ctx, frame_id, gray) : lsdgpu_frame_from_stage(ctx, frame_id, stage_index);
     if (r) return r;
     FrameSlot* kf = findSlot(ctx, kf_id);
@@ -1195,7 +1242,7 @@ extern "C" int lsdgpu_track_and_map(lsdgpu_ctx* ctx, int kf_id, int frame_id, co
 // permaRef tracking
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lsdgpu_frame_set_perma_ref(lsdgpu_ctx* ctx, int kf_id, int* num_points_out)
-{   // Frame::setPermaRef -> reference->makePointCloud(QUICK_KF_CHECK_LVL) + copy (Frame.cpp:149-174, TrackingReference.cpp:96-147)
+{ LSD_LOCK(ctx);   // Frame::setPermaRef -> reference->makePointCloud(QUICK_KF_CHECK_LVL) + copy (Frame.cpp:149-174, TrackingReference.cpp:96-147)
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -1249,7 +1296,7 @@ static int fillPermaItems(lsdgpu_ctx* ctx, int n, const int* kf_ids, const doubl
 }
 
 extern "C" int lsdgpu_perma_overlap_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, const double* refToFrame_qt, float* usage_out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     std::vector<PermaItem> items;
     int r = fillPermaItems(ctx, n, kf_ids, refToFrame_qt, items);
@@ -1266,7 +1313,7 @@ extern "C" int lsdgpu_perma_overlap_batch(lsdgpu_ctx* ctx, int n, const int* kf_
 
 extern "C" int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, int frame_id, const double* refToFrame_init_qt,
                                         lsdgpu_track_result* results)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* fr = findSlot(ctx, frame_id);
     if (!fr) return lsd_fail(ctx, "unknown frame id");
@@ -1389,7 +1436,7 @@ static int sim3Launch(lsdgpu_ctx* ctx, int n, const int* ref_ids, const int* fra
 
 extern "C" int lsdgpu_sim3_eval(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, int level, const double refToFrame_qts[8],
                                 float affine_a, float affine_b, const lsdgpu_track_settings* s, lsdgpu_sim3_eval_result* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     std::vector<Sim3Out> h;
     int r = sim3Launch(ctx, 1, &ref_kf_id, &frame_id, refToFrame_qts, true, level, level, s, 1, affine_a, affine_b, h);
@@ -1407,7 +1454,7 @@ extern "C" int lsdgpu_sim3_eval(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, in
 
 extern "C" int lsdgpu_sim3_track_batch(lsdgpu_ctx* ctx, int n, const int* ref_kf_ids, const int* frame_ids, const double* frameToRef_init_qts,
                                        int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* results)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     std::vector<Sim3Out> h;
     int r = sim3Launch(ctx, n, ref_kf_ids, frame_ids, frameToRef_init_qts, false, start_level, final_level, s, 0, 1.f, 0.f, h);
@@ -1434,7 +1481,7 @@ extern "C" int lsdgpu_sim3_track_batch(lsdgpu_ctx* ctx, int n, const int* ref_kf
 
 extern "C" int lsdgpu_sim3_track(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, const double frameToRef_init_qts[8],
                                  int start_level, int final_level, const lsdgpu_track_settings* s, lsdgpu_sim3_result* out)
-{
+{ LSD_LOCK(ctx);
     return lsdgpu_sim3_track_batch(ctx, 1, &ref_kf_id, &frame_id, frameToRef_init_qts, start_level, final_level, s, out);
 }
 
@@ -1442,7 +1489,7 @@ extern "C" int lsdgpu_sim3_track(lsdgpu_ctx* ctx, int ref_kf_id, int frame_id, c
 // keyframe output formats
 // ------------------------------------------------------------------------------------------------------
 extern "C" int lsdgpu_keyframe_pack_pointcloud(lsdgpu_ctx* ctx, int kf_id, int publish_level, lsdgpu_input_point_dense* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -1460,7 +1507,7 @@ extern "C" int lsdgpu_keyframe_pack_pointcloud(lsdgpu_ctx* ctx, int kf_id, int p
 }
 
 extern "C" int lsdgpu_frame_take_reactivation_data(lsdgpu_ctx* ctx, int kf_id)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -1469,7 +1516,7 @@ extern "C" int lsdgpu_frame_take_reactivation_data(lsdgpu_ctx* ctx, int kf_id)
 }
 
 extern "C" int lsdgpu_frame_download_reactivation_data(lsdgpu_ctx* ctx, int kf_id, float* idepth_reAct, float* idepthVar_reAct, uint8_t* validity_reAct)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -1483,7 +1530,7 @@ extern "C" int lsdgpu_frame_download_reactivation_data(lsdgpu_ctx* ctx, int kf_i
 }
 
 extern "C" int lsdgpu_depth_set_from_existing_kf(lsdgpu_ctx* ctx, int kf_id)
-{   // DepthMap::setFromExistingKF :920-962
+{ LSD_LOCK(ctx);   // DepthMap::setFromExistingKF :920-962
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* kf = findSlot(ctx, kf_id);
     if (!kf) return lsd_fail(ctx, "unknown keyframe id");
@@ -1584,7 +1631,7 @@ extern "C" int lsdgpu_undistorter_validate_tables(int in_width, int in_height, i
 }
 
 extern "C" int lsdgpu_set_undistorter(lsdgpu_ctx* ctx, int in_width, int in_height, const float* remapX, const float* remapY)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     if (in_width <= 0 || in_height <= 0) return lsd_fail(ctx, "bad input size");
     const size_t n = (size_t)ctx->w * ctx->h, nr = (size_t)in_width * in_height;
@@ -1627,7 +1674,7 @@ static int uploadRaw(lsdgpu_ctx* ctx, const uint8_t* raw)
 }
 
 extern "C" int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t* out)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     int r = uploadRaw(ctx, raw);
     if (r) return r;
@@ -1647,7 +1694,7 @@ extern "C" int lsdgpu_undistort_u8(lsdgpu_ctx* ctx, const uint8_t* raw, uint8_t*
 }
 
 extern "C" int lsdgpu_frame_upload_distorted_u8(lsdgpu_ctx* ctx, int frame_id, const uint8_t* raw)
-{
+{ LSD_LOCK(ctx);
     LSD_CHECK(ctx, cudaSetDevice(ctx->device));
     FrameSlot* s = acquireSlot(ctx, frame_id);
     if (!s) return lsd_fail(ctx, "no free frame slot (release frames or raise max_frames)");

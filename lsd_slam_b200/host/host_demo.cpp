@@ -32,6 +32,10 @@ int main(int argc, char** argv)
         return 0;
     }
     const int kfEvery = argc > 2 ? std::atoi(argv[2]) : 0;
+    // "late": after a keyframe change, a frame tracked on the OLD keyframe is mapped on the new one, as the frames still queued
+    // in unmappedTrackedFrames are (SlamSystem.cpp:559-575 -> DepthMap.cpp:1085-1099).  The first frame of the old keyframe is
+    // used: the last one is too close to the new keyframe for the epipolar-length gate (DepthMap.cpp:203).
+    const bool lateMapping = argc > 3 && std::string(argv[3]) == "late";
     FILE* f = std::fopen(argv[1], "rb");
     if (!f) { std::perror("open"); return 2; }
     int w, h, n;
@@ -46,7 +50,8 @@ int main(int argc, char** argv)
         tracker.settings.maxItsPerLvl[4] = 0;                              // SlamSystem.cpp:80-81
         DepthMap map(dev, w, h, K);
         TrackingReference ref;
-        std::shared_ptr<Frame> kf, prev;
+        std::shared_ptr<Frame> kf, prev, early;              // early: first frame tracked on the current keyframe
+        std::vector<std::shared_ptr<Frame>> oldKeyframes;                  // their FramePoseStructs stay in the pose chain
         SE3 last;
         for (int k = 0; k < n; k++) {
             if (std::fread(img.data(), 1, img.size(), f) != img.size()) return 2;
@@ -64,8 +69,14 @@ int main(int argc, char** argv)
             if (kfEvery > 0 && k % kfEvery == 0) {
                 map.finalizeKeyFrame();                                    // :400
                 map.createKeyFrame(fr.get());                              // :473
-                prev.reset();
+                oldKeyframes.push_back(kf);
                 kf = fr;
+                if (lateMapping && early) {
+                    std::deque<std::shared_ptr<Frame>> refs{ early };
+                    map.updateKeyframe(refs);                              // refToKf from the chained absolute poses, :1099
+                }
+                prev.reset();
+                early.reset();
                 last = SE3();
             } else {
                 std::deque<std::shared_ptr<Frame>> refs{ fr };
@@ -73,6 +84,7 @@ int main(int argc, char** argv)
                 fr->clear_refPixelWasGood();                               // :573
                 last = pose;
                 prev = fr;
+                if (!early) early = fr;
             }
         }
         map.invalidate();

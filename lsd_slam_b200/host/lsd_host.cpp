@@ -52,6 +52,35 @@ SE3 SE3::operator*(const SE3& o) const
     return r;
 }
 
+Sim3 Sim3::inverse() const
+{
+    Sim3 r;
+    r.q[0] = -q[0]; r.q[1] = -q[1]; r.q[2] = -q[2]; r.q[3] = q[3];
+    qnorm(r.q);
+    r.s = 1.0 / s;
+    double nt[3] = { -t[0], -t[1], -t[2] }, rt[3];
+    qrot(r.q, nt, rt);
+    for (int i = 0; i < 3; i++) r.t[i] = r.s * rt[i];
+    return r;
+}
+Sim3 Sim3::operator*(const Sim3& o) const
+{
+    Sim3 r;
+    double rt[3];
+    qrot(q, o.t, rt);
+    qmul(q, o.q, r.q);
+    qnorm(r.q);
+    r.s = s * o.s;
+    for (int i = 0; i < 3; i++) r.t[i] = t[i] + s * rt[i];
+    return r;
+}
+Sim3 FramePoseStruct::getCamToWorld(int recursionDepth) const
+{
+    if (recursionDepth >= 5000) throw LsdGpuError("FramePoseStruct::getCamToWorld: assert(recursionDepth < 5000)");
+    if (trackingParent == nullptr) return Sim3();
+    return trackingParent->getCamToWorld(recursionDepth + 1) * thisToParent_raw;
+}
+
 DeviceContext::DeviceContext(int device, int w, int h, const Matrix3f& K, int maxFrames) : w_(w), h_(h)
 {
     int rc = lsdgpu_create(device, w, h, K.m, maxFrames, &ctx_);
@@ -318,12 +347,26 @@ void DepthMap::setFromExistingKF(Frame* kf, const float* idepth, const float* id
 void DepthMap::updateKeyframe(std::deque<std::shared_ptr<Frame>> referenceFrames)
 {
     if (!isValid()) throw LsdGpuError("DepthMap::updateKeyframe: assert(isValid())");
-    std::vector<int> ids;
-    for (auto& f : referenceFrames) ids.push_back(f->id());
+    std::vector<lsdgpu_ref_desc> refs;
+    for (auto& f : referenceFrames) {
+        if (!f->hasTrackingParent()) throw LsdGpuError("DepthMap::updateKeyframe: assert(frame->hasTrackingParent())");   // :1085
+        lsdgpu_ref_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.frame_id = f->id();
+        d.tracked_on_kf = f->pose->trackingParent->frameID == activeKeyFrame->id();                    // :1096
+        if (!d.tracked_on_kf) {
+            // :1087-1099: "tracked on a different frame ... While this should work, it is not recommended."
+            const Sim3 refToKf = activeKeyFrame->getScaledCamToWorld().inverse() * f->getScaledCamToWorld();
+            for (int i = 0; i < 4; i++) d.refToKf_qts[i] = refToKf.q[i];
+            for (int i = 0; i < 3; i++) d.refToKf_qts[4 + i] = refToKf.t[i];
+            d.refToKf_qts[7] = refToKf.s;
+        }
+        refs.push_back(d);
+    }
     // the device keeps its own copy of the counters the skip-ahead logic reads (DepthMap.cpp:454)
     dev_.check(lsdgpu_frame_set_counters(dev_.raw(), activeKeyFrame->id(), activeKeyFrame->numFramesTrackedOnThis, activeKeyFrame->numMappedOnThis),
                "DepthMap::updateKeyframe");
-    dev_.check(lsdgpu_depth_update_keyframe(dev_.raw(), ids.data(), (int)ids.size()), "DepthMap::updateKeyframe");
+    dev_.check(lsdgpu_depth_update_keyframe_refs(dev_.raw(), refs.data(), (int)refs.size()), "DepthMap::updateKeyframe");
     activeKeyFrame->numMappedOnThis++;
     activeKeyFrame->numMappedOnThisTotal++;
 }

@@ -38,6 +38,8 @@ struct Sim3 {
     double q[4] = { 0, 0, 0, 1 };
     double t[3] = { 0, 0, 0 };
     double s = 1.0;
+    Sim3 inverse() const;                            // thirdparty/Sophus/sophus/sim3.hpp:169-173
+    Sim3 operator*(const Sim3& o) const;             // sim3.hpp:257-260
 };
 inline Sim3 sim3FromSE3(const SE3& se3, double scale)     // util/SophusUtil.h:53-58
 {
@@ -82,6 +84,9 @@ struct FramePoseStruct {
     Sim3 thisToParent_raw;
     FramePoseStruct* trackingParent = nullptr;
     int frameID = -1;
+    // FramePoseStruct.cpp:84-105 without the pose-graph members (isOptimized / the cache belong to KeyFrameGraph, out of scope):
+    // identity for the first frame, otherwise the parent's absolute pose times thisToParent_raw
+    Sim3 getCamToWorld(int recursionDepth = 0) const;
 };
 
 // DataStructures/Frame.h -- device-resident frame; host keeps the bookkeeping the callers read
@@ -99,6 +104,7 @@ public:
     double timestamp() const { return timestamp_; }
     void setDepthFromGroundTruth(const float* depth, float cov_scale = 1.0f);      // Frame.cpp:245-293
     bool hasTrackingParent() const { return pose->trackingParent != nullptr; }
+    Sim3 getScaledCamToWorld() const { return pose->getCamToWorld(); }              // Frame.h:276-280
     void clear_refPixelWasGood();                                                   // Frame.h:439
     float meanIdepth();                                                             // Frame.cpp:234 (lazy D2H)
     int numPoints();

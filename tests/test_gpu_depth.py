@@ -207,6 +207,87 @@ def test_propagate_and_create_keyframe(gpu_ctx_small, oracle, seq_small, frames_
     assert np.max(np.abs(idg[both] - ido[both]) / ido[both]) <= 2e-5
 
 
+def _sim3(oracle, fn, *args):
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    out = np.zeros(8, np.float64)
+    arrs = [np.ascontiguousarray(a, np.float64) for a in args]
+    getattr(oracle.lib(), fn)(*[a.ctypes.data_as(dp) for a in arrs], out.ctypes.data_as(dp))
+    return out
+
+
+def test_update_keyframe_with_frames_tracked_on_the_previous_keyframe(gpu_ctx_small, oracle, seq_small, frames_small):
+    """DepthMap.cpp:1085-1099: frames still queued when the keyframe changes were tracked on the OLD keyframe; they are mapped with
+    refToKf = activeKeyFrame->getScaledCamToWorld().inverse() * frame->getScaledCamToWorld() and without their tracking mask
+    (:245, :322).  The caller passes that product in lsdgpu_ref_desc; every field of every pixel equals the oracle's.
+    (Scene rescaled to mean inverse depth 1 on keyframe 0 -- see test_ref_pin.test_create_keyframe_and_finalize_bit_exact.)"""
+    d0 = frames_small[0][1]
+    sc = float(np.mean(1.0 / d0[d0 > 0]))
+    frames = {k: (frames_small[k][0], (frames_small[k][1] * sc).astype(np.float32)) for k in range(13)}
+
+    def qt(k, ref=0):
+        q = seq_small.frame_to_ref_qt(k, ref=ref).copy()
+        q[4:7] *= sc
+        return q
+    p = Pair(gpu_ctx_small, oracle, seq_small, frames, "gt")
+    ctx = gpu_ctx_small
+    for k in (1, 2, 3):
+        of = p.add_frame(k, qt(k))
+        oracle.lib().lsdo_frame_set_depthHasBeenUpdatedFlag(p.okf.ptr, 0)
+        ctx.L.lsdgpu_ref_import(ctx.ptr, 0)
+        p.odm.updateKeyframe([of])
+        p.gdm.updateKeyframe([k])
+    p.compare(exact=True)
+    # frames 4 and 5: TRACKED on keyframe 0 on both sides (so both carry a tracking mask), poses then set to ground truth
+    trk = abi.SE3Tracker(ctx, mode=1)
+    for k in (4, 5):
+        of = p.add_frame(k, qt(k))
+        r = oracle.se3_track(p.okf, of, qt(k))
+        trk.trackFrame(0, k, qt(k))
+        qts = np.concatenate([qt(k), [1.0]])
+        of.set_thisToParent(qts, p.okf)
+        oracle.lib().lsdo_frame_set_initialTrackedResidual(of.ptr, float(r.initialTrackedResidual))
+        ctx.set_pose(k, qts, 0, float(r.initialTrackedResidual))
+        assert of.refPixelWasGood(create=False) is not None
+    ctx.set_counters(0, oracle.lib().lsdo_frame_numFramesTrackedOnThis(p.okf.ptr), oracle.lib().lsdo_frame_numMappedOnThis(p.okf.ptr))
+    # keyframe change to frame 9 (no mask on it: identical inputs -> identical maps, rescale included)
+    of9 = p.add_frame(9, qt(9))
+    p.odm.finalizeKeyFrame()
+    p.gdm.finalizeKeyFrame()
+    p.odm.createKeyFrame(of9)
+    q9 = p.gdm.createKeyFrame(9)
+    assert np.float32(q9[7]).tobytes() == np.float32(of9.thisToParent()[7]).tobytes() and 0.8 < q9[7] < 1.25
+    p.compare(exact=True)
+    # ids only: refused, with a pointer to the descriptor call
+    with pytest.raises(abi.LsdGpuError, match="update_keyframe_refs"):
+        p.gdm.updateKeyframe([4])
+    c2w9 = of9.thisToParent()                                     # keyframe 0 is the first frame: its camToWorld is the identity
+    items = []
+    for k in (4, 5):
+        c2wk = p.oframes[k].thisToParent()
+        items.append((k, _sim3(oracle, "lsdo_sim3d_mul", _sim3(oracle, "lsdo_sim3d_inverse", c2w9), c2wk)))
+    before = p.gdm.current().copy()
+    p.odm.updateKeyframe([p.oframes[4], p.oframes[5]])
+    p.gdm.updateKeyframe(items)
+    rep = p.compare(exact=True)
+    after = p.gdm.current()
+    both = (before["isValid"] != 0) & (after["isValid"] != 0)
+    assert rep["n_valid"] > 10000 and int((before["idepth"][both] != after["idepth"][both]).sum()) > 2000      # they did observe
+    # mixed parents in one call; a frame declared tracked_on_kf whose parent is another keyframe is refused
+    of12 = oracle.Frame(12, frames[12][0], seq_small.K)
+    q12 = np.concatenate([qt(12, ref=9), [1.0]])
+    q12[4:7] /= q9[7]
+    of12.set_thisToParent(q12, of9)
+    ctx.upload(12, frames[12][0])
+    ctx.set_pose(12, q12, 9, 0.0)
+    p.odm.updateKeyframe([p.oframes[5], of12])
+    p.gdm.updateKeyframe([items[1], 12])
+    p.compare(exact=True)
+    descs = (abi.RefDesc * 1)()
+    descs[0].frame_id, descs[0].tracked_on_kf = 4, 1
+    assert ctx.L.lsdgpu_depth_update_keyframe_refs(ctx.ptr, descs, 1) != 0
+
+
 def test_finalize_keyframe(gpu_ctx_small, oracle, seq_small, frames_small):
     p = Pair(gpu_ctx_small, oracle, seq_small, frames_small, "random")
     p.odm.finalizeKeyFrame()

@@ -51,6 +51,87 @@ def test_host_demo_matches_python_loop(tmp_path, seq_small, frames_small):
     ctx.close()
 
 
+def _qmul(a, b):
+    x1, y1, z1, w1 = a
+    x2, y2, z2, w2 = b
+    return np.array([w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2, w1 * y2 + y1 * w2 + z1 * x2 - x1 * z2,
+                     w1 * z2 + z1 * w2 + x1 * y2 - y1 * x2, w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2])
+
+
+def _qrot(q, v):
+    qv = np.array([v[0], v[1], v[2], 0.0])
+    qc = np.array([-q[0], -q[1], -q[2], q[3]])
+    return _qmul(_qmul(q, qv), qc)[:3]
+
+
+def _sim3_inv(a):
+    qi = np.array([-a[0], -a[1], -a[2], a[3]])
+    s = 1.0 / a[7]
+    return np.concatenate([qi, s * _qrot(qi, -a[4:7]), [s]])
+
+
+def _sim3_mul(a, b):
+    q = _qmul(a[:4], b[:4])
+    return np.concatenate([q / np.linalg.norm(q), a[4:7] + a[7] * _qrot(a[:4], b[4:7]), [a[7] * b[7]]])
+
+
+@pytest.mark.gpu
+def test_host_classes_map_a_frame_tracked_on_the_previous_keyframe(tmp_path, seq_small, frames_small):
+    """DepthMap::updateKeyframe of the C++ adapter with a frame whose tracking parent is the OLD keyframe: the adapter chains
+    FramePoseStruct::getCamToWorld (FramePoseStruct.cpp:84-105) into refToKf (DepthMap.cpp:1099) and hands it to
+    lsdgpu_depth_update_keyframe_refs; the same loop through the Python mirror gives the same poses afterwards"""
+    from lsd_slam_b200 import abi, build
+    build.build_host()
+    n, kf_every = 12, 5
+    d0 = frames_small[0][1]
+    depth0 = (d0 * float(np.mean(1.0 / d0[d0 > 0]))).astype(np.float32)   # mean inverse depth 1: no scale jump at the keyframe change
+    path = tmp_path / "frames.bin"
+    with open(path, "wb") as f:
+        np.array([seq_small.w, seq_small.h, n], np.int32).tofile(f)
+        seq_small.K.astype(np.float32).tofile(f)
+        depth0.tofile(f)
+        for k in range(n):
+            frames_small[k][0].tofile(f)
+    rows = {}
+    for late in (False, True):
+        r = subprocess.run([build.DEMO_OUT, str(path), str(kf_every)] + (["late"] if late else []), capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        rows[late] = np.array([[float(x) for x in ln.split()] for ln in r.stdout.strip().splitlines()])
+    assert np.abs(rows[True][6:, 1:8] - rows[False][6:, 1:8]).max() > 1e-7          # the extra mapping step changed the map
+    ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, max_frames=12)
+    trk, dm = abi.SE3Tracker(ctx, mode=1), abi.DepthMap(ctx)
+    trk.settings.maxItsPerLvl[4] = 0
+    ctx.upload(0, frames_small[0][0])
+    ctx.set_depth_gt(0, depth0)
+    dm.initializeFromGTDepth(0)
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float64)
+    kf, early, last, poses = 0, None, ident, []
+    cam_to_world = {0: np.array([0, 0, 0, 1, 0, 0, 0, 1.0])}
+    for k in range(1, n):
+        ctx.upload(k, frames_small[k][0])
+        if ctx.depth_updated_flag(kf):
+            trk.importFrame(kf)
+        pose = np.array(trk.trackFrame(kf, k, last))
+        poses.append(pose)
+        cam_to_world[k] = _sim3_mul(cam_to_world[kf], np.concatenate([pose, [1.0]]))
+        if k % kf_every == 0:
+            dm.finalizeKeyFrame()
+            q = dm.createKeyFrame(k)
+            cam_to_world[k] = _sim3_mul(cam_to_world[kf], q)
+            kf, last = k, ident
+            if early is not None:
+                dm.updateKeyframe([(early, _sim3_mul(_sim3_inv(cam_to_world[kf]), cam_to_world[early]))])
+            early = None
+        else:
+            dm.updateKeyframe([k])
+            ctx.clear_good_mask(k)
+            last = pose
+            if early is None:
+                early = k
+    ctx.close()
+    assert np.allclose(rows[True][:, 1:8], np.array(poses), atol=1e-9), np.abs(rows[True][:, 1:8] - np.array(poses)).max()
+
+
 def test_undistorter_config_file_parsing(tmp_path, oracle):
     """lsd_slam::UndistorterPTAM(configFileName) of the C++ adapter (util/Undistorter.cpp:100-166) -- host-only, no GPU --
     against the oracle's tables for the same four lines"""

@@ -202,27 +202,58 @@ def test_depthmap_individual_passes_bit_exact(seq_small, frames_small):
 
 def test_create_keyframe_and_finalize_bit_exact(seq_small, frames_small):
     """finalizeKeyFrame + createKeyFrame (propagateDepth with the tracking mask, 2x regularise, fill holes, rescale,
-    pose scale) -- DepthMap.cpp:475-653, 1222-1327, 1363-1395; then mapping continues on the new keyframe"""
-    t = Twin(seq_small, frames_small, "gt")
+    pose scale) -- DepthMap.cpp:475-653, 1222-1327, 1363-1395; then mapping continues on the new keyframe, including with
+    frames that were tracked on the PREVIOUS keyframe (:1085-1099).
+    The scene is rescaled so that keyframe 0 already has mean inverse depth 1, as every keyframe after the first has in a real
+    run: doLineStereo only accepts a reference frame whose depth ratio to the keyframe is within 0.7..1.4 (:119 `rescaleFactor`),
+    so with a 2x scale jump between keyframes the off-parent frames would be rejected pixel by pixel and test nothing."""
+    d0 = frames_small[0][1]
+    sc = float(np.mean(1.0 / d0[d0 > 0]))
+    frames = {k: (frames_small[k][0], (frames_small[k][1] * sc).astype(np.float32)) for k in range(13)}
+
+    def qts(k, ref=0):
+        q = seq_small.frame_to_ref_qt(k, ref=ref).copy()
+        q[4:7] *= sc
+        return np.concatenate([q, [1.0]])
+    t = Twin(seq_small, frames, "gt")
     rng = np.random.default_rng(3)
     w1, h1 = seq_small.w // 2, seq_small.h // 2
     for k in (1, 2, 3):
-        t.add_frame(k, _gt_qts(seq_small, k), itr=0.1)
+        t.add_frame(k, qts(k), itr=0.1)
         t.call(lambda dm, fr, fl: dm.updateKeyframe([fr[k]]))
     t.check("before finalize")
     t.call(lambda dm, fr, fl: dm.finalizeKeyFrame())
     t.check("finalizeKeyFrame")
     mask = (rng.random((h1, w1)) > 0.1).astype(np.uint8)
-    t.add_frame(6, _gt_qts(seq_small, 6), itr=0.1, mask=mask)
-    t.call(lambda dm, fr, fl: dm.createKeyFrame(fr[6]))
+    t.add_frame(9, qts(9), itr=0.1, mask=mask)
+    t.call(lambda dm, fr, fl: dm.createKeyFrame(fr[9]))
     t.check("createKeyFrame")
-    pa, pb = (t.fr[fl][6].thisToParent() for fl in t.fl)          # rescaled Sim3 (DepthMap.cpp:1305)
+    pa, pb = (t.fr[fl][9].thisToParent() for fl in t.fl)          # rescaled Sim3 (DepthMap.cpp:1305)
     assert np.allclose(pa, pb, rtol=0, atol=1e-12), pa - pb
+    assert 0.8 < pa[7] < 1.25
+    # frames tracked on the PREVIOUS keyframe, mapped on the new one: refToKf comes from the chained absolute poses (:1099), and the
+    # tracking-mask gate of :245 / :322 is off for them
+    for k in (4, 5):
+        t.add_frame(k, qts(k), itr=0.07, mask=mask, parent=0)
+    before = t.dm[False].current().copy()
+    t.call(lambda dm, fr, fl: dm.updateKeyframe([fr[4], fr[5]]))
+    n = t.check("updateKeyframe with frames tracked on the previous keyframe")
+    after = t.dm[False].current()
+    both = (before["isValid"] != 0) & (after["isValid"] != 0)
+    assert n > 10000 and int((before["idepth"][both] != after["idepth"][both]).sum()) > 2000     # they did observe
     # frames tracked on the NEW keyframe
-    for k in (7, 8):
-        t.add_frame(k, np.concatenate([seq_small.frame_to_ref_qt(k, ref=6), [1.0]]), itr=0.1, parent=6)
+    for k in (10, 11):
+        q = qts(k, ref=9)
+        q[4:7] /= pa[7]                                           # the new keyframe's units
+        t.add_frame(k, q, itr=0.1, parent=9)
         t.call(lambda dm, fr, fl: dm.updateKeyframe([fr[k]]))
         t.check(f"updateKeyframe on new keyframe [{k}]")
+    q = qts(12, ref=9)
+    q[4:7] /= pa[7]
+    t.add_frame(12, q, itr=0.1, parent=9)
+    t.add_frame(6, qts(6), itr=0.05, mask=mask, parent=0)
+    t.call(lambda dm, fr, fl: dm.updateKeyframe([fr[6], fr[12]]))           # mixed parents in one call
+    t.check("updateKeyframe with mixed tracking parents")
 
 
 def test_se3_single_evaluation_matches_reference_compiled(seq_small, frames_small):
