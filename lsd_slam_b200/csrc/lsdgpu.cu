@@ -180,6 +180,11 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hScalars, 64, cudaHostAllocDefault));
     // the tracker writes its result block straight into mapped pinned memory (no D2H copy on the path)
     LSD_CHECK(ctx, cudaHostAlloc((void**)&ctx->hTrackState, sizeof(TrackState), cudaHostAllocMapped));
+    // cudaHostAlloc does not clear: a recycled block may still hold the result of a destroyed context, whose doneSeq would satisfy
+    // the completion spin of this context's first launches (trackPersistentFinish) before the kernel has written anything
+    memset(ctx->hTrackState, 0, sizeof(TrackState));
+    memset(ctx->hScalars, 0, 64);
+    memset(ctx->hEvOut, 0, EV_NCH * 4);
     LSD_CHECK(ctx, cudaHostGetDevicePointer(&ctx->dTrackStateMapped, ctx->hTrackState, 0));
     for (int i = 0; i < 8; i++) {
         LSD_CHECK(ctx, cudaEventCreate(&ctx->tBegin[i]));

@@ -136,3 +136,25 @@ def test_tracker_modes_and_parity_hook_interleave_on_one_context(gpu_ctx_small, 
         assert c == (list(r.numCalcResidualCalls), list(r.numCalcWarpUpdateCalls))
     assert np.array_equal(poses[0], poses[2]) and np.array_equal(poses[2], poses[3])      # mode 1 is deterministic across the interleaving
     assert np.array_equal(poses[1], poses[4])
+
+
+def test_new_context_never_sees_the_result_block_of_a_destroyed_one(seq_small, frames_small):
+    """The device-resident tracker publishes its result in mapped pinned memory and the host polls a sequence number there.
+    Pinned blocks are recycled uncleared by the driver: a fresh context must not take the (matching) sequence number left by a
+    destroyed context for the completion of its own first launch.  Contexts come and go while another one stays alive (which is
+    what shifted the allocator into handing the same block out again when this was found)."""
+    def one(k, keep=False):
+        ctx = abi.Context(seq_small.w, seq_small.h, seq_small.K, device=0, max_frames=6)
+        ctx.upload(0, frames_small[0][0])
+        ctx.set_depth_gt(0, frames_small[0][1])
+        ctx.upload(k, frames_small[k][0])
+        first = np.array(abi.SE3Tracker(ctx, mode=1).trackFrame(0, k, IDENT))        # launch number 1 of this context
+        host = np.array(abi.SE3Tracker(ctx, mode=0).trackFrame(0, k, IDENT))          # host-driven LM, stream-synchronised
+        if not keep:
+            ctx.close()
+        return first, host, ctx
+    _, _, alive = one(1, keep=True)
+    for k in (1, 3, 8, 2, 6, 1, 8):
+        first, host, _ = one(k)
+        assert pose_err(first, host)[0] <= 1e-4, k
+    alive.close()
