@@ -723,7 +723,8 @@ __global__ void __launch_bounds__(256) k_set_depth(HypField cur, float* __restri
 // running them one after the other; it saves two launches and two round trips of the 9.8 MB hypothesis planes.
 #define FR_TW 32
 #define FR_TH 16
-#define FR_THREADS (FR_TW * FR_TH)
+#define FR_PPT 2                          // pixels per thread in the regularise stage: all CTAs resident in ONE wave
+#define FR_THREADS (FR_TW * FR_TH / FR_PPT)
 template <bool SETDEPTH>
 __global__ void __launch_bounds__(FR_THREADS) k_fill_regularize(HypField src, HypField dst, DepthCam cam, DepthGlobals G,
                                                                 const float* __restrict__ kfMaxGrad, int validityTH,
@@ -789,96 +790,122 @@ __global__ void __launch_bounds__(FR_THREADS) k_fill_regularize(HypField src, Hy
         sCreated[ly][lx] = created;
     }
     __syncthreads();
-    // stage 3: regularizeDepthMapRow<false> on the tile
-    const int tx = threadIdx.x % FR_TW, ty = threadIdx.x / FR_TW;
-    const int x = bx * FR_TW + tx, y = by * FR_TH + ty;
-    const bool inside = x < width && y < height;
-    const int idx = x + y * width;
-    float4 hf = make_float4(0.f, 0.f, 0.f, 0.f);
-    int4 hi = make_int4(0, 0, 0, 0);
-    if (inside) {
-        if (sCreated[ty + 2][tx + 2]) {  // fresh DepthMapPixelHypothesis(idepth, var, 0): blacklisted = 0, smoothed = -1
-            const float4 c = sB[ty + 2][tx + 2];
-            hf = make_float4(c.x, c.y, -1.f, -1.f);
-            hi = make_int4(1, 0, 0, __float_as_int(0.f));
-        } else {
-            hf = src.hf[idx];
-            hi = src.hi[idx];
-        }
-        if (x >= 2 && x < width - 2 && y >= 2 && y < height - 2 && hi.x) {
-            const float regDistVar = G.regDistVar;
-            float sum = 0, val_sum = 0, sumIvar = 0;
-            for (int dx = -2; dx <= 2; dx++)             // dx outer, dy inner as in the reference (:782-783)
-                for (int dy = -2; dy <= 2; dy++) {
-                    const float4 q = sB[ty + 2 + dy][tx + 2 + dx];
-                    if (!__float_as_int(q.w)) continue;
-                    const float diff = q.x - hf.x;
-                    if (DIFF_FAC_SMOOTHING * diff * diff > q.y + hf.y) continue;
-                    val_sum += __float_as_int(q.z);
-                    const float distFac = (float)(dx * dx + dy * dy) * regDistVar;
-                    const float ivar = 1.0f / (q.y + distFac);
-                    sum += q.x * ivar;
-                    sumIvar += ivar;
-                }
-            if (val_sum < validityTH) {
-                hi.x = 0;
-                hi.y--;
+    // stage 3: regularizeDepthMapRow<false> on the tile; a thread owns the pixels (tx, ty) and (tx, ty + FR_TH/2)
+    const int tx = threadIdx.x % FR_TW, ty0 = threadIdx.x / FR_TW;
+    float2 vOut[FR_PPT];
+    double ssum = 0.0;
+    int scnt = 0;
+#pragma unroll
+    for (int pp = 0; pp < FR_PPT; pp++) {
+        const int ty = ty0 + pp * (FR_TH / FR_PPT);
+        const int x = bx * FR_TW + tx, y = by * FR_TH + ty;
+        const bool inside = x < width && y < height;
+        const int idx = x + y * width;
+        float4 hf = make_float4(0.f, 0.f, 0.f, 0.f);
+        int4 hi = make_int4(0, 0, 0, 0);
+        if (inside) {
+            if (sCreated[ty + 2][tx + 2]) {  // fresh DepthMapPixelHypothesis(idepth, var, 0): blacklisted = 0, smoothed = -1
+                const float4 c = sB[ty + 2][tx + 2];
+                hf = make_float4(c.x, c.y, -1.f, -1.f);
+                hi = make_int4(1, 0, 0, __float_as_int(0.f));
             } else {
-                sum = sum / sumIvar;
-                sum = unzero_f(sum);
-                hf.z = sum;
-                hf.w = 1.0f / sumIvar;
+                hf = src.hf[idx];
+                hi = src.hi[idx];
             }
+            if (x >= 2 && x < width - 2 && y >= 2 && y < height - 2 && hi.x) {
+                const float regDistVar = G.regDistVar;
+                float sum = 0, val_sum = 0, sumIvar = 0;
+                for (int dx = -2; dx <= 2; dx++)             // dx outer, dy inner as in the reference (:782-783)
+                    for (int dy = -2; dy <= 2; dy++) {
+                        const float4 q = sB[ty + 2 + dy][tx + 2 + dx];
+                        if (!__float_as_int(q.w)) continue;
+                        const float diff = q.x - hf.x;
+                        if (DIFF_FAC_SMOOTHING * diff * diff > q.y + hf.y) continue;
+                        val_sum += __float_as_int(q.z);
+                        const float distFac = (float)(dx * dx + dy * dy) * regDistVar;
+                        const float ivar = 1.0f / (q.y + distFac);
+                        sum += q.x * ivar;
+                        sumIvar += ivar;
+                    }
+                if (val_sum < validityTH) {
+                    hi.x = 0;
+                    hi.y--;
+                } else {
+                    sum = sum / sumIvar;
+                    sum = unzero_f(sum);
+                    hf.z = sum;
+                    hf.w = 1.0f / sumIvar;
+                }
+            }
+            dst.hf[idx] = hf;
+            dst.hi[idx] = hi;
         }
-        dst.hf[idx] = hf;
-        dst.hi[idx] = hi;
+        if (SETDEPTH) {
+            // Frame::setDepth (Frame.cpp:217-232): level-0 idepth / idepthVar and the frame's sum / count
+            float2 v = make_float2(-1.f, -1.f);
+            if (inside && hi.x && hf.z >= -0.05) { v = make_float2(hf.z, hf.w); ssum += (double)hf.z; scnt++; }
+            if (inside) { id.l[0][idx] = v.x; var.l[0][idx] = v.y; }
+            vOut[pp] = v;
+        }
     }
     if (!SETDEPTH) return;
-    // stage 4: Frame::setDepth (Frame.cpp:217-232) + idepth pyramid blocks of this tile + ordered sum / count
+    // stage 4: idepth pyramid blocks of this tile (Frame::buildIDepthAndIDepthVar, Frame.cpp:775-877) + ordered sum / count
     float2* t0 = reinterpret_cast<float2*>(&sA[0][0]);          // sA is dead: reuse it for the pyramid staging
     float2* t1 = t0 + FR_TW * FR_TH;
     float2* t2 = t1 + (FR_TW / 2) * (FR_TH / 2);
     float2* t3 = t2 + (FR_TW / 4) * (FR_TH / 4);
     __syncthreads();
-    double ssum = 0.0;
-    int scnt = 0;
-    float2 v = make_float2(-1.f, -1.f);
-    if (inside && hi.x && hf.z >= -0.05) { v = make_float2(hf.z, hf.w); ssum = hf.z; scnt = 1; }
-    if (inside) { id.l[0][idx] = v.x; var.l[0][idx] = v.y; }
-    t0[ty * FR_TW + tx] = v;
+#pragma unroll
+    for (int pp = 0; pp < FR_PPT; pp++) t0[(ty0 + pp * (FR_TH / FR_PPT)) * FR_TW + tx] = vOut[pp];
     __syncthreads();
-    if (tx < FR_TW / 2 && ty < FR_TH / 2) {
-        const float2 r = mergeIdepth4(t0[(2 * ty) * FR_TW + 2 * tx], t0[(2 * ty) * FR_TW + 2 * tx + 1],
-                                      t0[(2 * ty + 1) * FR_TW + 2 * tx], t0[(2 * ty + 1) * FR_TW + 2 * tx + 1]);
-        t1[ty * (FR_TW / 2) + tx] = r;
-        const int ox = bx * (FR_TW / 2) + tx, oy = by * (FR_TH / 2) + ty;
-        if (ox < (width >> 1) && oy < (height >> 1)) { id.l[1][oy * (width >> 1) + ox] = r.x; var.l[1][oy * (width >> 1) + ox] = r.y; }
+    {
+        const int t = threadIdx.x;                               // (FR_TW/2) x (FR_TH/2) = 128 outputs
+        if (t < (FR_TW / 2) * (FR_TH / 2)) {
+            const int px = t % (FR_TW / 2), py = t / (FR_TW / 2);
+            const float2 r = mergeIdepth4(t0[(2 * py) * FR_TW + 2 * px], t0[(2 * py) * FR_TW + 2 * px + 1],
+                                          t0[(2 * py + 1) * FR_TW + 2 * px], t0[(2 * py + 1) * FR_TW + 2 * px + 1]);
+            t1[py * (FR_TW / 2) + px] = r;
+            const int ox = bx * (FR_TW / 2) + px, oy = by * (FR_TH / 2) + py;
+            if (ox < (width >> 1) && oy < (height >> 1)) { id.l[1][oy * (width >> 1) + ox] = r.x; var.l[1][oy * (width >> 1) + ox] = r.y; }
+        }
     }
     __syncthreads();
-    if (tx < FR_TW / 4 && ty < FR_TH / 4) {
-        const int W1 = FR_TW / 2;
-        const float2 r = mergeIdepth4(t1[(2 * ty) * W1 + 2 * tx], t1[(2 * ty) * W1 + 2 * tx + 1],
-                                      t1[(2 * ty + 1) * W1 + 2 * tx], t1[(2 * ty + 1) * W1 + 2 * tx + 1]);
-        t2[ty * (FR_TW / 4) + tx] = r;
-        const int ox = bx * (FR_TW / 4) + tx, oy = by * (FR_TH / 4) + ty;
-        if (ox < (width >> 2) && oy < (height >> 2)) { id.l[2][oy * (width >> 2) + ox] = r.x; var.l[2][oy * (width >> 2) + ox] = r.y; }
+    {
+        const int t = threadIdx.x;
+        if (t < (FR_TW / 4) * (FR_TH / 4)) {
+            const int W1 = FR_TW / 2;
+            const int px = t % (FR_TW / 4), py = t / (FR_TW / 4);
+            const float2 r = mergeIdepth4(t1[(2 * py) * W1 + 2 * px], t1[(2 * py) * W1 + 2 * px + 1],
+                                          t1[(2 * py + 1) * W1 + 2 * px], t1[(2 * py + 1) * W1 + 2 * px + 1]);
+            t2[py * (FR_TW / 4) + px] = r;
+            const int ox = bx * (FR_TW / 4) + px, oy = by * (FR_TH / 4) + py;
+            if (ox < (width >> 2) && oy < (height >> 2)) { id.l[2][oy * (width >> 2) + ox] = r.x; var.l[2][oy * (width >> 2) + ox] = r.y; }
+        }
     }
     __syncthreads();
-    if (tx < FR_TW / 8 && ty < FR_TH / 8) {
-        const int W2 = FR_TW / 4;
-        const float2 r = mergeIdepth4(t2[(2 * ty) * W2 + 2 * tx], t2[(2 * ty) * W2 + 2 * tx + 1],
-                                      t2[(2 * ty + 1) * W2 + 2 * tx], t2[(2 * ty + 1) * W2 + 2 * tx + 1]);
-        t3[ty * (FR_TW / 8) + tx] = r;
-        const int ox = bx * (FR_TW / 8) + tx, oy = by * (FR_TH / 8) + ty;
-        if (ox < (width >> 3) && oy < (height >> 3)) { id.l[3][oy * (width >> 3) + ox] = r.x; var.l[3][oy * (width >> 3) + ox] = r.y; }
+    {
+        const int t = threadIdx.x;
+        if (t < (FR_TW / 8) * (FR_TH / 8)) {
+            const int W2 = FR_TW / 4;
+            const int px = t % (FR_TW / 8), py = t / (FR_TW / 8);
+            const float2 r = mergeIdepth4(t2[(2 * py) * W2 + 2 * px], t2[(2 * py) * W2 + 2 * px + 1],
+                                          t2[(2 * py + 1) * W2 + 2 * px], t2[(2 * py + 1) * W2 + 2 * px + 1]);
+            t3[py * (FR_TW / 8) + px] = r;
+            const int ox = bx * (FR_TW / 8) + px, oy = by * (FR_TH / 8) + py;
+            if (ox < (width >> 3) && oy < (height >> 3)) { id.l[3][oy * (width >> 3) + ox] = r.x; var.l[3][oy * (width >> 3) + ox] = r.y; }
+        }
     }
     __syncthreads();
-    if (tx < FR_TW / 16 && ty < FR_TH / 16) {
-        const int W3 = FR_TW / 8;
-        const float2 r = mergeIdepth4(t3[(2 * ty) * W3 + 2 * tx], t3[(2 * ty) * W3 + 2 * tx + 1],
-                                      t3[(2 * ty + 1) * W3 + 2 * tx], t3[(2 * ty + 1) * W3 + 2 * tx + 1]);
-        const int ox = bx * (FR_TW / 16) + tx, oy = by * (FR_TH / 16) + ty;
-        if (ox < (width >> 4) && oy < (height >> 4)) { id.l[4][oy * (width >> 4) + ox] = r.x; var.l[4][oy * (width >> 4) + ox] = r.y; }
+    {
+        const int t = threadIdx.x;
+        if (t < (FR_TW / 16) * (FR_TH / 16)) {
+            const int W3 = FR_TW / 8;
+            const int px = t % (FR_TW / 16), py = t / (FR_TW / 16);
+            const float2 r = mergeIdepth4(t3[(2 * py) * W3 + 2 * px], t3[(2 * py) * W3 + 2 * px + 1],
+                                          t3[(2 * py + 1) * W3 + 2 * px], t3[(2 * py + 1) * W3 + 2 * px + 1]);
+            const int ox = bx * (FR_TW / 16) + px, oy = by * (FR_TH / 16) + py;
+            if (ox < (width >> 4) && oy < (height >> 4)) { id.l[4][oy * (width >> 4) + ox] = r.x; var.l[4][oy * (width >> 4) + ox] = r.y; }
+        }
     }
     finishSumCount(ssum, scnt, partials, counter, statsOut);
 }

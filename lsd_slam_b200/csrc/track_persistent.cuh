@@ -246,7 +246,7 @@ struct WarpWindow {
 
 // One pass: nPose candidate poses over this CTA's chunks of level `lvl`, CTA reduction, one row per CTA through L2 behind ONE
 // grid barrier, then every CTA sums the rows in block order.  On return sh.sums holds the totals, bit-identical in every CTA.
-__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCHX], double (*comb)[TP_ROW],
+__device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCHX], float (*comb)[TP_ROW],
                                              unsigned int& epoch, long long* cyc, WarpWindow& W)
 {
     long long t0 = clock64();
@@ -387,36 +387,43 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
     long long t2 = clock64();
     gridBarrier(p.sync, p.barrierBase[0] + epoch * gridDim.x);
     long long t3 = clock64();
-    // warp wi adds rows wi, wi+16, ... (<= 10) in row order, lane = channel (and channel 32 + lane): every load is one full
-    // line, all of them in flight before the first add; the 16 per-warp partial sums are then added in warp order.  Double
-    // throughout: every CTA executes the same additions in the same order, so the totals are bit-identical everywhere.
+    // warp wi adds rows wi, wi+16, ... (<= 10): the lower half-warp takes the even ones of those, the upper half the odd ones, each
+    // lane one float4 (4 channels) of a 256-byte row -- 5 vector loads per thread, all in flight before the first add.  fp32 adds
+    // in a fixed order (rows ascending per half-warp, then upper half onto lower, then the 16 warps in order): every CTA executes
+    // the same additions in the same order on the same data, so the totals are bit-identical everywhere, and the sums stay in
+    // the precision the per-point accumulators and the reference's own (sequential fp32) sums have.
     {
         const int nb = (int)gridDim.x;
-        const bool hi = (32 + lane) < nch;
-        float v0[TP_MAXGRID / TP_WARPS], v1[TP_MAXGRID / TP_WARPS];
+        const int half = lane >> 4, q = lane & 15;
+        constexpr int NR = (TP_MAXGRID / TP_WARPS + 1) / 2;
+        float4 v[NR];
 #pragma unroll
-        for (int r = 0; r < TP_MAXGRID / TP_WARPS; r++) {
-            const int row = warp + r * TP_WARPS;
-            const bool ok = row < nb;
-            v0[r] = ok ? __ldcg(part + (size_t)row * TP_ROW + lane) : 0.f;
-            v1[r] = (ok && hi) ? __ldcg(part + (size_t)row * TP_ROW + 32 + lane) : 0.f;
+        for (int r = 0; r < NR; r++) {
+            const int row = warp + (2 * r + half) * TP_WARPS;
+            v[r] = (row < nb) ? __ldcg(reinterpret_cast<const float4*>(part + (size_t)row * TP_ROW) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        double a0 = 0.0, a1 = 0.0;
+        float4 a = v[0];
 #pragma unroll
-        for (int r = 0; r < TP_MAXGRID / TP_WARPS; r++) { a0 += (double)v0[r]; a1 += (double)v1[r]; }
-        comb[warp][lane] = a0;
-        comb[warp][32 + lane] = a1;
+        for (int r = 1; r < NR; r++) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+        a.x += __shfl_down_sync(0xffffffffu, a.x, 16);
+        a.y += __shfl_down_sync(0xffffffffu, a.y, 16);
+        a.z += __shfl_down_sync(0xffffffffu, a.z, 16);
+        a.w += __shfl_down_sync(0xffffffffu, a.w, 16);
+        if (half == 0) reinterpret_cast<float4*>(&comb[warp][0])[q] = a;
     }
+    long long t3a = clock64();
     __syncthreads();
+    long long t3b = clock64();
     if (threadIdx.x < nch) {
-        double t = 0.0;
+        float t = comb[0][threadIdx.x];
 #pragma unroll
-        for (int wi = 0; wi < TP_WARPS; wi++) t += comb[wi][threadIdx.x];
-        sh.sums[threadIdx.x] = (float)t;
+        for (int wi = 1; wi < TP_WARPS; wi++) t += comb[wi][threadIdx.x];
+        sh.sums[threadIdx.x] = t;
     }
     __syncthreads();
     long long t4 = clock64();
     cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
+    cyc[4] += t3a - t3; cyc[5] += t3b - t3a;       // TEMP: combine sub-phases (overwritten at the end unless debug)
 }
 
 // Fully unrolled, register-resident LDL^T (no pivoting) for the damped 6x6 normal equations.  Returns false if
@@ -732,7 +739,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     __shared__ alignas(LMState) unsigned char lmStorage[sizeof(LMState)];     // every field is written before use; no constructor in shared memory
     LMState& lm = *reinterpret_cast<LMState*>(lmStorage);
     __shared__ float sm[TP_WARPS][EV_NCHX];
-    __shared__ double comb[TP_WARPS][TP_ROW];                      // per-warp partial sums of the combine
+    __shared__ __align__(16) float comb[TP_WARPS][TP_ROW];         // per-warp partial sums of the combine
     static_assert(EV_NCH == 40 && EV_NX == 16, "warpReduceAcc / warpReduceExt are written for 32 + 8 (+ 16) channels");
     extern __shared__ __align__(128) unsigned char winSmem[];      // TP_WARPS windows of TRK_WIN_H x TRK_WIN_W float4
     __shared__ __align__(8) uint64_t winBar[TP_WARPS];
@@ -835,6 +842,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         outDev->lastResidual = lm.last_residual; outDev->diverged = lm.diverged;
         if (p.doPrepare)
             devicePrepareObserve(lm.refToFrame, lm.diverged, lm.last_residual, ev.pointUsage, ev.goodCount, ev.badCount, p.prep, p.obsOut, p.skipOut);
+        if (p.debug) printf("[combine] loads+adds=%lld  sync=%lld\n", cyc[4], cyc[5]);
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
