@@ -48,6 +48,27 @@ struct EvalConsts {
     float cameraPixelNoise2, var_weight, huber_half;
 };
 
+// Rows 3 and 4 of the Jacobian carry double literals in the reference (SE3Tracker.cpp:1284-1285):
+//     v[3] = (-Wx*Wy*z_sqr)*gx + (-(1.0 + Wy*Wy*z_sqr))*gy          -> (float)((double)a + (-(1.0 + (double)b)) * (double)g)
+// i.e. the float nearest to  a - g - b*g  (a, b, g floats), computed through two 53-bit roundings.  FP64 issues at a small
+// fraction of the FP32 rate on B200 (the tracker's fp64 combine cost 2 200 cycles per pass), so the value is
+// formed from error-free float transformations instead: b*g = ph + pl exactly (FMA), two TwoSums carry the rounding errors
+// of a - g - ph, and one last add rounds once.  The result is the correctly rounded float of the exact expression; it can
+// differ from the reference's doubly rounded one only when the exact value lies within 2^-29 ulp of a rounding boundary
+// (about once in 10^8 points, one ulp of one Jacobian entry).
+__device__ __forceinline__ float jacRowMixed(float a, float b, float g)
+{
+    const float ph = b * g;
+    const float pl = fmaf(b, g, -ph);
+    const float s = a - g;
+    const float sv = s - a;
+    const float se = (a - (s - sv)) + (-g - sv);
+    const float t = s - ph;
+    const float tv = t - s;
+    const float te = (s - (t - tv)) + (-ph - tv);
+    return t + ((se + te) - pl);
+}
+
 struct PointAcc {
     float v[EV_NCH];
 };
@@ -126,8 +147,8 @@ __device__ __forceinline__ int evalPoint(float px, float py, float pz, float col
     J[0] = z * gx + 0;
     J[1] = 0 + z * gy;
     J[2] = (-Wx * z_sqr) * gx + (-Wy * z_sqr) * gy;
-    J[3] = (float)((double)((-Wx * Wy * z_sqr) * gx) + (-(1.0 + (double)(Wy * Wy * z_sqr))) * (double)gy);
-    J[4] = (float)((1.0 + (double)(Wx * Wx * z_sqr)) * (double)gx + (double)((Wx * Wy * z_sqr) * gy));
+    J[3] = jacRowMixed((-Wx * Wy * z_sqr) * gx, Wy * Wy * z_sqr, gy);
+    J[4] = -jacRowMixed(-((Wx * Wy * z_sqr) * gy), Wx * Wx * z_sqr, gx);
     J[5] = (-Wy * z) * gx + (Wx * z) * gy;
 
     // LGS6::update, LGSX.h:390-396

@@ -227,6 +227,16 @@ __device__ __forceinline__ void warpReduceExt(float (&x)[EV_NX], int lane, float
     if ((lane & 1) == 0) smRow[EV_NCH + warpReduceChannel<EV_NX>(lane)] = x[0];
 }
 
+// Chunk (32 consecutive interior pixels) number `k` of CTA `b` on a grid of G CTAs.  A plain b + G*k would hand a CTA the
+// same image columns in every slot (on the 320-wide level G = 148 chunks are 14.9 rows, so consecutive slots of a CTA lie almost
+// exactly under one another): the semi-dense points cluster on textured structures, and the CTAs under them took 13 % longer than
+// the mean, which every pass's barrier then waited for.  Rotating the assignment by a stride coprime to G per slot spreads a
+// CTA's chunks over the columns.  Any bijection gives the same sums up to fp32 summation order (fixed for a given G).
+__device__ __forceinline__ int tpChunkOf(int b, int k, int G)
+{
+    return k * G + (b + k * 37) % G;
+}
+
 struct WarpWindow {
     const float4* win;               // this warp's TRK_WIN_H x TRK_WIN_W window in shared memory
     uint64_t* bar;
@@ -263,12 +273,14 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
     const float4* fg = L.frameGrad;
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // chunks of this CTA: c = blockIdx.x + G * k, k = 0 .. nMine-1; warp `warp` takes k = warp, warp + 16, ...
-    const int nMine = ((int)blockIdx.x < L.nChunks) ? (L.nChunks - (int)blockIdx.x + G - 1) / G : 0;
+    // chunks of this CTA: tpChunkOf(b, k, G), k = 0 .. nSlots-1 where it exists; warp `warp` takes k = warp, warp + 16, ...
+    const int nSlots = (L.nChunks + G - 1) / G;
     if (mask) { W.lastBits = 0u; W.pointBits = 0u; }
     int slot = 0;
-    for (int k = warp; k < nMine; k += TP_WARPS, slot++) {
-        const int j = (((int)blockIdx.x + G * k) << 5) + lane;        // interior pixel number
+    for (int k = warp; k < nSlots; k += TP_WARPS, slot++) {
+        const int chunk = tpChunkOf((int)blockIdx.x, k, G);
+        if (chunk >= L.nChunks) continue;                              // warp-uniform
+        const int j = (chunk << 5) + lane;                             // interior pixel number
         const bool firstChunk = (k == warp);
         bool isPoint = false;
         float px = 0.f, py = 0.f, pz = 0.f, var = 0.f, color = 0.f;
@@ -411,9 +423,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
         a.w += __shfl_down_sync(0xffffffffu, a.w, 16);
         if (half == 0) reinterpret_cast<float4*>(&comb[warp][0])[q] = a;
     }
-    long long t3a = clock64();
     __syncthreads();
-    long long t3b = clock64();
     if (threadIdx.x < nch) {
         float t = comb[0][threadIdx.x];
 #pragma unroll
@@ -423,7 +433,6 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
     __syncthreads();
     long long t4 = clock64();
     cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
-    cyc[4] += t3a - t3; cyc[5] += t3b - t3a;       // TEMP: combine sub-phases (overwritten at the end unless debug)
 }
 
 // Fully unrolled, register-resident LDL^T (no pivoting) for the damped 6x6 normal equations.  Returns false if
@@ -603,6 +612,14 @@ __device__ __forceinline__ double ipowd(double f, int n)
     for (int i = 0; i < n; i++) r *= f;
     return r;
 }
+// LM_lambda *= std::pow(lambdaFailFac, incTry), :445.  For the reference's factor 2 the product is an exact scaling by 2^n:
+// one float multiply (FP64 issues at a fraction of the FP32 rate on B200 and this sits on the serial path of every pass).
+__device__ __forceinline__ float lambdaAfterFail(float lambda, float failFac, int incTry)
+{
+    if (failFac == 2.0f && incTry >= 0 && incTry < 100 && lambda > 1e-30f && lambda < 1e8f)
+        return lambda * __int_as_float((127 + incTry) << 23);
+    return (float)((double)lambda * ipowd((double)failFac, incTry));
+}
 
 // Build the chain of the iteration that starts (or continues) now: lanes 0..kmax-1 of warp 0 solve, in parallel, for
 // lambda_1 = lm.LM_lambda and its successors under rejection (lambda == 0 ? 0.2 : lambda * failFac^incTry, :443-446).
@@ -613,8 +630,8 @@ __device__ __forceinline__ void buildChain(const TrackParams& p, LMState& lm, LM
     if (lane < p.kmax) {
         float lam = lm.LM_lambda;
         for (int u = 1; u <= lane; u++) {
-            if (lam == 0) lam = 0.2;
-            else lam *= ipowd((double)p.st.lambdaFailFac, lm.incTry + u);
+            if (lam == 0) lam = 0.2f;
+            else lam = lambdaAfterFail(lam, p.st.lambdaFailFac, lm.incTry + u);
         }
         solveCandidate(lm.lsq, lam, lm.refToFrame, sh.cand[lane], sh.pose[lane], lm.affine_a, lm.affine_b);
     }
@@ -643,6 +660,7 @@ __device__ __forceinline__ void lmNextLevel(const TrackParams& p, LMState& lm, L
 __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMShared& sh, int lane)
 {
     int build = 0;                       // 1: start / continue an iteration (lane 0 decides, broadcast below)
+    int copyLsq = 0;                     // 1: the sums of this pass become the accepted normal equations
     if (lane == 0) {
         const long long ta = clock64();
         const float* s = sh.sums;
@@ -659,11 +677,11 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
             const bool converged = !init && (error / lm.lastErr > p.st.convergenceEps[lvl]);   // :404
             if (!init) lm.last_residual = error;                                         // :414
             lm.lastErr = error;                                                          // :336 / :414
-#pragma unroll
-            for (int k = 0; k < 27; k++) lm.lsq[k] = s[k];                               // buffers now belong to this pose
+            copyLsq = 1;                                                                 // buffers now belong to this pose (all lanes copy below)
             if (init) { lm.LM_lambda = p.st.lambdaInitial[lvl]; lm.iteration = 0; }      // :341
             else {
-                if (lm.LM_lambda <= 0.2) lm.LM_lambda = 0;                               // :417-420
+                // :417-420 `if(LM_lambda <= 0.2)` compares the float with the DOUBLE 0.2 < 0.2f, i.e. LM_lambda < 0.2f
+                if (lm.LM_lambda < 0.2f) lm.LM_lambda = 0;
                 else lm.LM_lambda *= p.st.lambdaSuccessFac;
                 if (!converged) lm.iteration++;
             }
@@ -714,8 +732,8 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
                 }
                 // rejected, :424-447
                 if (!(sh.cand[k].incSq > p.st.stepSizeMin[lvl])) { leave = true; break; }        // :432-441
-                if (lm.LM_lambda == 0) lm.LM_lambda = 0.2;                               // :443-446
-                else lm.LM_lambda *= ipowd((double)p.st.lambdaFailFac, lm.incTry);
+                if (lm.LM_lambda == 0) lm.LM_lambda = 0.2f;                              // :443-446
+                else lm.LM_lambda = lambdaAfterFail(lm.LM_lambda, p.st.lambdaFailFac, lm.incTry);
                 if (k == K - 1) build = 1;                                               // chain used up: continue it
             }
         }
@@ -723,7 +741,12 @@ __device__ __forceinline__ void lmAdvance(const TrackParams& p, LMState& lm, LMS
         if (sh.action != ACT_CONTINUE) build = 0;
         lm.dbg[0] += clock64() - ta;
     }
-    build = __shfl_sync(0xffffffffu, build, 0);
+    build = __shfl_sync(0xffffffffu, build | (copyLsq << 1), 0);
+    if (build & 2) {                     // 27 lanes instead of 27 dependent shared-memory round trips of lane 0
+        if (lane < 27) lm.lsq[lane] = sh.sums[lane];
+        __syncwarp();
+    }
+    build &= 1;
     if (build) {
         const long long tb = clock64();
         __syncwarp();
@@ -792,11 +815,11 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     if (lm.commitLast && p.minLevel == SE3TRACKING_MIN_LEVEL) {
         const TrackLevelParams& L = p.lvl[SE3TRACKING_MIN_LEVEL];
         const int G = (int)gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int nMine = ((int)blockIdx.x < L.nChunks) ? (L.nChunks - (int)blockIdx.x + G - 1) / G : 0;
+        const int nSlots = (L.nChunks + G - 1) / G;
         int slot = 0;
-        for (int k = warp; k < nMine; k += TP_WARPS, slot++) {
+        for (int k = warp; k < nSlots; k += TP_WARPS, slot++) {
             if (!((W.pointBits >> slot) & 1u)) continue;
-            const int j = (((int)blockIdx.x + G * k) << 5) + lane;
+            const int j = (tpChunkOf((int)blockIdx.x, k, G) << 5) + lane;
             const int yy = j / L.iw;
             p.goodMask[(j - yy * L.iw + 1) + (yy + 1) * L.w] = (uint8_t)((W.lastBits >> slot) & 1u);
         }
@@ -842,7 +865,6 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
         outDev->lastResidual = lm.last_residual; outDev->diverged = lm.diverged;
         if (p.doPrepare)
             devicePrepareObserve(lm.refToFrame, lm.diverged, lm.last_residual, ev.pointUsage, ev.goodCount, ev.badCount, p.prep, p.obsOut, p.skipOut);
-        if (p.debug) printf("[combine] loads+adds=%lld  sync=%lld\n", cyc[4], cyc[5]);
         cyc[5] = clock64() - tStart;
         cyc[4] = cyc[5] - cyc[0] - cyc[1] - cyc[2] - cyc[3];
         for (int i = 0; i < 6; i++) out->cyc[i] = cyc[i];
@@ -1016,6 +1038,13 @@ static int trackPersistentFinish(lsdgpu_ctx* ctx, FrameSlot* fr, lsdgpu_track_re
                 sum += v;
             }
             fprintf(stderr, "   %-9s min=%lld (cta %d) max=%lld (cta %d) mean=%lld\n", nm[k], mn, imn, mx, imx, sum / gAll);
+        }
+        if (getenv("LSDGPU_TRACK_DEBUG_CTAS")) {
+            for (int k = 0; k < 3; k++) {
+                fprintf(stderr, "   %s per cta:", nm[k]);
+                for (int b = 0; b < gAll && b < TP_MAXGRID_DBG - 1; b++) fprintf(stderr, " %lld", hOut->cycBlk[b][k] / 100);
+                fprintf(stderr, "\n");
+            }
         }
     }
     // a TMA copy that never completed downgrades that warp to the L1/L2 path (same results): never silent
