@@ -384,7 +384,7 @@ __device__ __forceinline__ bool makeAndCheckEPL(const DepthCam& cam, const float
 // CTA first runs the cheap gates for its 2048 pixels (4 per thread, coalesced), collects the survivors in a shared-memory
 // list, and then walks that list densely: warps stay full during the expensive doLineStereo part.  The per-pixel
 // arithmetic is untouched (the list order does not matter: pixels are independent).
-#define OBS_THREADS 512
+#define OBS_THREADS 768
 #define OBS_PIX_PER_CTA 2048          // 640x480: 147 CTAs = one wave of 1 CTA per SM on 148 SMs
 
 // gates of observeDepthRow (:124-132) and of observeDepthCreate / Update up to and including makeAndCheckEPL
@@ -510,9 +510,8 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(HypField cur, DepthCam 
     if (threadIdx.x == 0) sCount = 0;
     __syncthreads();
     const int base = blockIdx.x * OBS_PIX_PER_CTA;
-#pragma unroll
-    for (int k = 0; k < OBS_PIX_PER_CTA / OBS_THREADS; k++) {
-        const int j = base + k * OBS_THREADS + threadIdx.x;
+    for (int jj = threadIdx.x; jj < OBS_PIX_PER_CTA; jj += OBS_THREADS) {
+        const int j = base + jj;
         if (j < nInterior) {
             const int x = 3 + j % iw, y = 3 + j / iw;
             const int idx = x + y * cam.w;
