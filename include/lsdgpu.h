@@ -259,6 +259,23 @@ int lsdgpu_perma_overlap_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, const 
 int lsdgpu_perma_track_batch(lsdgpu_ctx* ctx, int n, const int* kf_ids, int frame_id, const double* refToFrame_init_qt,
                              lsdgpu_track_result* results);
 
+/* ---- one stream over several GPUs (BASELINE.json config 5) ------------------------------------------------------------------
+ * The device-resident tracker (lsdgpu_se3_track, mode 1) can split the points of every level over n_ranks GPUs, one process per
+ * GPU.  Every rank holds the same frames and the same depth map (all ranks issue the same calls); rank r evaluates every
+ * n_ranks-th 32-pixel chunk, and the 40..56 sums of each pass as well as the level-1 refPixelWasGood flags cross NVLink INSIDE
+ * the kernel through peer-mapped memory (posted stores + polling of tagged 8-byte slots; no host round trip, no NCCL call on the
+ * path), added in rank order on every GPU, so every rank takes identical LM decisions and returns identical results.
+ *   lsdgpu_peer_export  CUDA IPC handle (LSDGPU_PEER_HANDLE_BYTES) of this context's arena; the caller gathers the handles of
+ *                       all ranks (e.g. torch.distributed.all_gather)
+ *   lsdgpu_peer_attach  handles = n_ranks * LSDGPU_PEER_HANDLE_BYTES bytes in rank order; maps the peers and switches the
+ *                       tracker to sharded operation.  All contexts must have been created with the same size and max_frames
+ *                       (same arena layout).  Synchronise the ranks after attach and before the first tracking.
+ *   lsdgpu_peer_detach  back to single-GPU operation (also done by lsdgpu_destroy); synchronise the ranks first. */
+#define LSDGPU_PEER_HANDLE_BYTES 64
+int lsdgpu_peer_export(lsdgpu_ctx* ctx, void* handle_out);
+int lsdgpu_peer_attach(lsdgpu_ctx* ctx, int rank, int n_ranks, const void* handles);
+int lsdgpu_peer_detach(lsdgpu_ctx* ctx);
+
 /* Point-sharded tracking across GPUs (BASELINE config 5): rank `shard` of `n_shards` evaluates every
  * n_shards-th 32-pixel chunk of the level; the LSDGPU_EVAL_NSUMS partial sums of every evaluation are handed to
  * `allreduce` (sum over ranks, in place, HOST buffer) before the LM decision, so all ranks take identical

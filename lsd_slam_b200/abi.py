@@ -147,6 +147,9 @@ SYMBOLS = [
     ("lsdgpu_depth_set_hypotheses", C.c_int, [_vp, C.c_int, C.POINTER(Hyp), C.c_int, C.c_int]),
     ("lsdgpu_depth_update_keyframe", C.c_int, [_vp, _ip, C.c_int]),
     ("lsdgpu_depth_update_keyframe_refs", C.c_int, [_vp, C.c_void_p, C.c_int]),
+    ("lsdgpu_peer_export", C.c_int, [_vp, C.c_void_p]),
+    ("lsdgpu_peer_attach", C.c_int, [_vp, C.c_int, C.c_int, C.c_void_p]),
+    ("lsdgpu_peer_detach", C.c_int, [_vp]),
     ("lsdgpu_depth_create_keyframe", C.c_int, [_vp, C.c_int, _dp]),
     ("lsdgpu_seq_sum_f32", C.c_int, [_vp, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     ("lsdgpu_depth_finalize_keyframe", C.c_int, [_vp]),
@@ -337,6 +340,23 @@ class Context:
         pid, itr = C.c_int(), C.c_float()
         self._ck(self.L.lsdgpu_frame_get_pose(self.ptr, fid, q.ctypes.data_as(_dp), C.byref(pid), C.byref(itr)))
         return q, pid.value, itr.value
+
+    PEER_HANDLE_BYTES = 64
+
+    def peer_export(self) -> bytes:
+        """CUDA IPC handle of this context's arena (lsdgpu_peer_export)"""
+        buf = C.create_string_buffer(self.PEER_HANDLE_BYTES)
+        self._ck(self.L.lsdgpu_peer_export(self.ptr, buf))
+        return buf.raw
+
+    def peer_attach(self, rank: int, handles: list):
+        """map the arenas of all ranks (handles in rank order) and shard the device-resident tracker over them"""
+        blob = b"".join(handles)
+        assert len(blob) == self.PEER_HANDLE_BYTES * len(handles)
+        self._ck(self.L.lsdgpu_peer_attach(self.ptr, rank, len(handles), C.c_char_p(blob) if len(handles) > 1 else None))
+
+    def peer_detach(self):
+        self._ck(self.L.lsdgpu_peer_detach(self.ptr))
 
     def seq_sum_f32(self, x, valid=None):
         """the sequential fp32 `sum += x[i]` of DepthMap.cpp:1286-1293 through the kernels createKeyFrame uses"""

@@ -158,6 +158,10 @@ struct lsdgpu_ctx {
     unsigned int* trkSync = nullptr;     // per-level barrier counters + level records of the persistent tracker (TP_SYNC_WORDS)
     unsigned int trkBase[LSD_LEVELS] = { 0, 0, 0, 0, 0 };  // arrivals already counted on each level's counter (never reset)
     unsigned int tmaTimeoutsSeen = 0;
+    // one stream sharded over several GPUs (lsdgpu_peer_attach): every rank's arena mapped into this process
+    int nRanks = 1, rank = 0;
+    char* peerBase[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+    unsigned int trkTailBase = 0;
     // environment switches, read once at lsdgpu_create
     int optTrackTma = 1, optSingleSync = 0;
     bool optTrackDebug = false;

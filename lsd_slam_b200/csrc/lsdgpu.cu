@@ -197,11 +197,14 @@ extern "C" int lsdgpu_create(int device, int width, int height, const float K[9]
     return 0;
 }
 
+static void peerCloseAll(lsdgpu_ctx* ctx);
+
 extern "C" void lsdgpu_destroy(lsdgpu_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    peerCloseAll(ctx);
     cudaFree(ctx->arena);
     if (ctx->stageRing) cudaFree(ctx->stageRing);
     if (ctx->dRemapX) cudaFree(ctx->dRemapX);
@@ -706,6 +709,72 @@ extern "C" int lsdgpu_se3_track(lsdgpu_ctx* ctx, int kf_id, int frame_id, const 
         fr->thisToParent[7] = 1.0;
         fr->parentId = kf->id;                                                    // :484
     }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// one stream over several GPUs: peer mapping of the contexts' arenas (BASELINE config 5)
+// ------------------------------------------------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == LSDGPU_PEER_HANDLE_BYTES, "ABI constant out of sync with cudaIpcMemHandle_t");
+
+extern "C" int lsdgpu_peer_export(lsdgpu_ctx* ctx, void* handle_out)
+{ LSD_LOCK(ctx);
+    if (!ctx || !handle_out) return lsd_fail(ctx, "peer_export: null argument");
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    LSD_CHECK(ctx, cudaIpcGetMemHandle(&h, ctx->arena));
+    memcpy(handle_out, &h, sizeof(h));
+    return 0;
+}
+
+static void peerCloseAll(lsdgpu_ctx* ctx)
+{
+    for (int d = 0; d < 8; d++) {
+        if (ctx->peerBase[d] && d != ctx->rank) cudaIpcCloseMemHandle(ctx->peerBase[d]);
+        ctx->peerBase[d] = nullptr;
+    }
+    ctx->nRanks = 1; ctx->rank = 0;
+}
+
+extern "C" int lsdgpu_peer_attach(lsdgpu_ctx* ctx, int rank, int n_ranks, const void* handles)
+{ LSD_LOCK(ctx);
+    if (!ctx) return -2;
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    if (n_ranks < 1 || n_ranks > TP_MAX_RANKS || rank < 0 || rank >= n_ranks) return lsd_fail(ctx, "peer_attach: bad rank / number of ranks");
+    if (n_ranks > 1 && !handles) return lsd_fail(ctx, "peer_attach: null handle array");
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    peerCloseAll(ctx);
+    if (n_ranks == 1) return 0;
+    for (int d = 0; d < n_ranks; d++) {
+        if (d == rank) { ctx->peerBase[d] = ctx->arena; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)d * sizeof(h), sizeof(h));
+        void* base = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            ctx->rank = rank;
+            peerCloseAll(ctx);
+            cudaGetLastError();
+            const std::string msg = std::string("peer_attach: cudaIpcOpenMemHandle failed for rank ") + std::to_string(d) + ": " + cudaGetErrorString(e);
+            return lsd_fail(ctx, msg.c_str());
+        }
+        ctx->peerBase[d] = (char*)base;
+    }
+    ctx->rank = rank; ctx->nRanks = n_ranks;
+    // the exchange rows, done slots and the tail counter start from a known state on every rank (the caller synchronises the ranks
+    // between attach and the first tracking)
+    LSD_CHECK(ctx, cudaMemsetAsync(ctx->trkSync + TP_XCHG_OFFSET, 0, (TP_SYNC_WORDS - 4 - TP_XCHG_OFFSET) * sizeof(unsigned int), ctx->stream));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->trkTailBase = 0;
+    return 0;
+}
+
+extern "C" int lsdgpu_peer_detach(lsdgpu_ctx* ctx)
+{ LSD_LOCK(ctx);
+    if (!ctx) return -2;
+    LSD_CHECK(ctx, cudaSetDevice(ctx->device));
+    LSD_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    peerCloseAll(ctx);
     return 0;
 }
 

@@ -34,7 +34,11 @@
 #define TP_MAXGRID 160               // combine code is unrolled for <= 160 CTAs (B200: 148 SMs)
 #define TP_MAXGRID_DBG 160
 #define TP_WIN_SMEM (TP_WARPS * TRK_WIN_W * TRK_WIN_H * 16)    // 16 warps x 13056 B = 208896 B of dynamic smem
-#define TP_SYNC_WORDS 1024           // ctx->trkSync: word 0 = arrival counter of the grid barrier; last 4 words: debug counters
+#define TP_SYNC_WORDS 4096           // ctx->trkSync: word 0 = arrival counter of the grid barrier; last 4 words: debug counters
+#define TP_MAX_RANKS 8               // GPUs one stream's tracking can be sharded over (peer exchange, see gridExchangeRanks)
+#define TP_XCHG_OFFSET 1024          // word offset of the cross-GPU exchange rows: [TP_MAX_RANKS][64] slots of {value, tag} (8 B each)
+#define TP_DONE_OFFSET 3072          // word offset of the per-peer "my writes into your memory are complete" slots (8 B each)
+#define TP_TAIL_OFFSET 3200          // word: arrival counter of the end-of-kernel barrier of a sharded launch
 #define TP_KMAX 3                    // poses per pass: the try + up to two speculative successors
 #define TP_ROW 64                    // floats per exchange row (256 B, one row per CTA; EV_NCHX = 56 used)
 
@@ -71,6 +75,12 @@ struct alignas(64) TrackParams {
     int minLevel;                    // last level of the coarse-to-fine loop (1 for trackFrame, 4 for permaRef tracking)
     int useTma;                      // 1: per-warp shared-memory windows loaded by TMA; 0: all taps through L1/L2
     int kmax;                        // candidate poses per pass (1 = no speculation; <= TP_KMAX)
+    // one stream sharded over nRanks GPUs (BASELINE config 5): this GPU evaluates every nRanks-th chunk; the per-pass sums and the
+    // level-1 mask are exchanged through peer-mapped memory inside the kernel (no host, no NCCL call on the path)
+    int nRanks, rank;
+    unsigned int* peerSync[TP_MAX_RANKS];     // each rank's `sync` block as mapped into THIS process (own entry = sync)
+    uint8_t* peerMask[TP_MAX_RANKS];          // the tracked frame's level-1 mask on each rank
+    unsigned int tailBase;                    // arrivals already counted on the tail barrier
     int doPrepare;                   // 1: the last thread also turns the result into the observe parameters of the same frame
     PrepareConsts prep;              //    (Frame::prepareForStereoWith + head of DepthMap::updateKeyframe), no host round trip
     ObserveParams* obsOut;
@@ -256,6 +266,66 @@ struct WarpWindow {
 
 // One pass: nPose candidate poses over this CTA's chunks of level `lvl`, CTA reduction, one row per CTA through L2 behind ONE
 // grid barrier, then every CTA sums the rows in block order.  On return sh.sums holds the totals, bit-identical in every CTA.
+// ---- one stream over several GPUs (BASELINE config 5): the per-pass sums cross NVLink inside the kernel ---------------------------
+// After the local combine every CTA of this GPU holds this GPU's totals.  CTA 0 stores them, one 8-byte {value, tag} slot per
+// channel, straight into every peer's exchange rows (peer-mapped memory: a posted NVLink write, no host, no NCCL call); every
+// CTA then polls THE LOCAL copy of the peers' rows and adds the rows in rank order -- the same additions in the same order on
+// every GPU, so all GPUs take the same LM decisions from identical bits.  Slots are double-buffered by pass parity: a row is
+// overwritten two passes later, which needs this GPU's own next row, which CTA 0 sends only after every local CTA has passed the
+// next local barrier, i.e. has consumed this one.
+__device__ __forceinline__ void gridExchangeRanks(const TrackParams& p, LMShared& sh, int nch, unsigned int tag, unsigned int parity)
+{
+    const int t = threadIdx.x;
+    if (t < nch) {
+        const float mine = sh.sums[t];
+        const size_t rowBase = (size_t)parity * TP_MAX_RANKS * 64;
+        if (blockIdx.x == 0) {
+            const unsigned long long w = ((unsigned long long)tag << 32) | __float_as_uint(mine);
+            for (int d = 0; d < p.nRanks; d++) {
+                if (d == p.rank) continue;
+                unsigned long long* slot = reinterpret_cast<unsigned long long*>(p.peerSync[d] + TP_XCHG_OFFSET) + rowBase + p.rank * 64 + t;
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(slot), "l"(w) : "memory");
+            }
+        }
+        float total = 0.f;
+        for (int r = 0; r < p.nRanks; r++) {
+            float v = mine;
+            if (r != p.rank) {
+                const unsigned long long* slot = reinterpret_cast<const unsigned long long*>(p.sync + TP_XCHG_OFFSET) + rowBase + r * 64 + t;
+                unsigned long long w;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
+                } while ((unsigned int)(w >> 32) != tag);
+                v = __uint_as_float((unsigned int)w);
+            }
+            total = (r == 0) ? v : total + v;
+        }
+        sh.sums[t] = total;
+    }
+    __syncthreads();
+}
+
+// End of a sharded launch: when this kernel retires, (a) every level-1 flag this GPU wrote into its peers has landed and (b) every
+// flag the peers wrote into this GPU has landed -- the mapping kernels that follow on each GPU's stream read the whole mask.
+__device__ __forceinline__ void gridTailRanks(const TrackParams& p)
+{
+    __threadfence_system();                                   // this thread's peer stores are performed system-wide
+    gridBarrier(p.sync + TP_TAIL_OFFSET, p.tailBase + gridDim.x);
+    if (blockIdx.x != 0) return;
+    const int d = threadIdx.x;
+    if (d < p.nRanks && d != p.rank) {
+        const unsigned long long tag = ((unsigned long long)p.launchSeq << 32) | 0xd0d0d0d0ull;
+        unsigned long long* theirs = reinterpret_cast<unsigned long long*>(p.peerSync[d] + TP_DONE_OFFSET) + p.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(tag) : "memory");
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(p.sync + TP_DONE_OFFSET) + d;
+        unsigned long long w;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(mine) : "memory");
+        } while (w != tag);
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMShared& sh, float (*sm)[EV_NCHX], float (*comb)[TP_ROW],
                                              unsigned int& epoch, long long* cyc, WarpWindow& W)
 {
@@ -274,11 +344,13 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
     uint8_t* mask = (lvl == SE3TRACKING_MIN_LEVEL) ? p.goodMask : nullptr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // chunks of this CTA: tpChunkOf(b, k, G), k = 0 .. nSlots-1 where it exists; warp `warp` takes k = warp, warp + 16, ...
-    const int nSlots = (L.nChunks + G - 1) / G;
+    // sharded over nRanks GPUs: the CTAs of all ranks form one virtual grid (this CTA is number b * nRanks + rank of it)
+    const int Gv = G * p.nRanks, vb = (int)blockIdx.x * p.nRanks + p.rank;
+    const int nSlots = (L.nChunks + Gv - 1) / Gv;
     if (mask) { W.lastBits = 0u; W.pointBits = 0u; }
     int slot = 0;
     for (int k = warp; k < nSlots; k += TP_WARPS, slot++) {
-        const int chunk = tpChunkOf((int)blockIdx.x, k, G);
+        const int chunk = tpChunkOf(vb, k, Gv);
         if (chunk >= L.nChunks) continue;                              // warp-uniform
         const int j = (chunk << 5) + lane;                             // interior pixel number
         const bool firstChunk = (k == warp);
@@ -374,7 +446,11 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
                 const int goodL = evalPointLight<true>(px, py, pz, color, var, sh.pose[K - 1], p.C, L.fx, L.fy, L.cx, L.cy, w, h, tap, ext);
                 if (mask) W.lastBits |= (unsigned int)goodL << slot;
             }
-            if (mask) { mask[i] = (uint8_t)good; W.pointBits |= 1u << slot; }
+            if (mask) {
+                mask[i] = (uint8_t)good; W.pointBits |= 1u << slot;
+                if (p.nRanks > 1)                                      // the other ranks own other chunks: give them this one's flag
+                    for (int d = 0; d < p.nRanks; d++) if (d != p.rank) p.peerMask[d][i] = (uint8_t)good;
+            }
         }
     }
     __syncthreads();
@@ -431,6 +507,7 @@ __device__ __forceinline__ void gridEvaluate(const TrackParams& p, int lvl, LMSh
         sh.sums[threadIdx.x] = t;
     }
     __syncthreads();
+    if (p.nRanks > 1) gridExchangeRanks(p, sh, nch, (p.launchSeq << 16) | (epoch & 0xffffu), epoch & 1u);
     long long t4 = clock64();
     cyc[0] += t1 - t0; cyc[1] += t2 - t1; cyc[2] += t3 - t2; cyc[3] += t4 - t3;
 }
@@ -815,15 +892,21 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_track_persistent(const __grid
     if (lm.commitLast && p.minLevel == SE3TRACKING_MIN_LEVEL) {
         const TrackLevelParams& L = p.lvl[SE3TRACKING_MIN_LEVEL];
         const int G = (int)gridDim.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        const int nSlots = (L.nChunks + G - 1) / G;
+        const int Gv = G * p.nRanks, vb = (int)blockIdx.x * p.nRanks + p.rank;
+        const int nSlots = (L.nChunks + Gv - 1) / Gv;
         int slot = 0;
         for (int k = warp; k < nSlots; k += TP_WARPS, slot++) {
             if (!((W.pointBits >> slot) & 1u)) continue;
-            const int j = (tpChunkOf((int)blockIdx.x, k, G) << 5) + lane;
+            const int j = (tpChunkOf(vb, k, Gv) << 5) + lane;
             const int yy = j / L.iw;
-            p.goodMask[(j - yy * L.iw + 1) + (yy + 1) * L.w] = (uint8_t)((W.lastBits >> slot) & 1u);
+            const int i = (j - yy * L.iw + 1) + (yy + 1) * L.w;
+            const uint8_t g = (uint8_t)((W.lastBits >> slot) & 1u);
+            p.goodMask[i] = g;
+            if (p.nRanks > 1)
+                for (int d = 0; d < p.nRanks; d++) if (d != p.rank) p.peerMask[d][i] = g;
         }
     }
+    if (p.nRanks > 1) gridTailRanks(p);
 
     if (p.debug) {
         atomicAdd(p.sync + TP_SYNC_WORDS - 3, W.hits & 0xffffu);
@@ -949,6 +1032,14 @@ static int trackPersistentEnqueue(lsdgpu_ctx* ctx, FrameSlot* kf, FrameSlot* fr,
     P.sync = ctx->trkSync;
     P.barrierBase[0] = ctx->trkBase[0];
     P.kmax = ctx->optTrackKmax;
+    P.nRanks = ctx->nRanks; P.rank = ctx->rank;
+    P.tailBase = ctx->trkTailBase;
+    for (int d = 0; d < ctx->nRanks; d++) {
+        char* base = d == ctx->rank ? ctx->arena : ctx->peerBase[d];
+        P.peerSync[d] = reinterpret_cast<unsigned int*>(base + ((char*)ctx->trkSync - ctx->arena));
+        P.peerMask[d] = reinterpret_cast<uint8_t*>(base + ((char*)fr->goodMask - ctx->arena));
+    }
+    if (ctx->nRanks > 1) ctx->trkTailBase += (unsigned int)ctx->trackGrid;
     if (prep) { P.doPrepare = 1; P.prep = *prep; P.obsOut = ctx->dObs; P.skipOut = ctx->dSkipFlag; }
     TrackState* dOut = (TrackState*)ctx->dTrackStateMapped;
     TrackState* dOutDev = (TrackState*)ctx->dTrackState;

@@ -53,3 +53,19 @@ class ShardedSE3Tracker(abi.SE3Tracker):
         self.affineEstimation_a, self.affineEstimation_b = r.affineEstimation_a, r.affineEstimation_b
         self.diverged, self.trackingWasGood = bool(r.diverged), bool(r.trackingWasGood)
         return np.array(r.frameToRef_qt, np.float64)
+
+
+def attach_peers(ctx: abi.Context, dist, group=None):
+    """Device-side exchange (include/lsdgpu.h, "one stream over several GPUs"): gather the CUDA IPC handles of all ranks' arenas,
+    map them, and switch this context's device-resident tracker to sharded operation.  Collective: every rank calls it."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.peer_export(), group=group)
+    ctx.peer_attach(rank, handles)
+    dist.barrier(group)
+
+
+def detach_peers(ctx: abi.Context, dist, group=None):
+    dist.barrier(group)
+    ctx.peer_detach()
+    dist.barrier(group)
