@@ -9,18 +9,19 @@
  * Sophus SE3 exp / product / inverse, 6x6 LDLT).  Each function cites the
  * reference file:line it follows.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for
- * this path and cannot be compiled in this image (Eigen,
- * Boost, OpenCV C++, g2o, ROS are absent), so this restatement is checked only
- * against (a) the property tests the vendored Sophus test-suite states
- * (thirdparty/Sophus/sophus/test_se3.cpp:38-60, tests.hpp:70-133) and (b) its
- * own self-consistency KATs (tests/test_oracle_*.py).
+ * PARITY PINNED TO THE REFERENCE'S OWN CODE (round 2): oracle/ref_build.py compiles DepthMap.cpp, SE3Tracker.cpp,
+ * Sim3Tracker.cpp, Frame.cpp, TrackingReference.cpp ... unmodified from /root/reference against stand-in headers
+ * (oracle/ref_shim/: an Eigen 3.2 subset, Boost -> std, OpenCV debug stubs) into oracle/_ref/liblsd_ref.so, exported under the
+ * same lsdo_* API by oracle/ref_driver.cpp; tests/test_ref_pin.py holds this restatement to it BIT FOR BIT on every function of
+ * the path, and tests/golden/reference_320x240.npz are outputs of that library.  Still unpinned: UndistorterPTAM
+ * (util/Undistorter.cpp needs OpenCV's remap machinery and is not part of the _ref build) -- see lsd_oracle_undistort.inc.
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
  * reference legs may load this library.  The product (lsd_slam_b200/) never does.
  *
  * Third-party arithmetic restated here because its source is not vendored:
- *   Eigen 3.x (unpinned: find_package(Eigen3 REQUIRED), lsd_slam_core/CMakeLists.txt:19)
+ *   Eigen 3.x (find_package(Eigen3 REQUIRED), lsd_slam_core/CMakeLists.txt:19; conventions of Eigen 3.2, the release the
+ *   reference was written against: the vendored Sophus test programs pass on the same conventions, tests/test_ref_pin.py)
  *   - 3x3 inverse by cofactors (Eigen/src/LU/Inverse.h compute_inverse_size3)
  *   - Quaternion product / toRotationMatrix / _transformVector (Eigen/src/Geometry/Quaternion.h)
  *   - LDLT with diagonal pivoting (Eigen/src/Cholesky/LDLT.h, unblocked)
