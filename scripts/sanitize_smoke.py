@@ -16,6 +16,23 @@ for mode in (1, 0):
     ctx.close()
 print("sanitize run ok")
 
+# round 2: the sequential-sum kernels on adversarial data, and updateKeyframe with a frame tracked on another keyframe
+ctx = abi.Context(160, 112, seq.K, max_frames=8)
+rng = np.random.default_rng(3)
+x = (rng.integers(1, 64, 70001) * 2.0 ** -9).astype(np.float32)
+x[[5, 4000, 69999]] = [-1.0, np.inf, 0.0]
+ctx.seq_sum_f32(x, rng.random(70001) < 0.7)
+ctx.seq_sum_f32(np.full(3000, 100.0, np.float32))
+ctx.upload(0, fr[0][0]); ctx.set_depth_gt(0, fr[0][1])
+dm = abi.DepthMap(ctx); dm.initializeFromGTDepth(0)
+for k in (1, 5):
+    ctx.upload(k, fr[k][0]); ctx.set_pose(k, np.concatenate([seq.frame_to_ref_qt(k), [1.0]]), 0, 0.0)
+dm.updateKeyframe([1])
+dm.finalizeKeyFrame(); q5 = dm.createKeyFrame(5)
+dm.updateKeyframe([(1, np.array([0, 0, 0, 1, 0.01, 0, 0, 1.0]))])
+ctx.close()
+print("sanitize run (round 2) ok")
+
 # permaRef batch, Sim3 batch (every cluster size), undistorter, keyframe output
 import os
 ctx = abi.Context(160, 112, seq.K, max_frames=8)
