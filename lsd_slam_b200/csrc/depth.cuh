@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(OBS_THREADS) k_observe(HypField cur, DepthCam 
 {
     __shared__ int sList[OBS_PIX_PER_CTA];
     __shared__ int sCount;
+    pdlWait();                                       // launched early (programmatic dependent launch): wait for the tracking kernel
     if (skip && *skip) return;                       // this frame's tracking diverged: no mapping (SlamSystem.cpp:948-967)
     const ObserveParams* OP = OPdev ? OPdev : &OPv;
     const int iw = cam.w - 6, ih = cam.h - 6;        // x in [3, w-3), y in [3, h-3)  (:118, :150)
@@ -734,6 +735,7 @@ __global__ void __launch_bounds__(FR_THREADS) k_fill_regularize(HypField src, Hy
     __shared__ float4 sA[FR_TH + 8][FR_TW + 8];      // source:      (idepth, idepth_var, validity_counter, isValid)
     __shared__ float4 sB[FR_TH + 4][FR_TW + 4];      // after fill:  same fields
     __shared__ unsigned char sCreated[FR_TH + 4][FR_TW + 4];
+    pdlWait();                                       // launched early (programmatic dependent launch): wait for k_observe
     if (skip && *skip) return;
     const int width = cam.w, height = cam.h;
     const int tilesX = (width + FR_TW - 1) / FR_TW;

@@ -112,6 +112,7 @@ __device__ __forceinline__ float vmax3Img(const float* __restrict__ img, int t, 
 #define GR_TH 8
 __global__ void __launch_bounds__(256) k_gradients(const __grid_constant__ GradPtrs p)
 {
+    pdlWait();                                    // launched early (programmatic dependent launch): wait for the pyramid kernel
     const int lvl = blockIdx.y;
     const int w = p.w[lvl], h = p.h[lvl];
     const float* __restrict__ img = p.img[lvl];

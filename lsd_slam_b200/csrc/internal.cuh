@@ -18,6 +18,7 @@
 #include <string.h>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/lsdgpu.h"
@@ -166,6 +167,7 @@ struct lsdgpu_ctx {
     int optTrackTma = 1, optSingleSync = 0;
     bool optTrackDebug = false;
     int optTrackKmax = 3;
+    bool optPdl = true;                  // LSDGPU_PDL=0: plain stream-ordered launches of the dependent kernels
     int2* seqTable = nullptr;            // seqsum.cuh: per-run maps of the sequential fp32 sum, [SEQ_NBIN][runs]
     unsigned char* seqFlags = nullptr;
     int* seqCounts = nullptr;
@@ -210,6 +212,26 @@ struct CtxLock {
             return -1;                                                                                    \
         }                                                                                                 \
     } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched with LSD_PDL_LAUNCH may be scheduled while its predecessor in the stream
+// is still running; it must not touch the predecessor's output before pdlWait() returns (griddepcontrol.wait: all memory operations
+// of the predecessor grid are complete and visible).  With the wait as the kernel's first statement the stream semantics are
+// unchanged; what is saved is the launch latency between dependent kernels of a step.
+__device__ __forceinline__ void pdlWait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launchPDL(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 static inline int lsd_fail(lsdgpu_ctx* ctx, const char* msg)
 {

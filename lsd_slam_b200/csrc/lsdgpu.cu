@@ -360,7 +360,7 @@ static int buildFrameFromDeviceU8(lsdgpu_ctx* ctx, FrameSlot* s, const uint8_t* 
     for (int l = 0; l < LSD_LEVELS; l++) { gp.img[l] = s->image[l]; gp.grad[l] = s->grad[l]; gp.w[l] = w >> l; gp.h[l] = h >> l; }
     gp.maxgrad0 = s->maxgrad;
     // blockIdx.y = level; level 0 runs as 32x8 tiles, levels 1..4 linearly (their block counts are smaller than the tile count)
-    k_gradients<<<dim3(divUp(w, GR_TW) * divUp(h, GR_TH), LSD_LEVELS), 256, 0, ctx->stream>>>(gp);      // + maxGradients of level 0
+    LSD_CHECK(ctx, launchPDL(k_gradients, dim3(divUp(w, GR_TW) * divUp(h, GR_TH), LSD_LEVELS), dim3(256), 0, ctx->stream, ctx->optPdl, gp));      // + maxGradients of level 0
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     s->hasDepth = false; s->idepthPyrValid = false; s->hasGoodMask = false;
@@ -895,14 +895,14 @@ static int runFillRegularize(lsdgpu_ctx* ctx, int validityTH, const int* skip = 
     PyrPtrs id, var;
     for (int l = 0; l < LSD_LEVELS; l++) { id.l[l] = setDepthOn ? setDepthOn->idepth[l] : nullptr; var.l[l] = setDepthOn ? setDepthOn->idepthVar[l] : nullptr; }
     if (setDepthOn) {
-        k_fill_regularize<true><<<grid, FR_THREADS, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip, id, var,
-                                                                      ctx->dScalars + 8, ctx->evCounter + 48, setDepthOn->dStats);
+        LSD_CHECK(ctx, launchPDL(k_fill_regularize<true>, dim3(grid), dim3(FR_THREADS), 0, ctx->stream, ctx->optPdl, ctx->oth, ctx->cur, cam, G,
+                                 (const float*)kf->maxgrad, validityTH, skip, id, var, ctx->dScalars + 8, ctx->evCounter + 48, setDepthOn->dStats));
         setDepthOn->statsPending = true;
         setDepthOn->hasDepth = true; setDepthOn->idepthPyrValid = true;
         setDepthOn->depthHasBeenUpdatedFlag = true;                    // Frame.cpp:242
     } else
-        k_fill_regularize<false><<<grid, FR_THREADS, 0, ctx->stream>>>(ctx->oth, ctx->cur, cam, G, kf->maxgrad, validityTH, skip, id, var,
-                                                                       nullptr, nullptr, nullptr);
+        LSD_CHECK(ctx, launchPDL(k_fill_regularize<false>, dim3(grid), dim3(FR_THREADS), 0, ctx->stream, ctx->optPdl, ctx->oth, ctx->cur, cam, G,
+                                 (const float*)kf->maxgrad, validityTH, skip, id, var, (double*)nullptr, (unsigned int*)nullptr, (double*)nullptr));
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;
@@ -1039,7 +1039,8 @@ static int runObserve(lsdgpu_ctx* ctx, const int* ref_ids, int n_refs, bool devP
     DepthCam cam = depthCam(ctx);
     DepthGlobals G = depthGlobals(ctx);
     const int grid = divUp((cam.w - 6) * (cam.h - 6), OBS_PIX_PER_CTA);
-    k_observe<<<grid, OBS_THREADS, 0, ctx->stream>>>(ctx->cur, cam, G, kf->image[0], kf->grad[0], kf->maxgrad, ctx->hObs, devParams ? ctx->dObs : nullptr, skip);
+    LSD_CHECK(ctx, launchPDL(k_observe, dim3(grid), dim3(OBS_THREADS), 0, ctx->stream, ctx->optPdl, ctx->cur, cam, G, (const float*)kf->image[0],
+                             (const float4*)kf->grad[0], (const float*)kf->maxgrad, ctx->hObs, (const ObserveParams*)(devParams ? ctx->dObs : nullptr), skip));
     LAUNCH(ctx);
     LSD_CHECK(ctx, cudaGetLastError());
     return 0;

@@ -966,6 +966,7 @@ static void trackReadOptions(lsdgpu_ctx* ctx)
     ctx->optSingleSync = (e = getenv("LSDGPU_SINGLE_SYNC")) ? atoi(e) : 0;
     // candidate poses per pass (1 = one pose per pass, the round-1 behaviour; default TP_KMAX)
     ctx->optTrackKmax = (e = getenv("LSDGPU_TRACK_KMAX")) ? atoi(e) : TP_KMAX;
+    ctx->optPdl = (e = getenv("LSDGPU_PDL")) ? atoi(e) != 0 : true;
     if (ctx->optTrackKmax < 1) ctx->optTrackKmax = 1;
     if (ctx->optTrackKmax > TP_KMAX) ctx->optTrackKmax = TP_KMAX;
 }
