@@ -8,7 +8,7 @@
 //                                          taken directly; the integral image is never needed on the GPU)
 //   regularizeDepthMapRow<removeOcclusions>:758-848                        -> k_regularize<bool>
 //   propagateDepth                         :475-653                        -> k_prop_project + k_prop_resolve
-//   createKeyFrame rescale                 :1285-1304                      -> k_sum_idepth + k_rescale
+//   createKeyFrame rescale                 :1285-1304                      -> seqsum.cuh (the sequential fp32 sum) + k_rescale
 //   Frame::setDepth                        DataStructures/Frame.cpp:199-243 -> k_set_depth
 // The reference's memcpy(other <- current) + read other / write current (:713, :862) is a ping-pong here:
 // every kernel reads `src` and writes every pixel of `dst`.
@@ -966,7 +966,8 @@ __global__ void __launch_bounds__(256) k_set_depth_pyr(HypField cur, PyrPtrs id,
     finishSumCount(s, c, partials, counter, out);
 }
 
-// sum of idepth_smoothed over valid hypotheses (createKeyFrame :1286-1293)
+// sum of idepth_smoothed over valid hypotheses in double (not used by createKeyFrame any more: seqsum.cuh reproduces the
+// reference's sequential fp32 sum there; kept for diagnostics)
 __global__ void __launch_bounds__(256) k_sum_idepth(HypField cur, int n, double* __restrict__ partials, unsigned int* counter,
                                                     double* __restrict__ out)
 {

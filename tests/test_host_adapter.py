@@ -132,6 +132,32 @@ def test_host_classes_map_a_frame_tracked_on_the_previous_keyframe(tmp_path, seq
     assert np.allclose(rows[True][:, 1:8], np.array(poses), atol=1e-9), np.abs(rows[True][:, 1:8] - np.array(poses)).max()
 
 
+def test_host_classes_chain_the_absolute_poses_like_the_reference(tmp_path, oracle):
+    """FramePoseStruct::getCamToWorld (FramePoseStruct.cpp:84-105) and refToKf = kf.camToWorld^-1 * frame.camToWorld
+    (DepthMap.cpp:1099) of the C++ adapter against the oracle's Sim3 product / inverse -- host code only, no GPU"""
+    import ctypes as C
+    from lsd_slam_b200 import build
+    build.build()
+    build.build_host()
+    exe = tmp_path / "host_sim3_chain"
+    here = os.path.dirname(build.HOST_OUT)
+    r = subprocess.run(["g++", "-std=c++17", "-O2", "-o", str(exe), os.path.join(ROOT, "tests", "native", "host_sim3_chain.cpp"),
+                        "-L" + here, "-Wl,-rpath," + here, "-l:liblsdgpu_host.so", "-l:liblsdgpu.so"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    got, kf1, fr = (np.array([float(x) for x in ln.split()]) for ln in out.stdout.strip().splitlines())
+    dp = C.POINTER(C.c_double)
+
+    def call(fn, *args):
+        o = np.zeros(8)
+        arrs = [np.ascontiguousarray(a, np.float64) for a in args]
+        getattr(oracle.lib(), fn)(*[a.ctypes.data_as(dp) for a in arrs], o.ctypes.data_as(dp))
+        return o
+    want = call("lsdo_sim3d_mul", call("lsdo_sim3d_inverse", kf1), fr)
+    assert np.abs(got - want).max() <= 1e-14, got - want
+
+
 def test_undistorter_config_file_parsing(tmp_path, oracle):
     """lsd_slam::UndistorterPTAM(configFileName) of the C++ adapter (util/Undistorter.cpp:100-166) -- host-only, no GPU --
     against the oracle's tables for the same four lines"""
