@@ -29,7 +29,9 @@ extern "C" {
 #endif
 
 #define LSDGPU_LEVELS 5                 /* PYRAMID_LEVELS, util/settings.h:106 */
-#define LSDGPU_ABI_VERSION 1
+/* 2: additive over 1 -- lsdgpu_get_globals, lsdgpu_depth_update_keyframe_refs (lsdgpu_ref_desc), lsdgpu_seq_sum_f32,
+ *    lsdgpu_peer_export / _attach / _detach; contexts are thread-safe (per-context mutex).  No existing signature changed. */
+#define LSDGPU_ABI_VERSION 2
 
 typedef struct lsdgpu_ctx lsdgpu_ctx;
 

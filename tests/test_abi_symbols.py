@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported():
 def test_abi_version_and_struct_sizes():
     from lsd_slam_b200 import abi
     L = abi.load()
-    assert L.lsdgpu_abi_version() == 1
+    assert L.lsdgpu_abi_version() == 2
     assert ctypes.sizeof(abi.Hyp) == 32 and abi.HYP_DTYPE.itemsize == 32     # DepthMapPixelHypothesis.h:37-61
     s = abi.default_track_settings()
     assert list(s.maxItsPerLvl) == [5, 20, 50, 100, 0]                       # settings.h:368 + SlamSystem.cpp:80-81
